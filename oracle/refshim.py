@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE ONLY -- import the *unmodified* reference sampler file under stub modules.
+
+The reference hot path lives in ``<reference>/impls/utils/datasets.py``.  That file imports ``jax``,
+``jax.numpy`` and ``flax.core.frozen_dict`` (datasets.py:5-8), none of which is installed in this image.
+Everything the sampler does with them on the GC/HGC path is: ``jax.tree_util.tree_map`` / ``tree_leaves``
+over plain dicts, ``FrozenDict`` as an immutable mapping, and one jitted crop (datasets.py:17-33).  This
+module registers minimal stand-ins for those three things in ``sys.modules`` *before* executing the reference
+file, and afterwards swaps ``batched_random_crop`` for the numpy restatement in ``oracle.replay_oracle``
+(JAX is absent, so that single function cannot run as written).
+
+Used by ``tests/golden/make_golden.py`` (fixture generation, in the build container only) and by the
+live cross-check tests, which skip when the reference tree is not mounted.  Nothing in the product package
+imports this file, and nothing here is read at run time on the GPU box (``/root/reference`` does not exist
+there).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get('OGB_REFERENCE_ROOT', '/root/reference')
+_REF_FILE = os.path.join(REFERENCE_ROOT, 'impls', 'utils', 'datasets.py')
+
+
+def reference_available() -> bool:
+    return os.path.isfile(_REF_FILE)
+
+
+def _tree_map(fn, tree, *rest):
+    """dict-only stand-in for jax.tree_util.tree_map (sorted keys, like jax's dict flattening)."""
+    if isinstance(tree, dict):
+        return {k: _tree_map(fn, tree[k], *[r[k] for r in rest]) for k in sorted(tree)}
+    if hasattr(tree, '_dict') and isinstance(tree._dict, dict):
+        return _tree_map(fn, tree._dict, *rest)
+    return fn(tree, *rest)
+
+
+def _tree_leaves(tree):
+    if isinstance(tree, dict):
+        out = []
+        for k in sorted(tree):
+            out.extend(_tree_leaves(tree[k]))
+        return out
+    if hasattr(tree, '_dict') and isinstance(tree._dict, dict):
+        return _tree_leaves(tree._dict)
+    return [tree]
+
+
+class _FrozenDict:
+    """The slice of flax.core.FrozenDict the reference sampler touches."""
+
+    def __init__(self, *args, **kwargs):
+        src = dict(*args, **kwargs) if not (len(args) == 1 and isinstance(args[0], _FrozenDict)) else dict(args[0]._dict)
+        self._dict = src
+
+    def __getitem__(self, key):
+        return self._dict[key]
+
+    def __contains__(self, key):
+        return key in self._dict
+
+    def __iter__(self):
+        return iter(self._dict)
+
+    def __len__(self):
+        return len(self._dict)
+
+    def keys(self):
+        return self._dict.keys()
+
+    def values(self):
+        return self._dict.values()
+
+    def items(self):
+        return self._dict.items()
+
+    def copy(self, add_or_replace=None):
+        merged = dict(self._dict)
+        merged.update(add_or_replace or {})
+        return type(self)(merged)
+
+
+def _identity_decorator(fn=None, **_kwargs):
+    if fn is None:
+        return lambda f: f
+    return fn
+
+
+def _install_stubs():
+    if 'jax' in sys.modules and not getattr(sys.modules['jax'], '_ogb_stub', False):
+        raise RuntimeError('a real jax is importable; refshim is only meant for images without it')
+    jax = types.ModuleType('jax')
+    jax._ogb_stub = True
+    jax.tree_util = types.ModuleType('jax.tree_util')
+    jax.tree_util.tree_map = _tree_map
+    jax.tree_util.tree_leaves = _tree_leaves
+    jax.jit = _identity_decorator
+    jax.vmap = lambda fn, in_axes=None: fn
+    jax.lax = types.ModuleType('jax.lax')
+    jnp = types.ModuleType('jax.numpy')
+    jnp.pad = np.pad
+    jax.numpy = jnp
+    flax = types.ModuleType('flax')
+    flax_core = types.ModuleType('flax.core')
+    flax_fd = types.ModuleType('flax.core.frozen_dict')
+    flax_fd.FrozenDict = _FrozenDict
+    flax.core = flax_core
+    flax_core.frozen_dict = flax_fd
+    flax_core.FrozenDict = _FrozenDict
+    for name, mod in [
+        ('jax', jax),
+        ('jax.tree_util', jax.tree_util),
+        ('jax.lax', jax.lax),
+        ('jax.numpy', jnp),
+        ('flax', flax),
+        ('flax.core', flax_core),
+        ('flax.core.frozen_dict', flax_fd),
+    ]:
+        sys.modules.setdefault(name, mod)
+
+
+_CACHED = None
+
+
+def load_reference_datasets_module():
+    """Execute the reference's datasets.py (unmodified, read from its own location) and return the module."""
+    global _CACHED
+    if _CACHED is not None:
+        return _CACHED
+    if not reference_available():
+        raise FileNotFoundError(f'reference sampler not found at {_REF_FILE}')
+    _install_stubs()
+    spec = importlib.util.spec_from_file_location('ogb_reference_datasets', _REF_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules['ogb_reference_datasets'] = mod
+    spec.loader.exec_module(mod)
+
+    # datasets.py:17-33 needs jnp.pad + lax.dynamic_slice under jit/vmap; substitute the closed form.
+    from oracle.replay_oracle import shifted_edge_crop
+
+    def batched_random_crop(imgs, crop_froms, padding):
+        return shifted_edge_crop(np.asarray(imgs), np.asarray(crop_froms)[:, :2], padding)
+
+    mod.batched_random_crop = batched_random_crop
+    _CACHED = mod
+    return mod
+
+
+class DrawRecorder:
+    """Context manager that logs every np.random.{randint,geometric,rand} call the reference makes.
+
+    The log order is the validation-mode draw schema: one entry per numpy call,
+    holding the already-transformed values.
+    """
+
+    def __init__(self):
+        self.log = []
+        self._saved = {}
+
+    def __enter__(self):
+        for name in ('randint', 'geometric', 'rand'):
+            self._saved[name] = getattr(np.random, name)
+
+        def randint(*args, **kwargs):
+            out = self._saved['randint'](*args, **kwargs)
+            self.log.append(('randint', np.array(out, copy=True)))
+            return out
+
+        def geometric(*args, **kwargs):
+            out = self._saved['geometric'](*args, **kwargs)
+            self.log.append(('geometric', np.array(out, copy=True)))
+            return out
+
+        def rand(*args, **kwargs):
+            out = self._saved['rand'](*args, **kwargs)
+            self.log.append(('rand', np.array(out, copy=True)))
+            return out
+
+        np.random.randint, np.random.geometric, np.random.rand = randint, geometric, rand
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._saved.items():
+            setattr(np.random, name, fn)
+        return False

@@ -1,0 +1,175 @@
+"""Generate golden vectors by running the UNMODIFIED reference sampler (build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/<case>.npz
+
+Each fixture holds: the toy dataset fields, the sampler config (JSON), the call arguments, every np.random draw
+the reference made (in call order, already transformed) and every output key the reference returned.  The
+reference file ``/root/reference/impls/utils/datasets.py`` is executed from where it lies through
+``oracle/refshim.py``; nothing of it is copied.  ``/root/reference`` does not exist on the GPU box, which is why
+the vectors are committed.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+
+OUT_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def toy_fields(seed, lengths, obs_shape, act_dim, obs_dtype, compact=True, oracle_rep_dim=None, extra=False):
+    """Ragged-trajectory dataset in the layout ogbench.load_dataset produces (ogbench/utils.py:60-91)."""
+    rng = np.random.default_rng(seed)
+    n = int(np.sum(lengths))
+    if np.dtype(obs_dtype) == np.uint8:
+        obs = rng.integers(0, 256, size=(n, *obs_shape), dtype=np.uint8)
+    else:
+        obs = rng.standard_normal((n, *obs_shape)).astype(obs_dtype)
+    actions = rng.uniform(-1, 1, size=(n, act_dim)).astype(np.float32)
+    ends = np.cumsum(lengths) - 1
+    terminals = np.zeros(n, dtype=np.float32)
+    terminals[ends] = 1.0
+    fields = {}
+    if compact:
+        valids = 1.0 - terminals
+        shifted = np.concatenate([terminals[1:], [1.0]])
+        terminals = np.minimum(terminals + shifted, 1.0).astype(np.float32)
+        fields.update(observations=obs, actions=actions, terminals=terminals, valids=valids.astype(np.float32))
+    else:
+        # regular layout: explicit next_observations, one terminal per trajectory, no valids
+        nxt = np.concatenate([obs[1:], obs[-1:]], axis=0).copy()
+        fields.update(observations=obs, actions=actions, terminals=terminals, next_observations=nxt)
+    if oracle_rep_dim is not None:
+        fields['oracle_reps'] = rng.standard_normal((n, oracle_rep_dim)).astype(np.float32)
+    if extra:
+        fields['qpos'] = rng.standard_normal((n, 3))  # float64 extra field, gathered like any other (datasets.py:80)
+    return fields
+
+
+BASE_CFG = dict(
+    discount=0.99, value_p_curgoal=0.2, value_p_trajgoal=0.5, value_p_randomgoal=0.3, value_geom_sample=True,
+    actor_p_curgoal=0.0, actor_p_trajgoal=1.0, actor_p_randomgoal=0.0, actor_geom_sample=False,
+    gc_negative=True, p_aug=0.0, frame_stack=None,
+)
+
+
+def cfg(**over):
+    out = dict(BASE_CFG)
+    out.update(over)
+    return out
+
+
+def ragged(seed, n_traj, lo, hi):
+    return np.random.default_rng(seed).integers(lo, hi + 1, size=n_traj)
+
+
+def cases():
+    L = ragged(11, 9, 2, 60)
+    Lp = ragged(12, 5, 2, 9)
+    px = dict(obs_shape=(16, 16, 3), act_dim=5, obs_dtype=np.uint8)
+    st = dict(obs_shape=(5,), act_dim=2, obs_dtype=np.float32)
+    hiql = dict(subgoal_steps=5)
+    sharsa = dict(
+        value_geom_sample=False, actor_p_curgoal=0.0, actor_p_trajgoal=0.5, actor_p_randomgoal=0.5,
+        actor_geom_sample=True, gc_negative=False, discount=0.999, subgoal_steps=4,
+    )
+    yield dict(name='gc_state_gcivl', kind='gc', fields=toy_fields(1, L, **st), cfg=cfg(), B=64, seed=101)
+    yield dict(name='gc_state_regular', kind='gc', fields=toy_fields(2, L, compact=False, **st), cfg=cfg(), B=64, seed=102)
+    yield dict(name='gc_state_qrl', kind='gc', fields=toy_fields(3, L, **st),
+               cfg=cfg(value_p_curgoal=0.0, value_p_trajgoal=0.0, value_p_randomgoal=1.0, gc_negative=False), B=48, seed=103)
+    yield dict(name='gc_state_crl_noaugkey', kind='gc', fields=toy_fields(4, L, extra=True, **st),
+               cfg=cfg(value_p_curgoal=0.0, value_p_trajgoal=1.0, value_p_randomgoal=0.0, gc_negative=False, p_aug=None),
+               B=48, seed=104)
+    yield dict(name='gc_state_pcur1', kind='gc', fields=toy_fields(5, L, **st),
+               cfg=cfg(value_p_curgoal=1.0, value_p_trajgoal=0.0, value_p_randomgoal=0.0, actor_p_curgoal=0.1,
+                       actor_p_trajgoal=0.6, actor_p_randomgoal=0.3), B=32, seed=105)
+    yield dict(name='gc_state_given_idxs_eval', kind='gc', fields=toy_fields(6, L, **st), cfg=cfg(), B=7, seed=106,
+               idxs='valid_subset', evaluation=True)
+    yield dict(name='gc_state_oracle_reps', kind='gc', fields=toy_fields(7, L, oracle_rep_dim=3, **st), cfg=cfg(), B=40, seed=107)
+    yield dict(name='gc_state_batch1', kind='gc', fields=toy_fields(8, L, **st), cfg=cfg(), B=1, seed=108)
+    yield dict(name='hgc_state_hiql', kind='hgc', fields=toy_fields(9, L, **st), cfg=cfg(**hiql), B=64, seed=109)
+    yield dict(name='hgc_state_hiql_pos', kind='hgc', fields=toy_fields(10, L, **st), cfg=cfg(gc_negative=False, **hiql), B=64, seed=110)
+    yield dict(name='hgc_state_sharsa', kind='hgc', fields=toy_fields(11, L, **st), cfg=cfg(**sharsa), B=64, seed=111)
+    yield dict(name='hgc_state_lowdisc_steps', kind='hgc', fields=toy_fields(12, L, **st),
+               cfg=cfg(subgoal_steps=6, high_subgoal_steps=7, low_subgoal_steps=3, value_subgoal_steps=5,
+                       actor_subgoal_steps=4, low_discount=0.9), B=64, seed=112)
+    yield dict(name='hgc_state_oracle_reps', kind='hgc', fields=toy_fields(13, L, oracle_rep_dim=4, **st), cfg=cfg(**hiql), B=32, seed=113)
+    yield dict(name='gc_pixel_fs3_aug', kind='gc', fields=toy_fields(14, Lp, **px), cfg=cfg(frame_stack=3, p_aug=1.0), B=8, seed=114)
+    yield dict(name='gc_pixel_fs3_coinfail', kind='gc', fields=toy_fields(15, Lp, **px), cfg=cfg(frame_stack=3, p_aug=0.0), B=8, seed=115)
+    yield dict(name='gc_pixel_fs3_eval', kind='gc', fields=toy_fields(16, Lp, **px), cfg=cfg(frame_stack=3, p_aug=1.0), B=8, seed=116,
+               evaluation=True)
+    yield dict(name='gc_pixel_nostack_aug', kind='gc', fields=toy_fields(17, Lp, **px), cfg=cfg(p_aug=1.0), B=8, seed=117)
+    yield dict(name='gc_pixel_fs2_aug', kind='gc', fields=toy_fields(18, Lp, **px), cfg=cfg(frame_stack=2, p_aug=1.0), B=6, seed=118)
+    yield dict(name='gc_pixel_fs4_aug', kind='gc', fields=toy_fields(19, Lp, **px), cfg=cfg(frame_stack=4, p_aug=1.0), B=6, seed=119)
+    yield dict(name='hgc_pixel_fs3_aug', kind='hgc', fields=toy_fields(20, Lp, **px),
+               cfg=cfg(frame_stack=3, p_aug=1.0, subgoal_steps=3), B=6, seed=120)
+    yield dict(name='hgc_pixel_oraclereps_aug', kind='hgc', fields=toy_fields(21, Lp, oracle_rep_dim=3, **px),
+               cfg=cfg(frame_stack=3, p_aug=1.0, subgoal_steps=3), B=6, seed=121)
+    yield dict(name='gc_pixel64_fs3_aug', kind='gc',
+               fields=toy_fields(22, ragged(13, 3, 3, 8), obs_shape=(64, 64, 3), act_dim=5, obs_dtype=np.uint8),
+               cfg=cfg(frame_stack=3, p_aug=1.0), B=3, seed=122)
+    yield dict(name='gc_pixel_odd_shape_aug', kind='gc',
+               fields=toy_fields(23, Lp, obs_shape=(10, 12, 2), act_dim=2, obs_dtype=np.uint8),
+               cfg=cfg(frame_stack=3, p_aug=1.0), B=6, seed=123)
+
+
+def run_reference(case):
+    ref = refshim.load_reference_datasets_module()
+    fields = {k: v.copy() for k, v in case['fields'].items()}
+    cls = ref.GCDataset if case['kind'] == 'gc' else ref.HGCDataset
+    outs = []
+    logs = []
+    for preprocess in (True, False):
+        ds = ref.Dataset.create(**{k: v.copy() for k, v in fields.items()})
+        sampler = cls(ds, dict(case['cfg']), preprocess_frame_stack=preprocess)
+        idxs = None
+        if case.get('idxs') == 'valid_subset':
+            idxs = ds.valid_idxs[np.random.default_rng(case['seed']).integers(0, len(ds.valid_idxs), case['B'])]
+        np.random.seed(case['seed'])
+        with refshim.DrawRecorder() as rec:
+            out = sampler.sample(case['B'], idxs=idxs, evaluation=case.get('evaluation', False))
+        outs.append(out)
+        logs.append(rec.log)
+    # the pre-stacked and on-the-fly paths of the reference must agree (they do; asserted so it stays true)
+    assert outs[0].keys() == outs[1].keys()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]) and outs[0][k].dtype == outs[1][k].dtype, k
+    return outs[1], logs[1], idxs
+
+
+def main():
+    total = 0
+    for case in cases():
+        out, log, idxs = run_reference(case)
+        payload = {
+            'meta': np.array(json.dumps(dict(
+                name=case['name'], kind=case['kind'], cfg=case['cfg'], B=case['B'], seed=case['seed'],
+                evaluation=case.get('evaluation', False), n_draws=len(log), draw_kinds=[k for k, _ in log],
+                numpy=np.__version__,
+            ))),
+        }
+        for k, v in case['fields'].items():
+            payload['field/' + k] = v
+        if idxs is not None:
+            payload['idxs'] = idxs
+        for i, (_, v) in enumerate(log):
+            payload[f'draw/{i}'] = v
+        for k, v in out.items():
+            payload['out/' + k] = v
+        path = os.path.join(OUT_DIR, case['name'] + '.npz')
+        np.savez_compressed(path, **payload)
+        total += os.path.getsize(path)
+        print(f"{case['name']:32s} keys={len(out):2d} draws={len(log):2d} {os.path.getsize(path) / 1024:8.1f} KiB")
+    print(f'total {total / 1e6:.2f} MB')
+
+
+if __name__ == '__main__':
+    main()
