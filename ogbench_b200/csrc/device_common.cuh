@@ -1,0 +1,105 @@
+// Device-side building blocks shared by the sampler kernels: Philox counter RNG, the draw transforms, and the
+// bucket-accelerated / warp-cooperative searches over the trajectory boundary table.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ogb {
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  key = seed, counter = (row, batch_lo, batch_hi, purpose | stream<<8).
+// A draw is a pure function of (seed, stream, batch index, row, purpose): no RNG state lives in memory, any
+// kernel can regenerate any draw, and the sampler's whole RNG state is one 64-bit batch counter.
+// oracle/philox_np.py restates exactly this for the tests.
+// ---------------------------------------------------------------------------------------------------------
+enum Purpose : uint32_t {
+  PURPOSE_IDX = 0,      // .x,.y -> transition index position; .z -> crop cy; .w -> crop cx
+  PURPOSE_GOAL_A = 1,   // + 2*goal_set: .x,.y -> random-goal position; .z,.w -> geometric / uniform-distance U
+  PURPOSE_GOAL_B = 2,   // + 2*goal_set: .x,.y -> u_traj; .z,.w -> u_cur
+  PURPOSE_COIN = 7      // row = 0xFFFFFFFF: .x,.y -> the per-batch augmentation coin
+};
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(M0, c.x), hi1 = __umulhi(M1, c.z);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c.x) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c.z) >> 32);
+#endif
+    const uint32_t lo0 = M0 * c.x, lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+struct RngKey {
+  uint64_t seed;
+  uint32_t stream;
+};
+
+__device__ __forceinline__ uint4 draw4(const RngKey& key, uint64_t batch, uint32_t row, uint32_t purpose) {
+  const uint4 ctr = make_uint4(row, (uint32_t)batch, (uint32_t)(batch >> 32), purpose | (key.stream << 8));
+  return philox4x32_10(ctr, make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32)));
+}
+
+// uniform integer in [0, n): 64-bit multiply-shift, bias < n / 2^64
+__device__ __forceinline__ int64_t bounded_u64(uint32_t hi, uint32_t lo, uint64_t n) {
+  return (int64_t)__umul64hi(((uint64_t)hi << 32) | lo, n);
+}
+
+// uniform double in [0, 1) with 53 random bits, the same construction numpy's legacy rand() uses on two words
+__device__ __forceinline__ double unit_double(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// geometric(p) by inversion, support [1, inf): ceil(log(1-U) / log(1-p)); log_1mp = log(1-p) comes from the host
+__device__ __forceinline__ int64_t geometric_from_unit(double u, double log_1mp) {
+  const double x = ceil(log(1.0 - u) / log_1mp);
+  return x < 1.0 ? 1 : (int64_t)x;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Searches.  `table` is sorted int32.  bucket[b] = lower_bound(table, b << shift), so a key's answer lies in
+// [bucket[key>>shift], bucket[(key>>shift)+1]] -- for trajectory tables that range is 0-2 entries wide.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_bucketed(const int32_t* __restrict__ table, const int32_t* __restrict__ bucket,
+                                                    int shift, int key) {
+  const int b = key >> shift;
+  int lo = __ldg(bucket + b), hi = __ldg(bucket + b + 1);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(table + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Warp-cooperative searchsorted: all 32 lanes of a warp resolve ONE key with a 32-ary search (each round the
+// lanes probe 32 evenly spaced splitters and a ballot picks the sub-range), ~log32(n) dependent loads instead of
+// log2(n).  side_right == 0: first j with table[j] >= key (np.searchsorted side='left'); 1: first j with
+// table[j] > key.  Returns the same value in every lane.
+template <typename T>
+__device__ __forceinline__ int64_t warp_searchsorted(const T* __restrict__ table, int64_t n, T key, bool side_right) {
+  const unsigned lane = threadIdx.x & 31u;
+  int64_t lo = 0, hi = n;  // invariant: the answer lies in [lo, hi]
+  while (lo < hi) {
+    const int64_t step = (hi - lo + 31) / 32;         // lane l probes position lo + (l+1)*step - 1
+    const int64_t pos = lo + (int64_t)(lane + 1) * step - 1;
+    bool before = false;                              // "table[pos] sorts before the answer"; false beyond hi
+    if (pos < hi) {
+      const T v = table[pos];
+      before = side_right ? !(key < v) : (v < key);
+    }
+    // the predicate is monotone over lanes, so the ballot is a run of ones followed by zeros
+    const int n_before = __popc(__ballot_sync(0xffffffffu, before));
+    const int64_t cap = lo + (int64_t)(n_before + 1) * step - 1;
+    lo = lo + (int64_t)n_before * step;
+    hi = cap < hi ? cap : hi;                         // new span <= step - 1, so step == 1 ends the loop
+  }
+  return lo;
+}
+
+}  // namespace ogb

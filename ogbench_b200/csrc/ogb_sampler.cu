@@ -1,0 +1,1219 @@
+// libogbsampler.so -- host runtime + C-ABI (include/ogb_sampler.h) of the B200 replay sampler.
+//
+// Layering: ogb_dataset = the reference's Dataset (fields resident in HBM); ogb_sampler = GCDataset/HGCDataset
+// (trajectory tables, key plan, Philox stream); ogb_batch = the dict sample() returns (one device block, one
+// sub-array per key).  The kernels are in relabel_rows.cuh and gather_frames.cuh.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ogb_sampler.h"
+#include "gather_frames.cuh"
+#include "relabel_rows.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define OGB_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t err_ = (expr);                                                                           \
+    if (err_ != cudaSuccess) return fail(OGB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(err_), \
+                                         __FILE__, __LINE__);                                            \
+  } while (0)
+
+#define OGB_TRY(expr)        \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case OGB_U8: case OGB_I8: case OGB_BOOL: return 1;
+    case OGB_I16: case OGB_F16: case OGB_U16: return 2;
+    case OGB_I32: case OGB_F32: case OGB_U32: return 4;
+    case OGB_I64: case OGB_F64: case OGB_U64: return 8;
+    default: return 0;
+  }
+}
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int largest_vec_log2(size_t a, size_t b) {  // largest power of two <= 16 dividing both
+  int v = 4;
+  while (v > 0 && ((a % ((size_t)1 << v)) != 0 || (b % ((size_t)1 << v)) != 0)) --v;
+  return v;
+}
+
+bool positive_at(const void* data, int dtype, int64_t i) {
+  switch (dtype) {
+    case OGB_U8: case OGB_BOOL: return ((const uint8_t*)data)[i] > 0;
+    case OGB_I8: return ((const int8_t*)data)[i] > 0;
+    case OGB_I16: return ((const int16_t*)data)[i] > 0;
+    case OGB_U16: return ((const uint16_t*)data)[i] > 0;
+    case OGB_I32: return ((const int32_t*)data)[i] > 0;
+    case OGB_U32: return ((const uint32_t*)data)[i] > 0;
+    case OGB_I64: return ((const int64_t*)data)[i] > 0;
+    case OGB_U64: return ((const uint64_t*)data)[i] > 0;
+    case OGB_F32: return ((const float*)data)[i] > 0.0f;
+    case OGB_F64: return ((const double*)data)[i] > 0.0;
+    default: return false;
+  }
+}
+
+struct Field {
+  std::string name;
+  int dtype = 0;
+  int ndim = 0;
+  int64_t shape[OGB_MAX_NDIM] = {0};
+  size_t itemsize = 0;
+  size_t row_bytes = 0;
+  size_t stride = 0;
+  uint8_t* dptr = nullptr;
+};
+
+int shift_for(int64_t key_range, int64_t table_len) {
+  // bucket width ~ half the mean gap between table entries, bounded so the bucket table stays <= 2^17 entries
+  int shift = 4;
+  const int64_t mean_gap = table_len > 0 ? std::max<int64_t>(1, key_range / table_len) : key_range;
+  while (((int64_t)1 << (shift + 1)) < mean_gap / 2) ++shift;
+  while ((key_range >> shift) > (1 << 17)) ++shift;
+  return shift;
+}
+
+// bucket[b] = lower_bound(table, b << shift) for b in [0, (max_key >> shift) + 1]
+std::vector<int32_t> build_buckets(const std::vector<int32_t>& table, int64_t max_key, int shift) {
+  const int64_t nb = (max_key >> shift) + 2;
+  std::vector<int32_t> bucket((size_t)nb);
+  for (int64_t b = 0; b < nb; ++b) {
+    const int64_t key = b << shift;
+    bucket[(size_t)b] = (int32_t)(std::lower_bound(table.begin(), table.end(), key,
+                                                  [](int32_t v, int64_t k) { return (int64_t)v < k; }) - table.begin());
+  }
+  return bucket;
+}
+
+template <typename T>
+int upload_vector(const std::vector<T>& host, T** dptr, cudaStream_t stream = 0) {
+  *dptr = nullptr;
+  const size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+  OGB_CUDA(cudaMalloc((void**)dptr, bytes));
+  if (!host.empty()) OGB_CUDA(cudaMemcpy(*dptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+__global__ void repad_rows_kernel(const uint8_t* __restrict__ dense, uint8_t* __restrict__ padded, int64_t n_rows,
+                                  uint32_t row_bytes, uint32_t stride, int vec_log2) {
+  const uint32_t epr = row_bytes >> vec_log2;
+  const int64_t total = n_rows * epr;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / epr;
+    const uint32_t c = (uint32_t)(e - r * epr);
+    const uint8_t* s = dense + (size_t)e * ((size_t)1 << vec_log2);
+    uint8_t* d = padded + (size_t)r * stride + ((size_t)c << vec_log2);
+    switch (vec_log2) {
+      case 2: *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(s); break;
+      case 1: *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s); break;
+      default: *d = *s; break;
+    }
+  }
+}
+
+__global__ void searchsorted_warp_kernel(const int64_t* __restrict__ table, int64_t n, const int64_t* __restrict__ keys, int64_t m,
+                                         int side_right, int64_t* __restrict__ out) {
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < m; k += n_warps) {
+    const int64_t pos = ogb::warp_searchsorted<int64_t>(table, n, keys[k], side_right != 0);
+    if ((threadIdx.x & 31) == 0) out[k] = pos;
+  }
+}
+
+__global__ void philox_fill_kernel(ogb::RngKey key, uint64_t batch, uint32_t purpose, int64_t n, uint4* out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    out[r] = ogb::draw4(key, batch, (uint32_t)r, purpose);
+}
+
+enum Route { ROUTE_ROW = 0, ROUTE_FRAMES = 1, ROUTE_SCALAR = 2 };
+enum ScalarKind {
+  SC_MASKS = 0, SC_REWARDS, SC_HV_OFFSETS, SC_HV_STEPS, SC_HV_MASKS, SC_HV_REWARDS, SC_LV_STEPS, SC_LV_MASKS, SC_LV_REWARDS,
+  SC_COUNT
+};
+
+struct KeyPlan {
+  std::string name;
+  int route = ROUTE_ROW;
+  int field = -1;
+  int slot = 0;
+  int fs = 1;
+  bool crop = false;
+  int scalar = -1;
+  int dtype = 0;
+  int ndim_tail = 0;
+  int64_t tail[OGB_MAX_NDIM] = {0};
+  size_t row_bytes = 0;
+  int alias_of = -1;
+};
+
+struct DLDevice_ { int32_t device_type; int32_t device_id; };
+struct DLDataType_ { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor_ {
+  void* data; DLDevice_ device; int32_t ndim; DLDataType_ dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset;
+};
+struct DLManagedTensor_ {
+  DLTensor_ dl_tensor; void* manager_ctx; void (*deleter)(struct DLManagedTensor_*);
+};
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------------------
+struct ogb_dataset {
+  std::atomic<int> refs{1};
+  int device = 0;
+  int64_t size = 0;
+  std::vector<Field> fields;
+  int obs_field = -1, terminals_field = -1, valids_field = -1, next_obs_field = -1, oracle_field = -1;
+  // valid rows
+  int valid_mode = 0;  // 0 none, 1 table, 2 gaps
+  int64_t n_valid = -1;
+  int32_t* d_valid_table = nullptr;
+  int32_t* d_gap_c = nullptr;
+  int32_t* d_gap_bucket = nullptr;
+  int gap_shift = 0;
+  std::vector<uint8_t> terminals_host;  // terminals > 0, one byte per row (tiny next to the data)
+  size_t resident_bytes = 0;
+  int sm_count = 148;
+
+  int find(const char* name) const {
+    for (size_t i = 0; i < fields.size(); ++i)
+      if (fields[i].name == name) return (int)i;
+    return -1;
+  }
+};
+
+struct ogb_sampler {
+  std::atomic<int> refs{1};
+  ogb_dataset* ds = nullptr;
+  ogb_config cfg{};
+  int kind = 0;
+  uint64_t seed = 0;
+  uint32_t stream_id = 0;
+  uint64_t counter = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  bool debug = false;
+  // trajectory tables
+  std::vector<int32_t> term_host;
+  int32_t* d_term = nullptr;
+  int32_t* d_term_bucket = nullptr;
+  int term_shift = 0;
+  double* d_neg_lut = nullptr;
+  double* d_pow_lut = nullptr;
+  int n_slots = 0;
+  std::vector<KeyPlan> plan[2];  // [evaluation]
+  std::map<std::pair<int, int>, CUtensorMap> tmaps;  // (field, band_rows) -> descriptor
+  std::mutex mu;
+};
+
+struct ogb_batch {
+  std::atomic<int> refs{1};
+  ogb_sampler* sampler = nullptr;
+  uint8_t* block = nullptr;
+  size_t block_bytes = 0;
+  size_t keys_bytes = 0;
+  int64_t batch = 0, n_batches = 1, total_rows = 0;
+  std::vector<KeyPlan> keys;
+  std::vector<size_t> offsets;
+  std::vector<std::string> names;
+  int32_t* vec_rows = nullptr;
+  int32_t* vec_init = nullptr;
+  int8_t* crop = nullptr;
+  int n_slots = 0;
+  int launches = 0;
+  cudaEvent_t ready = nullptr;
+  std::vector<cudaStream_t> consumers;
+  std::mutex mu;
+};
+
+namespace {
+
+void dataset_unref(ogb_dataset* ds) {
+  if (ds->refs.fetch_sub(1) != 1) return;
+  cudaSetDevice(ds->device);
+  for (auto& f : ds->fields) if (f.dptr) cudaFree(f.dptr);
+  if (ds->d_valid_table) cudaFree(ds->d_valid_table);
+  if (ds->d_gap_c) cudaFree(ds->d_gap_c);
+  if (ds->d_gap_bucket) cudaFree(ds->d_gap_bucket);
+  delete ds;
+}
+
+void sampler_unref(ogb_sampler* s) {
+  if (s->refs.fetch_sub(1) != 1) return;
+  cudaSetDevice(s->ds->device);
+  if (s->owns_stream && s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  if (s->d_term) cudaFree(s->d_term);
+  if (s->d_term_bucket) cudaFree(s->d_term_bucket);
+  if (s->d_neg_lut) cudaFree(s->d_neg_lut);
+  if (s->d_pow_lut) cudaFree(s->d_pow_lut);
+  dataset_unref(s->ds);
+  delete s;
+}
+
+void batch_unref(ogb_batch* b) {
+  if (b->refs.fetch_sub(1) != 1) return;
+  ogb_sampler* s = b->sampler;
+  cudaSetDevice(s->ds->device);
+  // consumers that took the batch on another stream (DLPack protocol) may still be reading it: order the free
+  for (cudaStream_t c : b->consumers) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ev, c);
+      cudaStreamWaitEvent(s->stream, ev, 0);
+      cudaEventDestroy(ev);
+    }
+  }
+  if (b->block) cudaFreeAsync(b->block, s->stream);
+  if (b->ready) cudaEventDestroy(b->ready);
+  delete b;
+  sampler_unref(s);
+}
+
+// ------------------------------------------------ key plan ------------------------------------------------
+struct PlanBuilder {
+  const ogb_dataset* ds;
+  const ogb_config* cfg;
+  bool crop_possible;
+  int slot_canon[ogb::kMaxSlots];
+  std::vector<KeyPlan> keys;
+
+  int canonical(int slot) const { return slot_canon[slot]; }
+
+  void push(KeyPlan k) {
+    if (k.route != ROUTE_SCALAR && cfg->dedup_keys) {
+      for (size_t i = 0; i < keys.size(); ++i) {
+        const KeyPlan& o = keys[i];
+        if (o.route != ROUTE_SCALAR && o.alias_of < 0 && o.field == k.field && o.slot == k.slot && o.fs == k.fs &&
+            o.crop == k.crop) {
+          k.alias_of = (int)i;
+          break;
+        }
+      }
+    }
+    keys.push_back(std::move(k));
+  }
+
+  void alias(const char* name, const char* target) {
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (keys[i].name == target) {
+        KeyPlan k = keys[i];
+        k.name = name;
+        k.alias_of = keys[i].alias_of >= 0 ? keys[i].alias_of : (int)i;
+        keys.push_back(std::move(k));
+        return;
+      }
+  }
+
+  void field_key(const char* name, int field, int slot, bool in_aug, int fs = 1) {
+    const Field& f = ds->fields[field];
+    KeyPlan k;
+    k.name = name;
+    k.field = field;
+    k.slot = canonical(slot);
+    k.fs = fs;
+    k.dtype = f.dtype;
+    k.ndim_tail = f.ndim - 1;
+    for (int d = 1; d < f.ndim; ++d) k.tail[d - 1] = f.shape[d];
+    if (fs > 1) {
+      if (k.ndim_tail == 0) { k.ndim_tail = 1; k.tail[0] = 1; }  // never happens for real data
+      k.tail[k.ndim_tail - 1] *= fs;                               // np.concatenate(axis=-1)  datasets.py:366
+    }
+    k.row_bytes = f.row_bytes * fs;
+    k.crop = in_aug && crop_possible && (f.ndim == 4);             // len(arr.shape) == 4  datasets.py:337
+    k.route = (fs > 1 || k.crop) ? ROUTE_FRAMES : ROUTE_ROW;
+    push(std::move(k));
+  }
+  void obs_key(const char* name, int slot, bool in_aug) {
+    field_key(name, ds->obs_field, slot, in_aug, cfg->frame_stack > 0 ? cfg->frame_stack : 1);
+  }
+  void goal_key(const char* name, int slot, bool in_aug) {  // datasets.py:348-357
+    if (ds->oracle_field >= 0) field_key(name, ds->oracle_field, slot, in_aug);
+    else obs_key(name, slot, in_aug);
+  }
+  void scalar_key(const char* name, int sc, int dtype) {
+    KeyPlan k;
+    k.name = name;
+    k.route = ROUTE_SCALAR;
+    k.scalar = sc;
+    k.dtype = dtype;
+    k.ndim_tail = 0;
+    k.row_bytes = 8;
+    push(std::move(k));
+  }
+  void base_keys() {  // datasets.py:78-83 (+ :229-231)
+    for (size_t i = 0; i < ds->fields.size(); ++i) {
+      const std::string& nm = ds->fields[i].name;
+      if ((int)i == ds->obs_field) obs_key("observations", ogb::SLOT_IDX, true);
+      else field_key(nm.c_str(), (int)i, ogb::SLOT_IDX, nm == "next_observations");
+    }
+    if (ds->next_obs_field < 0) obs_key("next_observations", ogb::SLOT_NEXT, true);
+  }
+};
+
+std::vector<KeyPlan> build_plan(const ogb_sampler* s, bool evaluation) {
+  using namespace ogb;
+  PlanBuilder pb;
+  pb.ds = s->ds;
+  pb.cfg = &s->cfg;
+  pb.crop_possible = s->cfg.has_p_aug && !evaluation && s->cfg.p_aug > 0.0 && s->kind != OGB_KIND_PLAIN;
+  for (int v = 0; v < kMaxSlots; ++v) pb.slot_canon[v] = v;
+  if (s->kind == OGB_KIND_HGC && s->cfg.dedup_keys) {
+    if (s->cfg.low_subgoal_steps == s->cfg.value_subgoal_steps) pb.slot_canon[HGC_LV_NEXT] = HGC_HV_NEXT;
+    if (s->cfg.low_subgoal_steps == s->cfg.actor_subgoal_steps) pb.slot_canon[HGC_LA_NEXT] = HGC_HA_NEXT;
+  }
+  pb.base_keys();
+  if (s->kind == OGB_KIND_GC) {                     // datasets.py:248-252, aug list :280
+    pb.goal_key("value_goals", GC_VALUE_GOAL, true);
+    pb.goal_key("actor_goals", GC_ACTOR_GOAL, true);
+    pb.scalar_key("masks", SC_MASKS, OGB_F64);
+    pb.scalar_key("rewards", SC_REWARDS, OGB_F64);
+  } else if (s->kind == OGB_KIND_HGC) {             // datasets.py:526-619, aug list :625-640
+    pb.obs_key("high_value_reps", SLOT_IDX, false);
+    pb.goal_key("high_value_goals", HGC_HV_GOAL, true);
+    pb.goal_key("high_value_actions", HGC_HV_NEXT, true);
+    pb.obs_key("high_value_next_observations", HGC_HV_NEXT, true);
+    pb.scalar_key("high_value_offsets", SC_HV_OFFSETS, OGB_I64);
+    pb.scalar_key("high_value_subgoal_steps", SC_HV_STEPS, OGB_I64);
+    pb.scalar_key("high_value_masks", SC_HV_MASKS, OGB_F64);
+    pb.scalar_key("high_value_rewards", SC_HV_REWARDS, OGB_F64);
+    pb.obs_key("low_value_next_observations", HGC_LV_NEXT, true);
+    pb.scalar_key("low_value_subgoal_steps", SC_LV_STEPS, OGB_I64);
+    pb.scalar_key("low_value_masks", SC_LV_MASKS, OGB_F64);
+    pb.scalar_key("low_value_rewards", SC_LV_REWARDS, OGB_F64);
+    if (s->cfg.has_low_discount) pb.goal_key("low_value_goals", HGC_LV_GOAL, false);
+    pb.alias("value_goals", "high_value_goals");
+    pb.scalar_key("masks", SC_MASKS, OGB_F64);
+    pb.scalar_key("rewards", SC_REWARDS, OGB_F64);
+    pb.goal_key("high_actor_goals", HGC_HA_GOAL, true);
+    pb.goal_key("high_actor_actions", HGC_HA_NEXT, true);
+    pb.obs_key("high_actor_next_observations", HGC_HA_NEXT, true);
+    pb.alias("high_actor_targets", "high_actor_actions");
+    pb.goal_key("low_actor_goals", HGC_LA_GOAL, true);
+    pb.obs_key("low_actor_goal_observations", HGC_LA_GOAL, true);
+    pb.obs_key("low_actor_next_observations", HGC_LA_NEXT, true);
+  }
+  return pb.keys;
+}
+
+// ------------------------------------------------ TMA descriptors ------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    OGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || fn == nullptr) return fail(OGB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    cached = (EncodeTiledFn)fn;
+  }
+  *out = cached;
+  return 0;
+}
+
+bool tma_eligible(const Field& f, const ogb_config& cfg, int fs) {
+  if (f.dtype != OGB_U8 || f.ndim != 4 || f.shape[3] != 3) return false;
+  const int64_t H = f.shape[1], W = f.shape[2];
+  if (W % ogb::kGroupPx != 0 || W * 3 > 256 || H < 8) return false;
+  if (fs < 1 || fs > 4 || cfg.crop_padding > 4) return false;
+  if (f.stride != f.row_bytes || (f.row_bytes % 16) != 0) return false;
+  return true;
+}
+
+int band_rows_for(int64_t H, int pad) {
+  for (int rb = 32; rb > pad; --rb)
+    if (H % rb == 0) return rb;
+  return 0;
+}
+
+int get_tmap(ogb_sampler* s, int field, int band_rows, CUtensorMap* out) {
+  auto it = s->tmaps.find({field, band_rows});
+  if (it != s->tmaps.end()) { *out = it->second; return 0; }
+  EncodeTiledFn encode;
+  OGB_TRY(get_encode_fn(&encode));
+  const Field& f = s->ds->fields[field];
+  const cuuint64_t H = (cuuint64_t)f.shape[1], rowb = (cuuint64_t)f.shape[2] * 3;
+  cuuint64_t gdim[3] = {rowb, H, (cuuint64_t)s->ds->size};
+  cuuint64_t gstr[2] = {rowb, (cuuint64_t)f.stride};
+  cuuint32_t box[3] = {(cuuint32_t)rowb, (cuuint32_t)band_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, f.dptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(OGB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  s->tmaps[{field, band_rows}] = tm;
+  *out = tm;
+  return 0;
+}
+
+template <int FS>
+int launch_frames_tma(const CUtensorMap& tm, const ogb::FramesParams& fp, int64_t n_items, size_t smem, cudaStream_t st) {
+  OGB_CUDA(cudaFuncSetAttribute(ogb::gather_frames_tma_kernel<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ogb::gather_frames_tma_kernel<FS><<<(unsigned)n_items, ogb::kFramesThreads, smem, st>>>(tm, fp);
+  OGB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+const char* ogb_last_error(void) { return g_error.c_str(); }
+int ogb_abi_version(void) { return OGB_ABI_VERSION; }
+
+int ogb_device_count(int* out) {
+  if (!out) return fail(OGB_ERR_INVALID, "null out");
+  OGB_CUDA(cudaGetDeviceCount(out));
+  return 0;
+}
+
+int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out) {
+  if (!fields || n_fields <= 0 || !out) return fail(OGB_ERR_INVALID, "ogb_dataset_create: bad arguments");
+  OGB_CUDA(cudaSetDevice(device));
+  ogb_dataset* ds = new ogb_dataset();
+  ds->device = device;
+  cudaDeviceGetAttribute(&ds->sm_count, cudaDevAttrMultiProcessorCount, device);
+  {  // keep freed batch blocks cached in the stream-ordered pool
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thresh = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+  }
+  int rc = 0;
+  auto bail = [&](int code) { dataset_unref(ds); return code; };
+  int64_t size = 0;
+  for (int i = 0; i < n_fields; ++i) {
+    const ogb_field& in = fields[i];
+    if (!in.name || !in.data || in.ndim < 1 || in.ndim > OGB_MAX_NDIM || dtype_size(in.dtype) == 0)
+      return bail(fail(OGB_ERR_INVALID, "field %d: bad descriptor", i));
+    size = std::max<int64_t>(size, in.shape[0]);  // get_size: the longest leaf (datasets.py:11-14)
+  }
+  for (int i = 0; i < n_fields; ++i)
+    if (fields[i].shape[0] != size)
+      return bail(fail(OGB_ERR_INVALID, "field '%s' has %lld rows, dataset size is %lld", fields[i].name,
+                       (long long)fields[i].shape[0], (long long)size));
+  if (size < 1 || size > (int64_t)2147483000) return bail(fail(OGB_ERR_UNSUPPORTED, "dataset size %lld out of range", (long long)size));
+  ds->size = size;
+
+  for (int i = 0; i < n_fields; ++i) {
+    const ogb_field& in = fields[i];
+    Field f;
+    f.name = in.name;
+    f.dtype = in.dtype;
+    f.ndim = in.ndim;
+    f.itemsize = dtype_size(in.dtype);
+    size_t row = f.itemsize;
+    for (int d = 0; d < in.ndim; ++d) {
+      f.shape[d] = in.shape[d];
+      if (d > 0) row *= (size_t)in.shape[d];
+    }
+    f.row_bytes = row;
+    if (row == 0) return bail(fail(OGB_ERR_INVALID, "field '%s' has empty rows", in.name));
+    // resident row stride: rows <= 32 B stay dense, longer rows start on a 32-byte sector boundary
+    f.stride = row <= 32 ? row : round_up(row, 32);
+    if (f.stride > 0xFFFFFFFFull) return bail(fail(OGB_ERR_UNSUPPORTED, "field '%s': row too large", in.name));
+    const size_t dense_bytes = (size_t)size * row, padded_bytes = (size_t)size * f.stride;
+    cudaError_t e = cudaMalloc((void**)&f.dptr, padded_bytes);
+    if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for field '%s': %s", padded_bytes, in.name, cudaGetErrorString(e)));
+    ds->fields.push_back(f);
+    ds->resident_bytes += padded_bytes;
+    const cudaMemcpyKind kind = in.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (f.stride == row) {
+      e = cudaMemcpy(f.dptr, in.data, dense_bytes, kind);
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "upload of field '%s': %s", in.name, cudaGetErrorString(e)));
+    } else {
+      const uint8_t* dense = (const uint8_t*)in.data;
+      uint8_t* staging = nullptr;
+      if (!in.on_device) {
+        e = cudaMalloc((void**)&staging, dense_bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(staging, in.data, dense_bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { if (staging) cudaFree(staging); return bail(fail(OGB_ERR_CUDA, "staging of field '%s': %s", in.name, cudaGetErrorString(e))); }
+        dense = staging;
+      }
+      cudaMemset(f.dptr, 0, padded_bytes);
+      const int v = std::min(2, largest_vec_log2(row, 16));
+      repad_rows_kernel<<<ds->sm_count * 8, 256>>>(dense, f.dptr, size, (uint32_t)row, (uint32_t)f.stride, v);
+      e = cudaDeviceSynchronize();
+      if (staging) cudaFree(staging);
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "repad of field '%s': %s", in.name, cudaGetErrorString(e)));
+    }
+  }
+  ds->obs_field = ds->find("observations");
+  ds->terminals_field = ds->find("terminals");
+  ds->valids_field = ds->find("valids");
+  ds->next_obs_field = ds->find("next_observations");
+  ds->oracle_field = ds->find("oracle_reps");
+  if (ds->obs_field < 0) return bail(fail(OGB_ERR_ASSERT, "assert 'observations' in data (datasets.py:54)"));
+
+  auto host_copy_1d = [&](int fi, std::vector<uint8_t>* flags) -> int {
+    const Field& f = ds->fields[fi];
+    std::vector<uint8_t> raw((size_t)size * f.row_bytes);
+    if (f.stride != f.row_bytes) return fail(OGB_ERR_UNSUPPORTED, "field '%s' must be one value per row", f.name.c_str());
+    OGB_CUDA(cudaMemcpy(raw.data(), f.dptr, raw.size(), cudaMemcpyDeviceToHost));
+    if (f.row_bytes != f.itemsize) return fail(OGB_ERR_UNSUPPORTED, "field '%s' must be one value per row", f.name.c_str());
+    flags->resize((size_t)size);
+    for (int64_t r = 0; r < size; ++r) (*flags)[(size_t)r] = positive_at(raw.data(), f.dtype, r) ? 1 : 0;
+    return 0;
+  };
+  if (ds->terminals_field >= 0) {
+    rc = host_copy_1d(ds->terminals_field, &ds->terminals_host);
+    if (rc) return bail(rc);
+  }
+  if (ds->valids_field >= 0) {  // Dataset.__init__: valid_idxs = nonzero(valids > 0)  (datasets.py:62-63)
+    std::vector<uint8_t> valid;
+    rc = host_copy_1d(ds->valids_field, &valid);
+    if (rc) return bail(rc);
+    std::vector<int32_t> table, gaps;
+    for (int64_t r = 0; r < size; ++r) {
+      if (valid[(size_t)r]) table.push_back((int32_t)r);
+      else gaps.push_back((int32_t)(r - (int64_t)gaps.size()));  // c[m] = (m-th invalid row) - m
+    }
+    ds->n_valid = (int64_t)table.size();
+    if (ds->n_valid == 0) return bail(fail(OGB_ERR_INVALID, "dataset has no valid rows"));
+    if ((int64_t)gaps.size() * 8 <= size) {
+      ds->valid_mode = 2;
+      ds->gap_shift = shift_for(ds->n_valid + 1, (int64_t)gaps.size());
+      std::vector<int32_t> bucket = build_buckets(gaps, ds->n_valid + 1, ds->gap_shift);
+      rc = upload_vector(gaps, &ds->d_gap_c);
+      if (!rc) rc = upload_vector(bucket, &ds->d_gap_bucket);
+      ds->resident_bytes += (gaps.size() + bucket.size()) * 4;
+    } else {
+      ds->valid_mode = 1;
+      rc = upload_vector(table, &ds->d_valid_table);
+      ds->resident_bytes += table.size() * 4;
+    }
+    if (rc) return bail(rc);
+  }
+  *out = ds;
+  return 0;
+}
+
+int ogb_dataset_size(const ogb_dataset* ds, int64_t* out) {
+  if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = ds->size;
+  return 0;
+}
+int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out) {
+  if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = ds->n_valid;
+  return 0;
+}
+int ogb_dataset_resident_bytes(const ogb_dataset* ds, size_t* out) {
+  if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = ds->resident_bytes;
+  return 0;
+}
+int ogb_dataset_destroy(ogb_dataset* ds) {
+  if (!ds) return fail(OGB_ERR_INVALID, "null dataset");
+  dataset_unref(ds);
+  return 0;
+}
+
+int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uint64_t seed, uint32_t stream_id, ogb_sampler** out) {
+  if (!ds || !cfg || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_create: null argument");
+  if (kind < OGB_KIND_GC || kind > OGB_KIND_PLAIN) return fail(OGB_ERR_INVALID, "unknown sampler kind %d", kind);
+  if (stream_id >= (1u << 24)) return fail(OGB_ERR_INVALID, "stream_id must be < 2^24");
+  OGB_CUDA(cudaSetDevice(ds->device));
+  if (kind != OGB_KIND_PLAIN) {
+    if (ds->terminals_field < 0) return fail(OGB_ERR_INVALID, "KeyError: 'terminals'");
+    auto close1 = [](double x) { return std::fabs(x - 1.0) <= 1e-8 + 1e-5; };  // np.isclose(x, 1.0)
+    if (!close1(cfg->value_p_curgoal + cfg->value_p_trajgoal + cfg->value_p_randomgoal))
+      return fail(OGB_ERR_ASSERT, "value_p_* do not sum to 1 (datasets.py:191-193)");
+    if (!close1(cfg->actor_p_curgoal + cfg->actor_p_trajgoal + cfg->actor_p_randomgoal))
+      return fail(OGB_ERR_ASSERT, "actor_p_* do not sum to 1 (datasets.py:194-196)");
+    if (cfg->frame_stack > 0 && ds->next_obs_field >= 0)
+      return fail(OGB_ERR_ASSERT, "frame_stack needs a compact dataset: 'next_observations' present (datasets.py:208)");
+    if (cfg->frame_stack < 0 || cfg->frame_stack > 64) return fail(OGB_ERR_INVALID, "frame_stack out of range");
+    if (!(cfg->discount > 0.0 && cfg->discount < 1.0)) return fail(OGB_ERR_INVALID, "discount must be in (0, 1)");
+    if (cfg->has_low_discount && !(cfg->low_discount > 0.0 && cfg->low_discount < 1.0))
+      return fail(OGB_ERR_INVALID, "low_discount must be in (0, 1)");
+    if (kind == OGB_KIND_HGC) {
+      const int kmax = std::max({cfg->value_subgoal_steps, cfg->actor_subgoal_steps, cfg->low_subgoal_steps});
+      if (cfg->value_subgoal_steps < 0 || cfg->actor_subgoal_steps < 0 || cfg->low_subgoal_steps < 0)
+        return fail(OGB_ERR_INVALID, "subgoal steps must be >= 0");
+      if (!cfg->neg_reward_lut || !cfg->pow_lut || cfg->lut_len < kmax + 1)
+        return fail(OGB_ERR_INVALID, "reward tables must cover steps 0..%d", kmax);
+    }
+  }
+  ogb_sampler* s = new ogb_sampler();
+  s->ds = ds;
+  ds->refs.fetch_add(1);
+  s->cfg = *cfg;
+  s->cfg.neg_reward_lut = nullptr;
+  s->cfg.pow_lut = nullptr;
+  s->kind = kind;
+  s->seed = seed;
+  s->stream_id = stream_id;
+  auto bail = [&](int code) { sampler_unref(s); return code; };
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "cudaStreamCreate failed"));
+
+  if (kind != OGB_KIND_PLAIN) {
+    // terminal_locs = nonzero(terminals > 0)  (datasets.py:186)
+    for (int64_t r = 0; r < ds->size; ++r)
+      if (ds->terminals_host[(size_t)r]) s->term_host.push_back((int32_t)r);
+    if (s->term_host.empty() || s->term_host.back() != ds->size - 1)
+      return bail(fail(OGB_ERR_ASSERT, "assert terminal_locs[-1] == size - 1 (datasets.py:188)"));
+    s->term_shift = shift_for(ds->size, (int64_t)s->term_host.size());
+    std::vector<int32_t> bucket = build_buckets(s->term_host, ds->size, s->term_shift);
+    int rc = upload_vector(s->term_host, &s->d_term);
+    if (!rc) rc = upload_vector(bucket, &s->d_term_bucket);
+    if (rc) return bail(rc);
+    if (kind == OGB_KIND_HGC) {
+      std::vector<double> neg(cfg->neg_reward_lut, cfg->neg_reward_lut + cfg->lut_len), pw(cfg->pow_lut, cfg->pow_lut + cfg->lut_len);
+      rc = upload_vector(neg, &s->d_neg_lut);
+      if (!rc) rc = upload_vector(pw, &s->d_pow_lut);
+      if (rc) return bail(rc);
+    }
+  }
+  s->n_slots = kind == OGB_KIND_GC ? ogb::GC_NUM_SLOTS : (kind == OGB_KIND_HGC ? ogb::HGC_NUM_SLOTS : 2);
+  s->plan[0] = build_plan(s, false);
+  s->plan[1] = build_plan(s, true);
+  *out = s;
+  return 0;
+}
+
+int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (s->owns_stream && s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  s->stream = (cudaStream_t)cuda_stream;
+  s->owns_stream = false;
+  return 0;
+}
+int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  s->debug = keep != 0;
+  return 0;
+}
+int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = (int64_t)s->term_host.size();
+  return 0;
+}
+int ogb_sampler_copy_bounds(const ogb_sampler* s, int64_t* terminal_locs, int64_t* initial_locs) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  for (size_t i = 0; i < s->term_host.size(); ++i) {
+    if (terminal_locs) terminal_locs[i] = s->term_host[i];
+    if (initial_locs) initial_locs[i] = i == 0 ? 0 : (int64_t)s->term_host[i - 1] + 1;  // datasets.py:187
+  }
+  return 0;
+}
+int ogb_sampler_get_counter(const ogb_sampler* s, uint64_t* out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = s->counter;
+  return 0;
+}
+int ogb_sampler_set_counter(ogb_sampler* s, uint64_t counter) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  s->counter = counter;
+  return 0;
+}
+int ogb_sampler_destroy(ogb_sampler* s) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  sampler_unref(s);
+  return 0;
+}
+
+int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
+                       const ogb_draws* draws, ogb_batch** out) {
+  using namespace ogb;
+  if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
+  if (batch_size < 1 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size and n_batches must be >= 1");
+  if ((draws || idxs) && n_batches != 1) return fail(OGB_ERR_INVALID, "validation draws / explicit idxs need n_batches == 1");
+  const ogb_dataset* ds = s->ds;
+  const ogb_config& cfg = s->cfg;
+  const int64_t total = batch_size * (int64_t)n_batches;
+  if (total > (int64_t)1 << 31) return fail(OGB_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
+  const bool stacked_next = cfg.frame_stack > 0 && s->kind != OGB_KIND_PLAIN;
+  if (idxs) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
+    for (int64_t r = 0; r < batch_size; ++r)
+      if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + 1 >= ds->size))
+        return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
+  }
+  const int64_t n_choices = ds->valid_mode == 0 ? ds->size : ds->n_valid;
+  const bool aug_mode = cfg.has_p_aug && !evaluation && s->kind != OGB_KIND_PLAIN;
+  const int n_goal_sets = s->kind == OGB_KIND_PLAIN ? 0 : 3;
+  const bool geom[3] = {cfg.value_geom_sample != 0, true, cfg.actor_geom_sample != 0};
+  const bool cur_only[3] = {cfg.value_p_curgoal == 1.0, cfg.value_p_curgoal == 1.0, cfg.actor_p_curgoal == 1.0};
+  const bool goal_used[3] = {true, s->kind == OGB_KIND_HGC && cfg.has_low_discount, true};
+  if (draws) {
+    if (!idxs && !draws->idx_pos) return fail(OGB_ERR_INVALID, "validation mode needs idx_pos or idxs");
+    for (int gs = 0; gs < n_goal_sets; ++gs) {
+      if (!goal_used[gs]) continue;
+      const ogb_goal_draws& d = draws->goals[gs];
+      if (!d.rand_pos || (geom[gs] ? !d.offset : !d.dist) || (!cur_only[gs] && (!d.u_traj || !d.u_cur)))
+        return fail(OGB_ERR_INVALID, "validation mode: goal set %d is missing draws", gs);
+      for (int64_t r = 0; r < batch_size; ++r)
+        if (d.rand_pos[r] < 0 || d.rand_pos[r] >= n_choices) return fail(OGB_ERR_INDEX, "rand_pos out of range");
+    }
+    if (draws->idx_pos && !idxs)
+      for (int64_t r = 0; r < batch_size; ++r)
+        if (draws->idx_pos[r] < 0 || draws->idx_pos[r] >= n_choices) return fail(OGB_ERR_INDEX, "idx_pos out of range");
+    if (aug_mode && !draws->has_aug_coin) return fail(OGB_ERR_INVALID, "validation mode: the augmentation coin is missing");
+    if (aug_mode && draws->aug_coin < cfg.p_aug && !draws->crop) return fail(OGB_ERR_INVALID, "validation mode: crop draws are missing");
+  }
+  OGB_CUDA(cudaSetDevice(ds->device));
+  std::lock_guard<std::mutex> lock(s->mu);
+
+  const std::vector<KeyPlan>& plan = s->plan[evaluation ? 1 : 0];
+  bool any_frames = false;
+  for (const KeyPlan& k : plan) any_frames |= (k.route == ROUTE_FRAMES && k.alias_of < 0);
+  const bool want_vecs = any_frames || s->debug;
+  const bool want_init = any_frames && cfg.frame_stack > 1;
+
+  // ---- lay out the single device block: keys first (so one D2H copy takes the whole batch), then scratch ----
+  ogb_batch* b = new ogb_batch();
+  b->sampler = s;
+  s->refs.fetch_add(1);
+  b->batch = batch_size;
+  b->n_batches = n_batches;
+  b->total_rows = total;
+  b->keys = plan;
+  b->offsets.assign(plan.size(), 0);
+  b->n_slots = s->n_slots;
+  size_t cursor = 0;
+  for (size_t i = 0; i < plan.size(); ++i) {
+    if (plan[i].alias_of >= 0) continue;
+    b->offsets[i] = cursor;
+    cursor = round_up(cursor + (size_t)total * plan[i].row_bytes, 256);
+  }
+  for (size_t i = 0; i < plan.size(); ++i)
+    if (plan[i].alias_of >= 0) b->offsets[i] = b->offsets[(size_t)plan[i].alias_of];
+  b->keys_bytes = cursor;
+  auto carve = [&](size_t bytes) { size_t off = cursor; cursor = round_up(cursor + bytes, 256); return off; };
+  size_t off_rows = 0, off_init = 0, off_crop = 0, off_idxs = 0, off_draw_i64[1 + 3 * 2 + 1] = {0}, off_draw_f64[3 * 3] = {0};
+  if (want_vecs) off_rows = carve((size_t)s->n_slots * total * 4);
+  if (want_init) off_init = carve((size_t)s->n_slots * total * 4);
+  if (want_vecs) off_crop = carve((size_t)total * 2);
+  if (idxs) off_idxs = carve((size_t)batch_size * 8);
+  if (draws) {
+    off_draw_i64[0] = carve((size_t)batch_size * 8);
+    for (int gs = 0; gs < 3; ++gs) {
+      off_draw_i64[1 + 2 * gs] = carve((size_t)batch_size * 8);
+      off_draw_i64[2 + 2 * gs] = carve((size_t)batch_size * 8);
+      for (int q = 0; q < 3; ++q) off_draw_f64[3 * gs + q] = carve((size_t)batch_size * 8);
+    }
+    off_draw_i64[7] = carve((size_t)batch_size * 16);
+  }
+  b->block_bytes = std::max<size_t>(cursor, 256);
+  auto bail = [&](int code) { batch_unref(b); return code; };
+  {
+    cudaError_t e = cudaMallocAsync((void**)&b->block, b->block_bytes, s->stream);
+    if (e != cudaSuccess) { b->block = nullptr; return bail(fail(OGB_ERR_CUDA, "cudaMallocAsync(%zu): %s", b->block_bytes, cudaGetErrorString(e))); }
+  }
+  uint8_t* base = b->block;
+  if (want_vecs) { b->vec_rows = (int32_t*)(base + off_rows); b->crop = (int8_t*)(base + off_crop); }
+  if (want_init) b->vec_init = (int32_t*)(base + off_init);
+
+  // ---- parameters of the fused index + row-gather kernel ----
+  RelabelParams p;
+  memset(&p, 0, sizeof(p));
+  p.term = s->d_term;
+  p.term_bucket = s->d_term_bucket;
+  p.term_shift = s->term_shift;
+  p.valid_table = ds->d_valid_table;
+  p.gap_c = ds->d_gap_c;
+  p.gap_bucket = ds->d_gap_bucket;
+  p.gap_shift = ds->gap_shift;
+  p.valid_mode = ds->valid_mode;
+  p.n_choices = n_choices;
+  p.n_rows_ds = (int32_t)ds->size;
+  const double p_cur[3] = {cfg.value_p_curgoal, cfg.value_p_curgoal, cfg.actor_p_curgoal};
+  const double p_traj[3] = {cfg.value_p_trajgoal, cfg.value_p_trajgoal, cfg.actor_p_trajgoal};
+  const double disc[3] = {cfg.discount, cfg.has_low_discount ? cfg.low_discount : cfg.discount, cfg.discount};
+  for (int gs = 0; gs < 3; ++gs) {
+    p.goal[gs].geom = geom[gs];
+    p.goal[gs].cur_only = cur_only[gs];
+    p.goal[gs].p_cur = p_cur[gs];
+    p.goal[gs].thr_traj = cur_only[gs] ? 0.0 : p_traj[gs] / (1.0 - p_cur[gs]);
+    p.goal[gs].log_1mp = std::log(1.0 - (1.0 - disc[gs]));
+  }
+  p.neg_lut = s->d_neg_lut;
+  p.pow_lut = s->d_pow_lut;
+  p.kind = s->kind;
+  p.has_low_goal = goal_used[1];
+  p.k_val = cfg.value_subgoal_steps;
+  p.k_act = cfg.actor_subgoal_steps;
+  p.k_lo = cfg.low_subgoal_steps;
+  p.gc_negative = cfg.gc_negative;
+  p.stacked_next = stacked_next;
+  p.aug_mode = aug_mode;
+  p.crop_pad = cfg.crop_padding;
+  p.p_aug = cfg.p_aug;
+  p.key.seed = s->seed;
+  p.key.stream = s->stream_id;
+  p.batch0 = s->counter;
+  p.batch = batch_size;
+  p.total_rows = total;
+  p.n_slots = s->n_slots;
+  p.vec_rows = b->vec_rows;
+  p.vec_init = b->vec_init;
+  p.crop_out = b->crop;
+
+  auto h2d = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    return cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, s->stream);
+  };
+  if (idxs) {
+    if (h2d(off_idxs, idxs, (size_t)batch_size * 8) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of idxs failed"));
+    p.given_idxs = (const int64_t*)(base + off_idxs);
+  }
+  if (draws) {
+    cudaError_t e = cudaSuccess;
+    if (draws->idx_pos && !idxs) { e = h2d(off_draw_i64[0], draws->idx_pos, (size_t)batch_size * 8); p.in_idx_pos = (const int64_t*)(base + off_draw_i64[0]); }
+    for (int gs = 0; gs < n_goal_sets && e == cudaSuccess; ++gs) {
+      if (!goal_used[gs]) continue;
+      const ogb_goal_draws& d = draws->goals[gs];
+      e = h2d(off_draw_i64[1 + 2 * gs], d.rand_pos, (size_t)batch_size * 8);
+      p.in_goal[gs].rand_pos = (const int64_t*)(base + off_draw_i64[1 + 2 * gs]);
+      if (d.offset && e == cudaSuccess) { e = h2d(off_draw_i64[2 + 2 * gs], d.offset, (size_t)batch_size * 8); p.in_goal[gs].offset = (const int64_t*)(base + off_draw_i64[2 + 2 * gs]); }
+      if (d.dist && e == cudaSuccess) { e = h2d(off_draw_f64[3 * gs], d.dist, (size_t)batch_size * 8); p.in_goal[gs].dist = (const double*)(base + off_draw_f64[3 * gs]); }
+      if (d.u_traj && e == cudaSuccess) { e = h2d(off_draw_f64[3 * gs + 1], d.u_traj, (size_t)batch_size * 8); p.in_goal[gs].u_traj = (const double*)(base + off_draw_f64[3 * gs + 1]); }
+      if (d.u_cur && e == cudaSuccess) { e = h2d(off_draw_f64[3 * gs + 2], d.u_cur, (size_t)batch_size * 8); p.in_goal[gs].u_cur = (const double*)(base + off_draw_f64[3 * gs + 2]); }
+    }
+    if (draws->crop && e == cudaSuccess) { e = h2d(off_draw_i64[7], draws->crop, (size_t)batch_size * 16); p.in_crop = (const int64_t*)(base + off_draw_i64[7]); }
+    p.in_coin = draws->has_aug_coin ? draws->aug_coin : 2.0;
+    if (p.aug_mode && !(p.in_coin < p.p_aug)) p.in_crop = nullptr;
+    if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of validation draws failed: %s", cudaGetErrorString(e)));
+  }
+  for (size_t i = 0; i < plan.size(); ++i) {
+    if (plan[i].route != ROUTE_SCALAR) continue;
+    void* ptr = base + b->offsets[i];
+    switch (plan[i].scalar) {
+      case SC_MASKS: p.masks = (double*)ptr; break;
+      case SC_REWARDS: p.rewards = (double*)ptr; break;
+      case SC_HV_OFFSETS: p.hv_offsets = (int64_t*)ptr; break;
+      case SC_HV_STEPS: p.hv_steps = (int64_t*)ptr; break;
+      case SC_HV_MASKS: p.hv_masks = (double*)ptr; break;
+      case SC_HV_REWARDS: p.hv_rewards = (double*)ptr; break;
+      case SC_LV_STEPS: p.lv_steps = (int64_t*)ptr; break;
+      case SC_LV_MASKS: p.lv_masks = (double*)ptr; break;
+      case SC_LV_REWARDS: p.lv_rewards = (double*)ptr; break;
+      default: break;
+    }
+  }
+  // tile size: big tiles amortise phase 1, but a single small batch should still spread over the SMs
+  int tile_rows = 128;
+  while (tile_rows > 32 && (total + tile_rows - 1) / tile_rows < 2 * (int64_t)ds->sm_count) tile_rows >>= 1;
+  p.tile_rows = tile_rows;
+  const int64_t n_tiles = (total + tile_rows - 1) / tile_rows;
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ds->sm_count * 8);
+
+  std::vector<size_t> row_keys;
+  for (size_t i = 0; i < plan.size(); ++i)
+    if (plan[i].route == ROUTE_ROW && plan[i].alias_of < 0) row_keys.push_back(i);
+  size_t done = 0;
+  do {  // normally one launch; more only if a dataset has > kMaxRowJobs vector fields
+    p.n_jobs = 0;
+    p.total_items = 0;
+    p.item_start[0] = 0;
+    while (done < row_keys.size() && p.n_jobs < kMaxRowJobs) {
+      const KeyPlan& k = plan[row_keys[done++]];
+      const Field& f = ds->fields[(size_t)k.field];
+      RowJob& job = p.jobs[p.n_jobs];
+      job.src = f.dptr;
+      job.dst = base + b->offsets[row_keys[done - 1]];
+      job.src_stride = (uint32_t)f.stride;
+      job.row_bytes = (uint32_t)f.row_bytes;
+      int v = largest_vec_log2(f.row_bytes, f.stride);
+      if ((f.row_bytes >> v) > 65535) return bail(fail(OGB_ERR_UNSUPPORTED, "row of field '%s' too long for the row path", f.name.c_str()));
+      job.vec_log2 = (uint8_t)v;
+      job.epr = (uint16_t)(f.row_bytes >> v);
+      int lpr = 0;
+      while ((1 << lpr) < job.epr && lpr < 5) ++lpr;
+      job.lpr_log2 = (uint8_t)lpr;
+      job.n_coliter = (uint16_t)((job.epr + (1 << lpr) - 1) >> lpr);
+      job.slot = (uint8_t)k.slot;
+      const int rows_per_pass = 32 >> lpr;
+      const int n_pass = (tile_rows + rows_per_pass - 1) / rows_per_pass;
+      p.total_items += n_pass * job.n_coliter;
+      p.item_start[++p.n_jobs] = p.total_items;
+    }
+    if (draws) relabel_rows_kernel<true><<<grid, kRelabelThreads, 0, s->stream>>>(p);
+    else relabel_rows_kernel<false><<<grid, kRelabelThreads, 0, s->stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "relabel_rows_kernel launch failed"));
+    b->launches++;
+  } while (done < row_keys.size());
+
+  // ---- image keys: frame stacking + crop fused into the gather ----
+  if (any_frames) {
+    std::vector<size_t> frame_keys;
+    for (size_t i = 0; i < plan.size(); ++i)
+      if (plan[i].route == ROUTE_FRAMES && plan[i].alias_of < 0) frame_keys.push_back(i);
+    std::vector<bool> taken(frame_keys.size(), false);
+    for (size_t a = 0; a < frame_keys.size(); ++a) {
+      if (taken[a]) continue;
+      const KeyPlan& ka = plan[frame_keys[a]];
+      const Field& f = ds->fields[(size_t)ka.field];
+      FramesParams fp;
+      memset(&fp, 0, sizeof(fp));
+      fp.vec_rows = b->vec_rows;
+      fp.vec_init = b->vec_init;
+      fp.crop = b->crop;
+      fp.total_rows = total;
+      if (f.ndim == 4) { fp.H = (int)f.shape[1]; fp.W = (int)f.shape[2]; fp.inner_bytes = (int)(f.shape[3] * f.itemsize); }
+      else {  // stacking of non-image rows: concatenate on the last axis, everything before it is "pixels"
+        int64_t outer = 1;
+        for (int d = 1; d < f.ndim - 1; ++d) outer *= f.shape[d];
+        fp.H = 1; fp.W = (int)outer; fp.inner_bytes = (int)((f.ndim > 1 ? f.shape[f.ndim - 1] : 1) * f.itemsize);
+      }
+      const bool tma = tma_eligible(f, cfg, ka.fs);
+      for (size_t c = a; c < frame_keys.size() && fp.n_jobs < kMaxFrameJobs; ++c) {
+        const KeyPlan& kc = plan[frame_keys[c]];
+        if (taken[c] || kc.field != ka.field || kc.fs != ka.fs) continue;
+        taken[c] = true;
+        FrameJob& job = fp.jobs[fp.n_jobs++];
+        job.src = f.dptr;
+        job.dst = base + b->offsets[frame_keys[c]];
+        job.src_row_stride = (int64_t)f.stride;
+        job.slot = kc.slot;
+        job.crop = kc.crop;
+        job.fs = kc.fs;
+      }
+      if (tma) {
+        const int rb = band_rows_for(fp.H, cfg.crop_padding);
+        if (rb == 0) return bail(fail(OGB_ERR_UNSUPPORTED, "no band size for image height %d", fp.H));
+        fp.band_rows = rb;
+        fp.n_bands = fp.H / rb;
+        CUtensorMap tm;
+        int rc = get_tmap(s, ka.field, rb, &tm);
+        if (rc) return bail(rc);
+        const size_t smem = 2 * (size_t)ka.fs * rb * fp.W * 3;
+        const int64_t n_items = total * fp.n_jobs * fp.n_bands;
+        if (n_items > 0x7fffffff) return bail(fail(OGB_ERR_UNSUPPORTED, "too many frame tiles in one launch"));
+        switch (ka.fs) {
+          case 1: rc = launch_frames_tma<1>(tm, fp, n_items, smem, s->stream); break;
+          case 2: rc = launch_frames_tma<2>(tm, fp, n_items, smem, s->stream); break;
+          case 3: rc = launch_frames_tma<3>(tm, fp, n_items, smem, s->stream); break;
+          default: rc = launch_frames_tma<4>(tm, fp, n_items, smem, s->stream); break;
+        }
+        if (rc) return bail(rc);
+        b->launches++;
+      } else {
+        const int v = largest_vec_log2((size_t)fp.inner_bytes, f.stride);
+        for (int jj = 0; jj < fp.n_jobs; ++jj) {
+          gather_frames_generic_kernel<<<ds->sm_count * 8, 256, 0, s->stream>>>(fp, jj, v);
+          if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_frames_generic_kernel launch failed"));
+          b->launches++;
+        }
+      }
+    }
+  }
+  if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
+    return bail(fail(OGB_ERR_CUDA, "ready event failed"));
+  if (!draws) s->counter += (uint64_t)n_batches;
+  *out = b;
+  return 0;
+}
+
+int ogb_batch_num_keys(const ogb_batch* b, int32_t* out) {
+  if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = (int32_t)b->keys.size();
+  return 0;
+}
+
+int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) {
+  if (!b || !out || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad key index");
+  const KeyPlan& k = b->keys[(size_t)i];
+  memset(out, 0, sizeof(*out));
+  out->name = k.name.c_str();
+  out->dtype = k.dtype;
+  int nd = 0;
+  if (b->n_batches > 1) out->shape[nd++] = b->n_batches;
+  out->shape[nd++] = b->batch;
+  for (int d = 0; d < k.ndim_tail; ++d) out->shape[nd++] = k.tail[d];
+  out->ndim = nd;
+  out->offset = b->offsets[(size_t)i];
+  out->device_ptr = b->block + out->offset;
+  out->nbytes = (size_t)b->total_rows * k.row_bytes;
+  out->alias_of = k.alias_of;
+  return 0;
+}
+
+int ogb_batch_nbytes(const ogb_batch* b, size_t* out) {
+  if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = b->keys_bytes;
+  return 0;
+}
+int ogb_batch_launches(const ogb_batch* b, int32_t* out) {
+  if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = b->launches;
+  return 0;
+}
+int ogb_batch_sync(ogb_batch* b) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  OGB_CUDA(cudaEventSynchronize(b->ready));
+  return 0;
+}
+int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  cudaStream_t c = (cudaStream_t)consumer_stream;
+  if (c == b->sampler->stream) return 0;
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaStreamWaitEvent(c, b->ready, 0));
+  std::lock_guard<std::mutex> lock(b->mu);
+  if (std::find(b->consumers.begin(), b->consumers.end(), c) == b->consumers.end()) b->consumers.push_back(c);
+  return 0;
+}
+int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) {
+  if (!b || !dst) return fail(OGB_ERR_INVALID, "null argument");
+  if (nbytes < b->keys_bytes) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, b->keys_bytes);
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  return 0;
+}
+int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) {
+  if (!b || !dst || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad argument");
+  const size_t need = (size_t)b->total_rows * b->keys[(size_t)i].row_bytes;
+  if (nbytes < need) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, need);
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaMemcpyAsync(dst, b->block + b->offsets[(size_t)i], need, cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  return 0;
+}
+int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {
+  if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
+  if (!b->vec_rows) return fail(OGB_ERR_INVALID, "index vectors were not kept (ogb_sampler_set_debug)");
+  if (slot < 0 || slot >= b->n_slots) return fail(OGB_ERR_INVALID, "bad slot");
+  std::vector<int32_t> tmp((size_t)b->total_rows);
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaMemcpyAsync(tmp.data(), b->vec_rows + (size_t)slot * b->total_rows, tmp.size() * 4, cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  for (size_t i = 0; i < tmp.size(); ++i) dst_host[i] = tmp[i];
+  return 0;
+}
+int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) {
+  if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
+  if (!b->crop) return fail(OGB_ERR_INVALID, "crop shifts were not kept (ogb_sampler_set_debug)");
+  std::vector<int8_t> tmp((size_t)b->total_rows * 2);
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaMemcpyAsync(tmp.data(), b->crop, tmp.size(), cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  const int pad = b->sampler->cfg.crop_padding;
+  for (size_t i = 0; i < tmp.size(); ++i) dst_host[i] = tmp[i] == -128 ? -1 : tmp[i] + pad;
+  return 0;
+}
+
+static void dl_deleter(DLManagedTensor_* t) {
+  if (!t) return;
+  ogb_batch* b = (ogb_batch*)t->manager_ctx;
+  delete[] t->dl_tensor.shape;
+  delete t;
+  batch_unref(b);
+}
+
+int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) {
+  if (!b || !out || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad key index");
+  ogb_key_info info;
+  OGB_TRY(ogb_batch_key_info(b, i, &info));
+  DLManagedTensor_* t = new DLManagedTensor_();
+  t->dl_tensor.data = info.device_ptr;
+  t->dl_tensor.device.device_type = 2;  // kDLCUDA
+  t->dl_tensor.device.device_id = b->sampler->ds->device;
+  t->dl_tensor.ndim = info.ndim;
+  uint8_t code = 0;
+  switch (info.dtype) {
+    case OGB_U8: case OGB_U16: case OGB_U32: case OGB_U64: code = 1; break;
+    case OGB_F16: case OGB_F32: case OGB_F64: code = 2; break;
+    case OGB_BOOL: code = 6; break;
+    default: code = 0; break;
+  }
+  t->dl_tensor.dtype.code = code;
+  t->dl_tensor.dtype.bits = (uint8_t)(dtype_size(info.dtype) * 8);
+  t->dl_tensor.dtype.lanes = 1;
+  t->dl_tensor.shape = new int64_t[(size_t)std::max(info.ndim, 1)];
+  for (int d = 0; d < info.ndim; ++d) t->dl_tensor.shape[d] = info.shape[d];
+  t->dl_tensor.strides = nullptr;  // compact row-major
+  t->dl_tensor.byte_offset = 0;
+  t->manager_ctx = b;
+  t->deleter = dl_deleter;
+  b->refs.fetch_add(1);
+  *out = t;
+  return 0;
+}
+int ogb_batch_retain(ogb_batch* b) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  b->refs.fetch_add(1);
+  return 0;
+}
+int ogb_batch_release(ogb_batch* b) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  batch_unref(b);
+  return 0;
+}
+
+int ogb_host_alloc(size_t nbytes, void** out) {
+  if (!out) return fail(OGB_ERR_INVALID, "null out");
+  OGB_CUDA(cudaHostAlloc(out, std::max<size_t>(nbytes, 1), cudaHostAllocDefault));
+  return 0;
+}
+int ogb_host_free(void* p) {
+  if (p) OGB_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* keys_host, int64_t m, int32_t side_right,
+                          int32_t device, int64_t* out_host) {
+  if (!sorted_host || !keys_host || !out_host || n < 0 || m < 0) return fail(OGB_ERR_INVALID, "bad arguments");
+  OGB_CUDA(cudaSetDevice(device));
+  int64_t *d_t = nullptr, *d_k = nullptr, *d_o = nullptr;
+  OGB_CUDA(cudaMalloc((void**)&d_t, std::max<int64_t>(n, 1) * 8));
+  OGB_CUDA(cudaMalloc((void**)&d_k, std::max<int64_t>(m, 1) * 8));
+  OGB_CUDA(cudaMalloc((void**)&d_o, std::max<int64_t>(m, 1) * 8));
+  OGB_CUDA(cudaMemcpy(d_t, sorted_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+  OGB_CUDA(cudaMemcpy(d_k, keys_host, (size_t)m * 8, cudaMemcpyHostToDevice));
+  if (m > 0) searchsorted_warp_kernel<<<(unsigned)std::min<int64_t>((m + 7) / 8, 148 * 8), 256>>>(d_t, n, d_k, m, side_right, d_o);
+  OGB_CUDA(cudaGetLastError());
+  OGB_CUDA(cudaMemcpy(out_host, d_o, (size_t)m * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_t); cudaFree(d_k); cudaFree(d_o);
+  return 0;
+}
+
+int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t purpose, int64_t n, int32_t device, uint32_t* out_host) {
+  if (!out_host || n < 0) return fail(OGB_ERR_INVALID, "bad arguments");
+  OGB_CUDA(cudaSetDevice(device));
+  uint4* d = nullptr;
+  OGB_CUDA(cudaMalloc((void**)&d, std::max<int64_t>(n, 1) * 16));
+  ogb::RngKey key{seed, stream_id};
+  if (n > 0) philox_fill_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256>>>(key, batch, purpose, n, d);
+  OGB_CUDA(cudaGetLastError());
+  OGB_CUDA(cudaMemcpy(out_host, d, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
+}  // extern "C"

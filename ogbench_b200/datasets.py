@@ -1,0 +1,483 @@
+"""Host-side mirror of the reference sampler API (impls/utils/datasets.py) over the CUDA library.
+
+Same names, arguments, key sets, shapes and dtypes as the reference:
+
+    dataset = Dataset.create(**fields)                       # datasets.py:45-57
+    sampler = GCDataset(dataset, config)                     # datasets.py:149-211   (HGCDataset: :467-643)
+    batch = sampler.sample(batch_size, idxs=None, evaluation=False)
+
+What differs is where things live: the fields are uploaded once and stay resident in HBM, the whole of
+``sample()`` is one or two CUDA launches, and the returned dict holds device arrays (``DeviceArray``: DLPack +
+``__cuda_array_interface__``; ``output='numpy'`` copies the batch to host like the reference returns it).
+Keyword-only extras (``device``, ``seed``, ``stream_id``, ``rng``, ``output``, ``dedup``) have defaults that keep
+reference call sites working unchanged.  There is no CPU implementation behind this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Any, Dict, Mapping, Optional
+
+import numpy as np
+
+from . import _native
+from .device_array import BatchHandle, DeviceArray
+
+TRL_AGENTS = ('trl', 'latent_trl', 'discrete_latent_trl')
+
+
+def get_size(data) -> int:
+    """Return the size of the dataset: the longest field (datasets.py:11-14)."""
+    return max(len(v) for v in data.values())
+
+
+def _is_device_array(x) -> bool:
+    return not isinstance(x, np.ndarray) and (hasattr(x, '__cuda_array_interface__') or hasattr(x, 'data_ptr'))
+
+
+def _describe_field(name: str, arr, keepalive: list) -> _native.Field:
+    f = _native.Field()
+    f.name = name.encode()
+    if _is_device_array(arr):
+        if hasattr(arr, 'data_ptr'):  # torch tensor
+            if not arr.is_cuda or not arr.is_contiguous():
+                raise ValueError(f'field {name!r}: device tensors must be contiguous CUDA tensors')
+            import torch
+
+            np_dtype = np.dtype(str(arr.dtype).replace('torch.', '').replace('bool', 'bool_'))
+            shape, ptr = tuple(arr.shape), arr.data_ptr()
+            torch.cuda.current_stream(arr.device).synchronize()
+        else:
+            cai = arr.__cuda_array_interface__
+            if cai.get('strides') is not None:
+                raise ValueError(f'field {name!r}: device arrays must be C-contiguous')
+            np_dtype, shape, ptr = np.dtype(cai['typestr']), tuple(cai['shape']), cai['data'][0]
+        f.on_device = 1
+    else:
+        arr = np.ascontiguousarray(arr)
+        np_dtype, shape, ptr = arr.dtype, arr.shape, arr.ctypes.data
+        f.on_device = 0
+    keepalive.append(arr)
+    if np_dtype not in _native.DTYPE_TO_CODE:
+        raise TypeError(f'field {name!r}: unsupported dtype {np_dtype}')
+    if not 1 <= len(shape) <= _native.OGB_MAX_NDIM:
+        raise ValueError(f'field {name!r}: unsupported rank {len(shape)}')
+    f.data = ptr
+    f.dtype = _native.DTYPE_TO_CODE[np_dtype]
+    f.ndim = len(shape)
+    for d, n in enumerate(shape):
+        f.shape[d] = n
+    return f
+
+
+class _NativeDataset:
+    """Owns the ogb_dataset handle (the HBM-resident copy)."""
+
+    def __init__(self, fields: Mapping[str, Any], device: int):
+        _native.require_device()
+        keepalive: list = []
+        descs = (_native.Field * len(fields))(*[_describe_field(k, v, keepalive) for k, v in fields.items()])
+        out = C.c_void_p()
+        _native.check(_native.lib().ogb_dataset_create(descs, len(fields), device, C.byref(out)))
+        self.ptr = out
+        self.device = device
+
+    def resident_bytes(self) -> int:
+        n = C.c_size_t()
+        _native.check(_native.lib().ogb_dataset_resident_bytes(self.ptr, C.byref(n)))
+        return n.value
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, 'ptr', None), None
+        if ptr:
+            try:
+                _native.lib().ogb_dataset_destroy(ptr)
+            except Exception:
+                pass
+
+
+class Dataset(Mapping):
+    """Immutable field dict (the reference's FrozenDict-based Dataset, datasets.py:36-83).
+
+    Supports compact datasets (no 'next_observations'; 'valids' masks each trajectory's last row) and regular ones.
+    Field values may be numpy arrays (uploaded once) or CUDA arrays (torch tensors / __cuda_array_interface__).
+    """
+
+    @classmethod
+    def create(cls, freeze=True, **fields):
+        data = fields
+        assert 'observations' in data
+        if freeze:
+            for arr in data.values():
+                if isinstance(arr, np.ndarray):
+                    arr.setflags(write=False)
+        return cls(data)
+
+    def __init__(self, *args, **kwargs):
+        if len(args) == 1 and isinstance(args[0], Dataset) and not kwargs:
+            self._dict = dict(args[0]._dict)
+        else:
+            self._dict = dict(*args, **kwargs)
+        for k, v in self._dict.items():
+            if isinstance(v, Mapping):
+                raise NotImplementedError(f'field {k!r}: nested (pytree) fields are not supported by the device sampler')
+        self.size = get_size(self._dict)
+        if 'valids' in self._dict and isinstance(self._dict['valids'], np.ndarray):
+            (self.valid_idxs,) = np.nonzero(self['valids'] > 0)
+        self._native: Dict[int, _NativeDataset] = {}
+        self._plain: Dict[int, '_Sampler'] = {}
+
+    # ---- Mapping ----
+    def __getitem__(self, key):
+        return self._dict[key]
+
+    def __iter__(self):
+        return iter(self._dict)
+
+    def __len__(self):
+        return len(self._dict)
+
+    def copy(self, add_or_replace=None):
+        merged = dict(self._dict)
+        merged.update(add_or_replace or {})
+        return type(self)(merged)
+
+    # ---- reference API ----
+    def get_random_idxs(self, num_idxs):
+        """Return `num_idxs` random indices from the global np.random stream (datasets.py:65-70)."""
+        if hasattr(self, 'valid_idxs'):
+            return self.valid_idxs[np.random.randint(len(self.valid_idxs), size=num_idxs)]
+        return np.random.randint(self.size, size=num_idxs)
+
+    def native(self, device: int = 0) -> _NativeDataset:
+        if device not in self._native:
+            self._native[device] = _NativeDataset(self._dict, device)
+        return self._native[device]
+
+    def _plain_sampler(self, device=0) -> '_Sampler':
+        if device not in self._plain:
+            self._plain[device] = _Sampler(self, None, _native.KIND_PLAIN, device=device)
+        return self._plain[device]
+
+    def sample(self, batch_size, idxs=None):
+        """Sample a batch of transitions (datasets.py:72-76)."""
+        return self._plain_sampler().sample(batch_size, idxs)
+
+    def get_subset(self, idxs):
+        """Return the rows `idxs` of every field plus next_observations (datasets.py:78-83)."""
+        idxs = np.asarray(idxs, dtype=np.int64)
+        return self._plain_sampler().sample(len(idxs), idxs)
+
+
+class _PinnedPool:
+    """Reusable page-locked host blocks for output='numpy'."""
+
+    def __init__(self):
+        self.free: Dict[int, list] = {}
+
+    def take(self, nbytes: int) -> '_PinnedBlock':
+        bucket = 1 << max(12, (nbytes - 1).bit_length())
+        stack = self.free.setdefault(bucket, [])
+        if stack:
+            return _PinnedBlock(self, bucket, stack.pop())
+        out = C.c_void_p()
+        _native.check(_native.lib().ogb_host_alloc(bucket, C.byref(out)))
+        return _PinnedBlock(self, bucket, out.value)
+
+
+class _PinnedBlock:
+    def __init__(self, pool, bucket, ptr):
+        self.pool, self.bucket, self.ptr = pool, bucket, ptr
+
+    def __del__(self):
+        try:
+            self.pool.free[self.bucket].append(self.ptr)
+        except Exception:
+            pass
+
+
+_PINNED = _PinnedPool()
+
+
+class _Sampler:
+    """Thin owner of an ogb_sampler handle; builds the C config from the reference's config mapping."""
+
+    def __init__(self, dataset: Dataset, config, kind: int, device: int = 0, seed: int = 0, stream_id: int = 0,
+                 dedup: bool = True, output: str = 'device'):
+        assert output in ('device', 'numpy')
+        self.dataset = dataset
+        self.kind = kind
+        self.device = device
+        self.output = output
+        self._keepalive = []
+        cfg = _native.Config()
+        cfg.dedup_keys = int(dedup)
+        cfg.crop_padding = 3  # GCDataset.augment, datasets.py:331
+        if kind != _native.KIND_PLAIN:
+            cfg.discount = float(config['discount'])
+            for side in ('value', 'actor'):
+                for part in ('cur', 'traj', 'random'):
+                    setattr(cfg, f'{side}_p_{part}goal', float(config[f'{side}_p_{part}goal']))
+                setattr(cfg, f'{side}_geom_sample', int(bool(config[f'{side}_geom_sample'])))
+            cfg.gc_negative = int(bool(config['gc_negative']))
+            p_aug = config['p_aug']
+            cfg.has_p_aug = int(p_aug is not None)
+            cfg.p_aug = float(p_aug) if p_aug is not None else 0.0
+            fs = config['frame_stack']
+            cfg.frame_stack = int(fs) if fs is not None else 0
+        if kind == _native.KIND_HGC:
+            # datasets.py:515-518, :543, :592-594 -- the optional overrides, resolved as the reference resolves them
+            high = config.get('high_subgoal_steps', config['subgoal_steps'])
+            value = high if config.get('value_subgoal_steps') is None else config['value_subgoal_steps']
+            actor = high if config.get('actor_subgoal_steps') is None else config['actor_subgoal_steps']
+            low = config.get('low_subgoal_steps', config['subgoal_steps'])
+            cfg.value_subgoal_steps, cfg.actor_subgoal_steps, cfg.low_subgoal_steps = int(value), int(actor), int(low)
+            low_discount = config.get('low_discount')
+            cfg.has_low_discount = int(low_discount is not None)
+            cfg.low_discount = float(low_discount) if low_discount is not None else 0.0
+            # numpy's own `discount ** steps` (its SIMD pow is not libm's), evaluated exactly as datasets.py:537-541
+            steps = np.arange(max(value, actor, low) + 1)
+            discount = config['discount']
+            neg = np.ascontiguousarray(-(1 - discount**steps) / (1 - discount), dtype=np.float64)
+            pw = np.ascontiguousarray(discount**steps, dtype=np.float64)
+            self._keepalive += [neg, pw]
+            cfg.lut_len = len(steps)
+            cfg.neg_reward_lut = neg.ctypes.data_as(C.POINTER(C.c_double))
+            cfg.pow_lut = pw.ctypes.data_as(C.POINTER(C.c_double))
+        self._cfg = cfg
+        self._nds = dataset.native(device)
+        out = C.c_void_p()
+        _native.check(_native.lib().ogb_sampler_create(self._nds.ptr, C.byref(cfg), kind, seed, stream_id, C.byref(out)))
+        self.ptr = out
+        self._finalizer = weakref.finalize(self, _native.lib().ogb_sampler_destroy, out)
+
+    # ---- bounds (terminal_locs / initial_locs, datasets.py:186-187) ----
+    def bounds(self):
+        n = C.c_int64()
+        _native.check(_native.lib().ogb_sampler_num_terminals(self.ptr, C.byref(n)))
+        term = np.empty(n.value, dtype=np.int64)
+        init = np.empty(n.value, dtype=np.int64)
+        _native.check(_native.lib().ogb_sampler_copy_bounds(self.ptr, term.ctypes.data_as(C.c_void_p),
+                                                            init.ctypes.data_as(C.c_void_p)))
+        return term, init
+
+    def set_stream(self, cuda_stream: int):
+        _native.check(_native.lib().ogb_sampler_set_stream(self.ptr, C.c_void_p(cuda_stream)))
+
+    def set_debug(self, on: bool = True):
+        _native.check(_native.lib().ogb_sampler_set_debug(self.ptr, int(on)))
+
+    @property
+    def counter(self) -> int:
+        n = C.c_uint64()
+        _native.check(_native.lib().ogb_sampler_get_counter(self.ptr, C.byref(n)))
+        return n.value
+
+    @counter.setter
+    def counter(self, value: int):
+        _native.check(_native.lib().ogb_sampler_set_counter(self.ptr, int(value)))
+
+    # ---- the hot call ----
+    def sample_native(self, batch_size, n_batches=1, idxs=None, evaluation=False, draws=None) -> BatchHandle:
+        lib = _native.lib()
+        keep = []
+        idx_ptr = None
+        if idxs is not None:
+            idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64)
+            if idxs.ndim != 1:
+                raise ValueError('idxs must be one-dimensional')
+            batch_size = len(idxs)  # datasets.py:74-76,298: len(idxs) rules
+            idx_ptr = idxs.ctypes.data_as(C.c_void_p)
+            keep.append(idxs)
+        c_draws = None
+        if draws is not None:
+            c_draws = _pack_draws(draws, keep)
+        out = C.c_void_p()
+        _native.check(lib.ogb_sampler_sample(self.ptr, int(batch_size), int(n_batches), idx_ptr, int(bool(evaluation)),
+                                             C.byref(c_draws) if c_draws is not None else None, C.byref(out)))
+        return BatchHandle(out, self.device, None)
+
+    def wrap(self, handle: BatchHandle) -> Dict[str, Any]:
+        lib = _native.lib()
+        n = C.c_int32()
+        _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
+        infos = []
+        for i in range(n.value):
+            info = _native.KeyInfo()
+            _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
+            infos.append(info)
+        if self.output == 'device':
+            return {info.name.decode(): DeviceArray(handle, i, info) for i, info in enumerate(infos)}
+        # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it
+        nbytes = C.c_size_t()
+        _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
+        block = _PINNED.take(max(nbytes.value, 1))
+        _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
+        raw = (C.c_ubyte * max(nbytes.value, 1)).from_address(block.ptr)
+        raw._owner = block  # numpy views -> ctypes buffer -> pinned block: returned to the pool when all views die
+        flat = np.frombuffer(raw, dtype=np.uint8)
+        out = {}
+        for info in infos:
+            shape = tuple(int(info.shape[d]) for d in range(info.ndim))
+            dtype = _native.CODE_TO_DTYPE[info.dtype]
+            out[info.name.decode()] = flat[info.offset:info.offset + info.nbytes].view(dtype).reshape(shape)
+        return out
+
+    def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1):
+        return self.wrap(self.sample_native(batch_size, n_batches, idxs, evaluation, draws))
+
+
+def _pack_draws(draws, keep) -> _native.Draws:
+    """`draws` is an oracle-style record: .idx_pos, .goals (list of records with rand_pos/offset/dist/u_traj/u_cur,
+    in reference call order: value, [low-value], actor), .aug_coin, .crop."""
+    d = _native.Draws()
+
+    def ptr(arr, dtype):
+        if arr is None:
+            return None
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data
+
+    d.idx_pos = ptr(getattr(draws, 'idx_pos', None), np.int64)
+    goals = list(draws.goals)
+    slots = {1: [0], 2: [0, 2], 3: [0, 1, 2]}[len(goals)] if goals else []
+    for slot, g in zip(slots, goals):
+        d.goals[slot].rand_pos = ptr(g.rand_pos, np.int64)
+        d.goals[slot].offset = ptr(g.offset, np.int64)
+        d.goals[slot].dist = ptr(g.dist, np.float64)
+        d.goals[slot].u_traj = ptr(g.u_traj, np.float64)
+        d.goals[slot].u_cur = ptr(g.u_cur, np.float64)
+    d.has_aug_coin = int(draws.aug_coin is not None)
+    d.aug_coin = float(draws.aug_coin) if draws.aug_coin is not None else 0.0
+    d.crop = ptr(getattr(draws, 'crop', None), np.int64)
+    return d
+
+
+class _HostDraws:
+    """The reference's np.random call sequence for one sample(), made on the host so the
+    device sampler consumes exactly the draws the reference would have consumed (rng='numpy')."""
+
+    class _Goal:
+        __slots__ = ('rand_pos', 'offset', 'dist', 'u_traj', 'u_cur')
+
+        def __init__(self):
+            self.rand_pos = self.offset = self.dist = self.u_traj = self.u_cur = None
+
+    def __init__(self):
+        self.idx_pos = None
+        self.goals = []
+        self.aug_coin = None
+        self.crop = None
+
+    def goal(self, n_choices, batch, geom, discount, p_cur):
+        g = self._Goal()
+        g.rand_pos = np.random.randint(n_choices, size=batch)          # datasets.py:303 -> :68/:70
+        if geom:
+            g.offset = np.random.geometric(p=1 - discount, size=batch)  # :309
+        else:
+            g.dist = np.random.rand(batch)                              # :313
+        if p_cur != 1.0:
+            g.u_traj = np.random.rand(batch)                            # :321
+            g.u_cur = np.random.rand(batch)                             # :325
+        self.goals.append(g)
+
+
+class GCDataset:
+    """Dataset class for goal-conditioned RL, device-resident (reference: datasets.py:149-366).
+
+    Reads from `config`: discount, value_p_{cur,traj,random}goal, value_geom_sample, actor_p_*goal,
+    actor_geom_sample, gc_negative, p_aug, frame_stack.  `preprocess_frame_stack` is accepted for compatibility;
+    frames are always stacked inside the gather (same values, none of the 3x resident copy of datasets.py:209-211).
+
+    rng='philox' (default): indices, offsets and crop shifts are drawn on the device from a counter RNG keyed by
+    (seed, stream_id, batch counter).  rng='numpy': the global np.random stream is consumed with exactly the
+    reference's calls and the device computes the batch from those draws -- bit-identical to the reference for the
+    same np.random.seed.
+    """
+
+    _KIND = _native.KIND_GC
+
+    def __init__(self, dataset: Dataset, config: Any, preprocess_frame_stack: bool = True, *, device: int = 0,
+                 seed: int = 0, stream_id: int = 0, rng: str = 'philox', output: str = 'device', dedup: bool = True):
+        if not isinstance(dataset, Dataset):
+            dataset = Dataset.create(freeze=False, **dataset)
+        assert rng in ('philox', 'numpy')
+        self.dataset = dataset
+        self.config = config
+        self.preprocess_frame_stack = preprocess_frame_stack
+        self.rng = rng
+        self.size = dataset.size
+        # datasets.py:191-196 (checked before touching the device, like the reference's __post_init__)
+        assert np.isclose(config['value_p_curgoal'] + config['value_p_trajgoal'] + config['value_p_randomgoal'], 1.0)
+        assert np.isclose(config['actor_p_curgoal'] + config['actor_p_trajgoal'] + config['actor_p_randomgoal'], 1.0)
+        if config.get('agent_name') in TRL_AGENTS:
+            raise NotImplementedError('the TRL branch of GCDataset (datasets.py:198-204,254-276) is not built yet')
+        self._sampler = _Sampler(dataset, config, self._KIND, device=device, seed=seed, stream_id=stream_id,
+                                 dedup=dedup, output=output)
+        self.terminal_locs, self.initial_locs = self._sampler.bounds()
+        self._n_choices = len(dataset.valid_idxs) if hasattr(dataset, 'valid_idxs') else self._num_choices_native()
+
+    def _num_choices_native(self):
+        n = C.c_int64()
+        _native.check(_native.lib().ogb_dataset_num_valid(self._sampler._nds.ptr, C.byref(n)))
+        return n.value if n.value >= 0 else self.size
+
+    # ---- the reference's draw order, host side (rng='numpy') ----
+    def _goal_sets(self):
+        cfg = self.config
+        return [(cfg['value_geom_sample'], cfg['discount'], cfg['value_p_curgoal']),
+                (cfg['actor_geom_sample'], cfg['discount'], cfg['actor_p_curgoal'])]
+
+    def _host_draws(self, batch_size, idxs, evaluation) -> _HostDraws:
+        d = _HostDraws()
+        if idxs is None:
+            d.idx_pos = np.random.randint(self._n_choices, size=batch_size)      # datasets.py:226 -> :68/:70
+        for geom, discount, p_cur in self._goal_sets():
+            d.goal(self._n_choices, batch_size, geom, discount, p_cur)
+        if self.config['p_aug'] is not None and not evaluation:                  # :278-279 / :621-622
+            d.aug_coin = np.random.rand()
+            if d.aug_coin < self.config['p_aug']:
+                d.crop = np.random.randint(0, 2 * 3 + 1, (batch_size, 2))        # :333
+        return d
+
+    def sample(self, batch_size, idxs=None, evaluation=False, *, draws=None):
+        """Sample a batch of transitions with goals (datasets.py:213-294).
+
+        Returns the reference's keys: every dataset field, next_observations, value_goals, actor_goals,
+        masks, rewards.  `draws` (an oracle-style record) selects validation mode explicitly.
+        """
+        if idxs is not None:
+            batch_size = len(idxs)
+        if draws is None and self.rng == 'numpy':
+            draws = self._host_draws(batch_size, idxs, evaluation)
+        return self._sampler.sample(batch_size, idxs, evaluation, draws)
+
+    def sample_many(self, num_batches, batch_size, evaluation=False):
+        """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis."""
+        return self._sampler.sample(batch_size, None, evaluation, None, n_batches=num_batches)
+
+    # ---- checkpointable sampler state: one integer ----
+    def state_dict(self):
+        return {'counter': self._sampler.counter}
+
+    def load_state_dict(self, state):
+        self._sampler.counter = state['counter']
+
+
+class HGCDataset(GCDataset):
+    """Dataset class for hierarchical goal-conditioned RL (reference: datasets.py:467-643).
+
+    Additional config keys: subgoal_steps (optional: high_/low_/value_/actor_subgoal_steps), low_discount.
+    """
+
+    _KIND = _native.KIND_HGC
+
+    def _goal_sets(self):
+        cfg = self.config
+        sets = [(cfg['value_geom_sample'], cfg['discount'], cfg['value_p_curgoal'])]
+        if cfg.get('low_discount') is not None:                                  # datasets.py:563-571
+            sets.append((True, cfg['low_discount'], cfg['value_p_curgoal']))
+        sets.append((cfg['actor_geom_sample'], cfg['discount'], cfg['actor_p_curgoal']))
+        return sets

@@ -117,6 +117,50 @@ class ReplaySource:
         return self.pos == len(self.log)
 
 
+class DrawsSource:
+    """Serves a structured ``Draws`` record back in reference call order (used to run the oracle on the draws the
+    device's Philox mode made, see oracle/philox_np.py)."""
+
+    def __init__(self, draws: Draws):
+        q = []
+        if draws.idx_pos is not None:
+            q.append(draws.idx_pos)
+        for g in draws.goals:
+            q.append(g.rand_pos)
+            q.append(g.offset if g.offset is not None else g.dist)
+            if g.u_traj is not None:
+                q.extend([g.u_traj, g.u_cur])
+        if draws.aug_coin is not None:
+            q.append(draws.aug_coin)
+        if draws.crop is not None:
+            q.append(draws.crop)
+        self.queue = q
+        self.pos = 0
+
+    def _pop(self):
+        out = self.queue[self.pos]
+        self.pos += 1
+        return out
+
+    def randint(self, high, size):
+        return self._pop()
+
+    def randint_box(self, low, high, shape):
+        return self._pop()
+
+    def geometric(self, p, size):
+        return self._pop()
+
+    def rand(self, size):
+        return self._pop()
+
+    def rand_scalar(self):
+        return float(self._pop())
+
+    def exhausted(self):
+        return self.pos == len(self.queue)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # Building blocks
 # --------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,137 @@
+"""GPU parity: the CUDA sampler (through the C-ABI) against the golden vectors and the oracle, bit-exact."""
+
+import numpy as np
+import pytest
+
+from tests.golden.make_golden import cfg, ragged, toy_fields
+from tests.golden_util import assert_batches_identical, case_names, load_case
+from tests.gpu_util import device_sampler, draws_from_log, oracle_with_draws, to_host
+
+pytestmark = pytest.mark.gpu
+CASES = case_names()
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_validation_mode_matches_golden(name):
+    """The device consumes the reference's recorded draws and must return the reference's batch, every key."""
+    case = load_case(name)
+    sampler = device_sampler(case['fields'], case['cfg'], case['kind'])
+    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'], draws=draws_from_log(case))
+    assert_batches_identical(to_host(got), case['out'], label=name + ':')
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_numpy_rng_mode_matches_golden(name):
+    """rng='numpy': same np.random.seed as the reference run -> same batch, with no recording in between."""
+    case = load_case(name)
+    sampler = device_sampler(case['fields'], case['cfg'], case['kind'], rng='numpy', output='numpy')
+    np.random.seed(case['meta']['seed'])
+    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'])
+    assert_batches_identical(got, case['out'], label=name + ':')
+
+
+@pytest.mark.parametrize('name', ['gc_state_gcivl', 'hgc_state_hiql', 'hgc_pixel_fs3_aug'])
+def test_no_dedup_matches_golden(name):
+    case = load_case(name)
+    sampler = device_sampler(case['fields'], case['cfg'], case['kind'], dedup=False)
+    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'], draws=draws_from_log(case))
+    assert_batches_identical(to_host(got), case['out'], label=name + ':')
+
+
+SWEEP = [
+    # kind, pixel, obs_shape, frame_stack, overrides
+    ('gc', False, (29,), None, {}),
+    ('gc', False, (2,), None, dict(value_geom_sample=False, actor_geom_sample=True, actor_p_curgoal=0.2, actor_p_trajgoal=0.3, actor_p_randomgoal=0.5)),
+    ('gc', False, (7,), 3, {}),                        # frame stacking of vector observations
+    ('gc', False, (3, 5), 2, {}),                      # ... and of rank-3 fields
+    ('hgc', False, (69,), None, dict(subgoal_steps=25, discount=0.995)),
+    ('hgc', False, (55,), None, dict(subgoal_steps=4, value_geom_sample=False, actor_geom_sample=True, gc_negative=False,
+                                      actor_p_curgoal=0.0, actor_p_trajgoal=0.5, actor_p_randomgoal=0.5, discount=0.999)),
+    ('hgc', False, (6,), None, dict(subgoal_steps=9, low_discount=0.95, low_subgoal_steps=2)),
+    ('gc', True, (64, 64, 3), 3, dict(p_aug=0.5)),
+    ('gc', True, (32, 48, 3), 3, dict(p_aug=1.0)),
+    ('gc', True, (64, 64, 3), None, dict(p_aug=1.0)),
+    ('gc', True, (64, 64, 3), 4, dict(p_aug=1.0)),
+    ('hgc', True, (64, 64, 3), 3, dict(p_aug=0.5, subgoal_steps=3)),
+    ('gc', True, (20, 12, 4), 3, dict(p_aug=1.0)),    # not TMA-eligible: generic frame kernel
+    ('gc', True, (8, 8, 3), 2, dict(p_aug=1.0)),      # not TMA-eligible (W % 16)
+]
+
+
+@pytest.mark.parametrize('spec', SWEEP, ids=[f'{s[0]}-{"x".join(map(str, s[2]))}-fs{s[3]}-{i}' for i, s in enumerate(SWEEP)])
+def test_oracle_sweep(spec):
+    """Seeded ragged datasets at sizes the oracle finishes in seconds; several batches, both evaluation modes."""
+    kind, pixel, obs_shape, fs, over = spec
+    seed = abs(hash(str(spec))) % 1000
+    lengths = ragged(seed, 12 if pixel else 200, 2, 20 if pixel else 300)
+    fields = toy_fields(seed, lengths, obs_shape, 5, np.uint8 if pixel else np.float32)
+    config = cfg(frame_stack=fs, **over)
+    sampler = device_sampler(fields, config, kind, rng='numpy', output='numpy')
+    B = 37 if pixel else 1024
+    for it, evaluation in enumerate([False, False, True, False]):
+        np.random.seed(seed * 10 + it)
+        _, want = oracle_with_draws(fields, config, kind, B, evaluation=evaluation)
+        np.random.seed(seed * 10 + it)
+        got = sampler.sample(B, evaluation=evaluation)
+        assert_batches_identical(got, want, label=f'{spec}/{it}:')
+
+
+def test_index_vectors_exposed():
+    case = load_case('hgc_state_hiql')
+    sampler = device_sampler(case['fields'], case['cfg'], 'hgc')
+    sampler._sampler.set_debug(True)
+    from oracle.replay_oracle import OracleSampler, ReplaySource
+    import ctypes as C
+    from ogbench_b200 import _native
+
+    o = OracleSampler(case['fields'], case['cfg'], 'hgc')
+    o.sample(case['B'], source=ReplaySource(case['log']))
+    handle = sampler._sampler.sample_native(case['B'], draws=o.last_draws)
+    names = ['idxs', None, 'hv_goal', 'hv_next', 'lv_next', 'ha_goal', 'ha_next', 'la_goal', 'la_next']
+    for slot, nm in enumerate(names):
+        if nm is None:
+            continue
+        out = np.empty(case['B'], dtype=np.int64)
+        _native.check(_native.lib().ogb_batch_index_vector(handle.ptr, slot, out.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(out, o.last_index_vectors[nm]), nm
+
+
+def test_given_idxs_out_of_range_raises():
+    case = load_case('gc_state_gcivl')
+    sampler = device_sampler(case['fields'], case['cfg'], 'gc')
+    with pytest.raises(IndexError):
+        sampler.sample(2, idxs=np.array([0, sampler.size]))
+
+
+def test_constructor_asserts():
+    from ogbench_b200 import Dataset, GCDataset
+
+    case = load_case('gc_state_gcivl')
+    with pytest.raises(AssertionError):
+        Dataset.create(actions=case['fields']['actions'])
+    bad = dict(case['cfg'], value_p_curgoal=0.5)
+    with pytest.raises(AssertionError):
+        device_sampler(case['fields'], bad, 'gc')
+    fields = dict(case['fields'])
+    fields['terminals'] = fields['terminals'].copy()
+    fields['terminals'][-1] = 0.0
+    with pytest.raises(AssertionError):
+        device_sampler(fields, case['cfg'], 'gc')
+    reg = load_case('gc_state_regular')
+    with pytest.raises(AssertionError):
+        device_sampler(reg['fields'], dict(reg['cfg'], frame_stack=3), 'gc')
+    with pytest.raises(KeyError):
+        GCDataset(Dataset.create(**case['fields']), {k: v for k, v in case['cfg'].items() if k != 'discount'})
+
+
+def test_plain_dataset_sample_and_subset():
+    """Dataset.sample / get_subset (datasets.py:72-83) on device."""
+    from ogbench_b200 import Dataset
+
+    case = load_case('gc_state_gcivl')
+    ds = Dataset.create(**{k: v.copy() for k, v in case['fields'].items()})
+    idxs = np.array([0, 5, ds.size - 1, 17])
+    got = to_host(ds.get_subset(idxs))
+    for k, v in case['fields'].items():
+        assert np.array_equal(got[k], v[idxs])
+    assert np.array_equal(got['next_observations'], case['fields']['observations'][np.minimum(idxs + 1, ds.size - 1)])
