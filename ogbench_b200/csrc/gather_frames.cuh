@@ -9,11 +9,14 @@
 // crop; here each output byte is produced once, straight from the un-stacked resident frames.
 //
 // gather_frames_tma_kernel: uint8 HWC images with C == 3 (the 64x64x3 OGBench pixels).
-//   * load  : one cp.async.bulk.tensor (TMA, tile mode) per source frame and row band.  The box is issued at
-//             coordinates (3*dx, y0+dy): the crop shift is applied by the TMA unit, out-of-image parts arrive as
-//             zeros and are patched to the edge pixel in registers (rows: index clamp; columns: first/last group).
-//   * permute: each thread turns 16 pixels x FS frames (aligned 16-byte shared loads) into 16 x 3FS interleaved
-//             output bytes with byte permutes and writes them as 16-byte shared stores into the output image.
+//   * load  : one cp.async.bulk.tensor (TMA, tile mode) per source frame and row band.  The box is issued at row
+//             coordinate y0+dy, so the vertical crop shift is applied by the TMA unit; rows outside the image
+//             arrive as zero fill and are never read (row index clamp = edge replication).  The innermost TMA
+//             coordinate has to stay 16-byte aligned (an unaligned one faults on sm_100a), so the horizontal
+//             shift of 3*dx bytes is applied when reading shared memory: 13 words + a funnel shift per frame,
+//             and the first/last pixel group patches its out-of-image pixels with the edge pixel in registers.
+//   * permute: each thread turns 16 pixels x FS frames into 16 x 3FS interleaved output bytes with byte permutes
+//             and writes them as 16-byte shared stores into the output image.
 //   * store : one cp.async.bulk (TMA) shared->global per band; the band is a contiguous, 16-byte-aligned span
 //             of the dense output.
 // gather_frames_generic_kernel: any dtype / shape / padding, element-granular; correctness fallback on device.
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kFramesThreads) gather_frames_tma_kernel(const
     for (int f = 0; f < FS; ++f) {
       int32_t fr = row - (FS - 1 - f);
       fr = fr > first ? fr : first;                  // np.maximum(idxs - i, initial_state_idxs)  datasets.py:364
-      tma_load_3d(s_in + (size_t)f * band_bytes, &tmap, C * dx, y0 + dy, fr, &bar);
+      tma_load_3d(s_in + (size_t)f * band_bytes, &tmap, 0, y0 + dy, fr, &bar);
     }
   }
   mbar_wait(&bar, 0);
@@ -153,37 +156,54 @@ __global__ void __launch_bounds__(kFramesThreads) gather_frames_tma_kernel(const
     const int rr = task / groups, gq = task - rr * groups;
     const int rc = min(max(rr, r_lo), r_hi);         // row clamp = edge replication in y
     uint32_t src[FS][kSrcWords];
-#pragma unroll
-    for (int f = 0; f < FS; ++f) {
-      const uint4* sp = reinterpret_cast<const uint4*>(s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes + gq * (kGroupPx * C));
-#pragma unroll
-      for (int q = 0; q < kSrcWords / 4; ++q) {
-        const uint4 v = sp[q];
-        src[f][4 * q + 0] = v.x; src[f][4 * q + 1] = v.y; src[f][4 * q + 2] = v.z; src[f][4 * q + 3] = v.w;
-      }
-    }
-    // column clamp = edge replication in x: only the first group (dx < 0) or the last group (dx > 0) has holes
-    if (dx < 0 && gq == 0) {
-      const int p_lo = -dx;                          // first in-image pixel of this row band, local index
+    if (dx == 0) {                                   // aligned fast path: 3 x 16-byte shared loads per frame
 #pragma unroll
       for (int f = 0; f < FS; ++f) {
-        const uint8_t* px = s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes + p_lo * C;
-        const uint32_t e0 = px[0], e1 = px[1], e2 = px[2];
+        const uint4* sp = reinterpret_cast<const uint4*>(s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes + gq * (kGroupPx * C));
 #pragma unroll
-        for (int k = 0; k < kMaxPad; ++k) {
-          if (k < p_lo) { set_byte(src[f], 3 * k, e0); set_byte(src[f], 3 * k + 1, e1); set_byte(src[f], 3 * k + 2, e2); }
+        for (int q = 0; q < kSrcWords / 4; ++q) {
+          const uint4 v = sp[q];
+          src[f][4 * q + 0] = v.x; src[f][4 * q + 1] = v.y; src[f][4 * q + 2] = v.z; src[f][4 * q + 3] = v.w;
         }
       }
-    } else if (dx > 0 && gq == groups - 1) {
-      const int p_hi = kGroupPx - 1 - dx;            // last in-image pixel, local index within the last group
+    } else {
+      // x shift: the 48-byte window starts 3*dx bytes off the group boundary -> 13 words + a funnel shift.
+      // Word indices are clamped into the row; bytes fetched through a clamped index only ever belong to
+      // out-of-image pixels, which the edge patch below overwrites.
+      const int o = gq * (kGroupPx * C) + C * dx;
+      const int w0 = o >> 2;                         // floor(o / 4), also for negative o
+      const uint32_t sh8 = (uint32_t)(o & 3) * 8u;
+      const int last_word = (row_bytes >> 2) - 1;
 #pragma unroll
       for (int f = 0; f < FS; ++f) {
-        const uint8_t* px = s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes + (gq * kGroupPx + p_hi) * C;
-        const uint32_t e0 = px[0], e1 = px[1], e2 = px[2];
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes);
+        uint32_t w[kSrcWords + 1];
 #pragma unroll
-        for (int k = 0; k < kMaxPad; ++k) {
-          const int q = kGroupPx - 1 - k;
-          if (q > p_hi) { set_byte(src[f], 3 * q, e0); set_byte(src[f], 3 * q + 1, e1); set_byte(src[f], 3 * q + 2, e2); }
+        for (int k = 0; k <= kSrcWords; ++k) w[k] = rowp[min(max(w0 + k, 0), last_word)];
+#pragma unroll
+        for (int k = 0; k < kSrcWords; ++k) src[f][k] = __funnelshift_r(w[k], w[k + 1], sh8);
+      }
+      // edge replication in x: only the first group (dx < 0) or the last group (dx > 0) has out-of-image pixels
+      if (dx < 0 && gq == 0) {
+#pragma unroll
+        for (int f = 0; f < FS; ++f) {
+          const uint8_t* px = s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes;   // source pixel 0
+          const uint32_t e0 = px[0], e1 = px[1], e2 = px[2];
+#pragma unroll
+          for (int k = 0; k < kMaxPad; ++k) {
+            if (k < -dx) { set_byte(src[f], 3 * k, e0); set_byte(src[f], 3 * k + 1, e1); set_byte(src[f], 3 * k + 2, e2); }
+          }
+        }
+      } else if (dx > 0 && gq == groups - 1) {
+#pragma unroll
+        for (int f = 0; f < FS; ++f) {
+          const uint8_t* px = s_in + (size_t)f * band_bytes + (size_t)rc * row_bytes + (p.W - 1) * C;  // source pixel W-1
+          const uint32_t e0 = px[0], e1 = px[1], e2 = px[2];
+#pragma unroll
+          for (int k = 0; k < kMaxPad; ++k) {
+            const int q = kGroupPx - 1 - k;
+            if (k < dx) { set_byte(src[f], 3 * q, e0); set_byte(src[f], 3 * q + 1, e1); set_byte(src[f], 3 * q + 2, e2); }
+          }
         }
       }
     }
