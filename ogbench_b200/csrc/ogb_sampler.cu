@@ -234,6 +234,11 @@ struct ogb_sampler {
   std::vector<KeyPlan> plan[2];  // [evaluation]
   std::map<std::pair<int, int>, CUtensorMap> tmaps;  // (field, band_rows) -> descriptor
   std::mutex mu;
+  // Batch blocks are recycled through this small per-sampler cache instead of going back to the driver: a block
+  // released by the consumer is handed to a later sample() on the same stream (stream order makes that safe).
+  std::mutex cache_mu;
+  std::vector<std::pair<size_t, uint8_t*>> block_cache;
+  size_t cache_bytes = 0;
 };
 
 struct ogb_batch {
@@ -258,6 +263,61 @@ struct ogb_batch {
 
 namespace {
 
+constexpr size_t kMaxCachedBlocks = 6;
+
+size_t block_size_class(size_t bytes) {  // round up to 1/8-octave steps so that similar requests share blocks
+  size_t cls = 4096;
+  while (cls < bytes) cls <<= 1;
+  const size_t step = cls / 16;
+  return step == 0 ? cls : (bytes + step - 1) / step * step;
+}
+
+int block_take(ogb_sampler* s, size_t bytes, uint8_t** out, size_t* out_bytes) {
+  const size_t want = block_size_class(bytes);
+  {
+    std::lock_guard<std::mutex> lock(s->cache_mu);
+    for (size_t i = 0; i < s->block_cache.size(); ++i)
+      if (s->block_cache[i].first == want) {
+        *out = s->block_cache[i].second;
+        *out_bytes = want;
+        s->cache_bytes -= want;
+        s->block_cache.erase(s->block_cache.begin() + (long)i);
+        return 0;
+      }
+  }
+  cudaError_t e = cudaMalloc((void**)out, want);
+  if (e != cudaSuccess) {  // drop the cache and retry once before giving up
+    std::vector<std::pair<size_t, uint8_t*>> drop;
+    {
+      std::lock_guard<std::mutex> lock(s->cache_mu);
+      drop.swap(s->block_cache);
+      s->cache_bytes = 0;
+    }
+    cudaGetLastError();
+    cudaStreamSynchronize(s->stream);
+    for (auto& blk : drop) cudaFree(blk.second);
+    e = cudaMalloc((void**)out, want);
+  }
+  if (e != cudaSuccess) { *out = nullptr; return fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for a batch block: %s", want, cudaGetErrorString(e)); }
+  *out_bytes = want;
+  return 0;
+}
+
+void block_give(ogb_sampler* s, uint8_t* block, size_t bytes) {
+  uint8_t* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(s->cache_mu);
+    s->block_cache.emplace_back(bytes, block);
+    s->cache_bytes += bytes;
+    if (s->block_cache.size() > kMaxCachedBlocks) {
+      evict = s->block_cache.front().second;
+      s->cache_bytes -= s->block_cache.front().first;
+      s->block_cache.erase(s->block_cache.begin());
+    }
+  }
+  if (evict) { cudaStreamSynchronize(s->stream); cudaFree(evict); }
+}
+
 void dataset_unref(ogb_dataset* ds) {
   if (ds->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(ds->device);
@@ -271,7 +331,9 @@ void dataset_unref(ogb_dataset* ds) {
 void sampler_unref(ogb_sampler* s) {
   if (s->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(s->ds->device);
-  if (s->owns_stream && s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (auto& blk : s->block_cache) cudaFree(blk.second);
+  if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
   if (s->d_term) cudaFree(s->d_term);
   if (s->d_term_bucket) cudaFree(s->d_term_bucket);
   if (s->d_neg_lut) cudaFree(s->d_neg_lut);
@@ -293,7 +355,7 @@ void batch_unref(ogb_batch* b) {
       cudaEventDestroy(ev);
     }
   }
-  if (b->block) cudaFreeAsync(b->block, s->stream);
+  if (b->block) block_give(s, b->block, b->block_bytes);
   if (b->ready) cudaEventDestroy(b->ready);
   delete b;
   sampler_unref(s);
@@ -709,7 +771,8 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
 int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   std::lock_guard<std::mutex> lock(s->mu);
-  if (s->owns_stream && s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks may still be in flight on the old stream
+  if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
   s->stream = (cudaStream_t)cuda_stream;
   s->owns_stream = false;
   return 0;
@@ -753,14 +816,14 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   using namespace ogb;
   if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
   if (batch_size < 1 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size and n_batches must be >= 1");
-  if ((draws || idxs) && n_batches != 1) return fail(OGB_ERR_INVALID, "validation draws / explicit idxs need n_batches == 1");
+  if (draws && n_batches != 1) return fail(OGB_ERR_INVALID, "validation draws need n_batches == 1");
   const ogb_dataset* ds = s->ds;
   const ogb_config& cfg = s->cfg;
   const int64_t total = batch_size * (int64_t)n_batches;
   if (total > (int64_t)1 << 31) return fail(OGB_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
   const bool stacked_next = cfg.frame_stack > 0 && s->kind != OGB_KIND_PLAIN;
   if (idxs) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
-    for (int64_t r = 0; r < batch_size; ++r)
+    for (int64_t r = 0; r < total; ++r)
       if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + 1 >= ds->size))
         return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
   }
@@ -792,7 +855,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   const std::vector<KeyPlan>& plan = s->plan[evaluation ? 1 : 0];
   bool any_frames = false;
   for (const KeyPlan& k : plan) any_frames |= (k.route == ROUTE_FRAMES && k.alias_of < 0);
-  const bool want_vecs = any_frames || s->debug;
+  const bool want_crop = any_frames;
   const bool want_init = any_frames && cfg.frame_stack > 1;
 
   // ---- lay out the single device block: keys first (so one D2H copy takes the whole batch), then scratch ----
@@ -816,10 +879,10 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   b->keys_bytes = cursor;
   auto carve = [&](size_t bytes) { size_t off = cursor; cursor = round_up(cursor + bytes, 256); return off; };
   size_t off_rows = 0, off_init = 0, off_crop = 0, off_idxs = 0, off_draw_i64[1 + 3 * 2 + 1] = {0}, off_draw_f64[3 * 3] = {0};
-  if (want_vecs) off_rows = carve((size_t)s->n_slots * total * 4);
+  off_rows = carve((size_t)s->n_slots * total * 4);
   if (want_init) off_init = carve((size_t)s->n_slots * total * 4);
-  if (want_vecs) off_crop = carve((size_t)total * 2);
-  if (idxs) off_idxs = carve((size_t)batch_size * 8);
+  if (want_crop) off_crop = carve((size_t)total * 2);
+  if (idxs) off_idxs = carve((size_t)total * 8);
   if (draws) {
     off_draw_i64[0] = carve((size_t)batch_size * 8);
     for (int gs = 0; gs < 3; ++gs) {
@@ -832,11 +895,12 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   b->block_bytes = std::max<size_t>(cursor, 256);
   auto bail = [&](int code) { batch_unref(b); return code; };
   {
-    cudaError_t e = cudaMallocAsync((void**)&b->block, b->block_bytes, s->stream);
-    if (e != cudaSuccess) { b->block = nullptr; return bail(fail(OGB_ERR_CUDA, "cudaMallocAsync(%zu): %s", b->block_bytes, cudaGetErrorString(e))); }
+    int rc = block_take(s, b->block_bytes, &b->block, &b->block_bytes);
+    if (rc) return bail(rc);
   }
   uint8_t* base = b->block;
-  if (want_vecs) { b->vec_rows = (int32_t*)(base + off_rows); b->crop = (int8_t*)(base + off_crop); }
+  b->vec_rows = (int32_t*)(base + off_rows);
+  if (want_crop) b->crop = (int8_t*)(base + off_crop);
   if (want_init) b->vec_init = (int32_t*)(base + off_init);
 
   // ---- parameters of the fused index + row-gather kernel ----
@@ -888,7 +952,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
     return cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, s->stream);
   };
   if (idxs) {
-    if (h2d(off_idxs, idxs, (size_t)batch_size * 8) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of idxs failed"));
+    if (h2d(off_idxs, idxs, (size_t)total * 8) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of idxs failed"));
     p.given_idxs = (const int64_t*)(base + off_idxs);
   }
   if (draws) {
@@ -925,48 +989,78 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       default: break;
     }
   }
-  // tile size: big tiles amortise phase 1, but a single small batch should still spread over the SMs
-  int tile_rows = 128;
-  while (tile_rows > 32 && (total + tile_rows - 1) / tile_rows < 2 * (int64_t)ds->sm_count) tile_rows >>= 1;
-  p.tile_rows = tile_rows;
-  const int64_t n_tiles = (total + tile_rows - 1) / tile_rows;
-  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ds->sm_count * 8);
-
-  std::vector<size_t> row_keys;
-  for (size_t i = 0; i < plan.size(); ++i)
-    if (plan[i].route == ROUTE_ROW && plan[i].alias_of < 0) row_keys.push_back(i);
-  size_t done = 0;
-  do {  // normally one launch; more only if a dataset has > kMaxRowJobs vector fields
-    p.n_jobs = 0;
-    p.total_items = 0;
-    p.item_start[0] = 0;
-    while (done < row_keys.size() && p.n_jobs < kMaxRowJobs) {
-      const KeyPlan& k = plan[row_keys[done++]];
-      const Field& f = ds->fields[(size_t)k.field];
-      RowJob& job = p.jobs[p.n_jobs];
-      job.src = f.dptr;
-      job.dst = base + b->offsets[row_keys[done - 1]];
-      job.src_stride = (uint32_t)f.stride;
-      job.row_bytes = (uint32_t)f.row_bytes;
-      int v = largest_vec_log2(f.row_bytes, f.stride);
-      if ((f.row_bytes >> v) > 65535) return bail(fail(OGB_ERR_UNSUPPORTED, "row of field '%s' too long for the row path", f.name.c_str()));
-      job.vec_log2 = (uint8_t)v;
-      job.epr = (uint16_t)(f.row_bytes >> v);
-      int lpr = 0;
-      while ((1 << lpr) < job.epr && lpr < 5) ++lpr;
-      job.lpr_log2 = (uint8_t)lpr;
-      job.n_coliter = (uint16_t)((job.epr + (1 << lpr) - 1) >> lpr);
-      job.slot = (uint8_t)k.slot;
-      const int rows_per_pass = 32 >> lpr;
-      const int n_pass = (tile_rows + rows_per_pass - 1) / rows_per_pass;
-      p.total_items += n_pass * job.n_coliter;
-      p.item_start[++p.n_jobs] = p.total_items;
-    }
-    if (draws) relabel_rows_kernel<true><<<grid, kRelabelThreads, 0, s->stream>>>(p);
-    else relabel_rows_kernel<false><<<grid, kRelabelThreads, 0, s->stream>>>(p);
-    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "relabel_rows_kernel launch failed"));
+  {  // ---- launch 1: index algebra + scalar keys ----
+    const unsigned grid = (unsigned)std::min<int64_t>((total + kRelabelThreads - 1) / kRelabelThreads, (int64_t)ds->sm_count * 16);
+    if (draws) relabel_index_kernel<true><<<grid, kRelabelThreads, 0, s->stream>>>(p);
+    else relabel_index_kernel<false><<<grid, kRelabelThreads, 0, s->stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "relabel_index_kernel launch failed"));
     b->launches++;
-  } while (done < row_keys.size());
+  }
+
+  // ---- launch 2: row gathers of every vector-valued key.  One launch per element width in use; a width class that
+  // carries little of the traffic is folded into the next narrower one to save the launch. ----
+  {
+    std::vector<size_t> row_keys;
+    for (size_t i = 0; i < plan.size(); ++i)
+      if (plan[i].route == ROUTE_ROW && plan[i].alias_of < 0) row_keys.push_back(i);
+    std::vector<int> vec_of(row_keys.size());
+    size_t bytes_by_vec[5] = {0, 0, 0, 0, 0}, bytes_all = 0;
+    for (size_t q = 0; q < row_keys.size(); ++q) {
+      const Field& f = ds->fields[(size_t)plan[row_keys[q]].field];
+      vec_of[q] = largest_vec_log2(f.row_bytes, f.stride);
+      bytes_by_vec[vec_of[q]] += f.row_bytes;
+      bytes_all += f.row_bytes;
+    }
+    for (int v = 4; v > 0; --v) {  // fold light classes downwards
+      if (bytes_by_vec[v] == 0 || bytes_by_vec[v] * 2 >= bytes_all) continue;
+      int lower = v - 1;
+      while (lower > 0 && bytes_by_vec[lower] == 0) --lower;
+      if (bytes_by_vec[lower] == 0) continue;
+      for (size_t q = 0; q < row_keys.size(); ++q)
+        if (vec_of[q] == v) vec_of[q] = lower;
+      bytes_by_vec[lower] += bytes_by_vec[v];
+      bytes_by_vec[v] = 0;
+    }
+    const int64_t n_warp_tiles = (total + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + 7) / 8, (int64_t)ds->sm_count * 32);
+    for (int v = 4; v >= 0; --v) {
+      size_t q = 0;
+      while (q < row_keys.size()) {
+        GatherParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.vec_rows = b->vec_rows;
+        gp.total_rows = total;
+        for (; q < row_keys.size() && gp.n_jobs < kMaxRowJobs; ++q) {
+          if (vec_of[q] != v) continue;
+          const KeyPlan& k = plan[row_keys[q]];
+          const Field& f = ds->fields[(size_t)k.field];
+          if ((f.row_bytes >> v) > 65535) return bail(fail(OGB_ERR_UNSUPPORTED, "row of field '%s' too long for the row path", f.name.c_str()));
+          RowJob& job = gp.jobs[gp.n_jobs++];
+          job.src = f.dptr;
+          job.dst = base + b->offsets[row_keys[q]];
+          job.src_stride = (uint32_t)f.stride;
+          job.row_bytes = (uint32_t)f.row_bytes;
+          job.vec_log2 = (uint8_t)v;
+          job.epr = (uint16_t)(f.row_bytes >> v);
+          int lpr = 0;
+          while ((1 << lpr) < job.epr && lpr < 5) ++lpr;
+          job.lpr_log2 = (uint8_t)lpr;
+          job.n_coliter = (uint16_t)((job.epr + (1 << lpr) - 1) >> lpr);
+          job.slot = (uint8_t)k.slot;
+        }
+        if (gp.n_jobs == 0) break;
+        switch (v) {
+          case 4: gather_rows_kernel<uint4><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
+          case 3: gather_rows_kernel<uint2><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
+          case 2: gather_rows_kernel<uint32_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
+          case 1: gather_rows_kernel<uint16_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
+          default: gather_rows_kernel<uint8_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
+        }
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_rows_kernel launch failed"));
+        b->launches++;
+      }
+    }
+  }
 
   // ---- image keys: frame stacking + crop fused into the gather ----
   if (any_frames) {
@@ -1107,7 +1201,6 @@ int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes
 }
 int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
-  if (!b->vec_rows) return fail(OGB_ERR_INVALID, "index vectors were not kept (ogb_sampler_set_debug)");
   if (slot < 0 || slot >= b->n_slots) return fail(OGB_ERR_INVALID, "bad slot");
   std::vector<int32_t> tmp((size_t)b->total_rows);
   OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
@@ -1118,7 +1211,7 @@ int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {
 }
 int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
-  if (!b->crop) return fail(OGB_ERR_INVALID, "crop shifts were not kept (ogb_sampler_set_debug)");
+  if (!b->crop) return fail(OGB_ERR_INVALID, "this batch has no image keys, hence no crop shifts");
   std::vector<int8_t> tmp((size_t)b->total_rows * 2);
   OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
   OGB_CUDA(cudaMemcpyAsync(tmp.data(), b->crop, tmp.size(), cudaMemcpyDeviceToHost, b->sampler->stream));

@@ -1,11 +1,14 @@
-// relabel_rows_kernel -- the fused hot path for vector-valued fields.
+// The index kernel and the row-gather kernel of the replay sampler.
 //
-// One CTA owns a tile of consecutive batch rows.  Phase 1 (one thread per row) restates the reference's per-row
-// index algebra (impls/utils/datasets.py:296-327 sample_goals, :478-491 compute_high_next_idxs, :250-252 and
-// :533-582 rewards/masks) from either injected draws (validation mode) or Philox draws,
-// and leaves every index vector of the tile in shared memory.  Phase 2 (whole CTA, warp-per-row-group) gathers
-// the dataset rows those vectors name (datasets.py:78-83 get_subset, :341-357 get_observations /
-// get_goal_observations) into the dense output arrays.  Nothing but the final batch is written to HBM.
+// relabel_index_kernel (one thread per batch row) restates the reference's per-row index algebra
+// (impls/utils/datasets.py:296-327 sample_goals, :478-491 compute_high_next_idxs, :250-252 and :533-582
+// rewards/masks) from either injected draws (validation mode) or Philox draws.  It writes the
+// scalar keys (masks, rewards, offsets, steps) and one int32 row-index vector per slot.
+//
+// gather_rows_kernel<V> (one warp per 32 batch rows) gathers the dataset rows those vectors name
+// (datasets.py:78-83 get_subset, :341-357 get_observations / get_goal_observations) into the dense output arrays.
+// The two are separate launches so that the gather runs at its own (high) occupancy: the index vectors are
+// 4 bytes per row and slot and stay in L2 between the launches.
 #pragma once
 #include "device_common.cuh"
 
@@ -14,8 +17,6 @@ namespace ogb {
 constexpr int kMaxSlots = 10;
 constexpr int kMaxRowJobs = 24;
 constexpr int kRelabelThreads = 256;
-constexpr int kMaxTileRows = 256;
-constexpr int kGatherUnroll = 4;
 
 // index-vector slots
 enum : int {
@@ -89,8 +90,8 @@ struct RelabelParams {
   // ---- launch shape ----
   int64_t batch;               // rows per sample() call
   int64_t total_rows;          // batch * n_batches
-  int32_t tile_rows;
   int32_t n_slots;
+  int32_t pad0_;
   // ---- scalar outputs (float64 / int64 like the reference) ----
   double* masks;
   double* rewards;
@@ -101,15 +102,10 @@ struct RelabelParams {
   double* hv_rewards;
   double* lv_masks;
   double* lv_rewards;
-  // ---- optional index outputs for the frame kernels / debug: [slot][total_rows] ----
-  int32_t* vec_rows;
-  int32_t* vec_init;
-  int8_t* crop_out;            // [total_rows][2] (dy, dx) or -128 when the batch is not augmented
-  // ---- row gathers ----
-  int32_t n_jobs;
-  int32_t total_items;
-  int32_t item_start[kMaxRowJobs + 1];
-  RowJob jobs[kMaxRowJobs];
+  // ---- index outputs: [slot][total_rows] ----
+  int32_t* vec_rows;           // row index vectors, consumed by the gather kernels
+  int32_t* vec_init;           // first row of each row's trajectory segment (frame stacking only; may be null)
+  int8_t* crop_out;            // [total_rows][2] (dy, dx) or -128 when the batch is not augmented (may be null)
 };
 
 __device__ __forceinline__ int32_t valid_row(const RelabelParams& p, int64_t pos) {
@@ -170,171 +166,198 @@ __device__ __forceinline__ int32_t trajectory_first_row(const RelabelParams& p, 
   return t == 0 ? 0 : __ldg(p.term + t - 1) + 1;
 }
 
+__device__ __forceinline__ void put_slot(const RelabelParams& p, const int slot, const int64_t g, const int32_t x) {
+  p.vec_rows[(int64_t)slot * p.total_rows + g] = x;
+  if (p.vec_init != nullptr) p.vec_init[(int64_t)slot * p.total_rows + g] = trajectory_first_row(p, x);
+}
+
 template <bool kInject>
-__global__ void __launch_bounds__(kRelabelThreads) relabel_rows_kernel(const __grid_constant__ RelabelParams p) {
-  __shared__ int32_t s_row[kMaxSlots][kMaxTileRows];
-  const int tile_rows = p.tile_rows;
-  const int64_t n_tiles = (p.total_rows + tile_rows - 1) / tile_rows;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+__global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.total_rows; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t kb = g / p.batch;
+    const uint32_t r = (uint32_t)(g - kb * p.batch);
+    const uint64_t batch_id = p.batch0 + (uint64_t)kb;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t g0 = tile * tile_rows;
-    const int n = (int)((p.total_rows - g0) < tile_rows ? (p.total_rows - g0) : tile_rows);
+    uint4 w0 = make_uint4(0, 0, 0, 0);
+    if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
+    int32_t i;
+    if (p.given_idxs != nullptr) {
+      i = (int32_t)p.given_idxs[g];
+    } else {
+      const int64_t pos = kInject ? p.in_idx_pos[g] : bounded_u64(w0.x, w0.y, (uint64_t)p.n_choices);
+      i = valid_row(p, pos);                                            // datasets.py:65-70
+    }
+    put_slot(p, SLOT_IDX, g, i);
+    const int32_t nxt = p.stacked_next ? i + 1 : (i + 1 < p.n_rows_ds ? i + 1 : p.n_rows_ds - 1);  // :82 / :231
+    put_slot(p, SLOT_NEXT, g, nxt);
 
-    // ------------------------------- phase 1: per-row index algebra -------------------------------
-    if ((int)threadIdx.x < n) {
-      const int t = threadIdx.x;
-      const int64_t g = g0 + t;
-      const int64_t kb = g / p.batch;
-      const uint32_t r = (uint32_t)(g - kb * p.batch);
-      const uint64_t batch_id = p.batch0 + (uint64_t)kb;
-
-      uint4 w0 = make_uint4(0, 0, 0, 0);
-      if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
-      int32_t i;
-      if (p.given_idxs != nullptr) {
-        i = (int32_t)p.given_idxs[g];
+    if (p.kind != 2) {
+      const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
+      const int32_t fin = __ldg(p.term + tl);                            // final_state_idxs  :306,:505
+      const double neg = p.gc_negative ? 1.0 : 0.0;
+      if (p.kind == 0) {
+        const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);
+        const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);
+        put_slot(p, GC_VALUE_GOAL, g, vg);
+        put_slot(p, GC_ACTOR_GOAL, g, ag);
+        const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
+        p.masks[g] = 1.0 - succ;
+        p.rewards[g] = succ - neg;
       } else {
-        const int64_t pos = kInject ? p.in_idx_pos[g] : bounded_u64(w0.x, w0.y, (uint64_t)p.n_choices);
-        i = valid_row(p, pos);                                            // datasets.py:65-70
+        const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);          // :508-514
+        int32_t hv_next, hv_s, lv_next, lv_s;
+        subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
+        subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
+        put_slot(p, HGC_HV_GOAL, g, hv);
+        put_slot(p, HGC_HV_NEXT, g, hv_next);
+        put_slot(p, HGC_LV_NEXT, g, lv_next);
+        p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
+        p.hv_steps[g] = hv_s;
+        p.lv_steps[g] = lv_s;
+        const double hv_succ = hv_s < p.k_val ? 1.0 : 0.0;                            // :533
+        const double lv_succ = lv_s < p.k_lo ? 1.0 : 0.0;                             // :552
+        p.hv_masks[g] = 1.0 - hv_succ;
+        p.hv_rewards[g] = p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ);
+        double lv_mask = 1.0 - lv_succ;
+        double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
+        if (p.has_low_goal) {                                                         // :563-576
+          const int32_t lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g);
+          put_slot(p, HGC_LV_GOAL, g, lvg);
+          const double s = (i == lvg) ? 1.0 : 0.0;
+          lv_mask = 1.0 - s;
+          lv_rew = s - neg;
+        }
+        p.lv_masks[g] = lv_mask;
+        p.lv_rewards[g] = lv_rew;
+        const double succ = (i == hv) ? 1.0 : 0.0;                                    // :579-582
+        p.masks[g] = 1.0 - succ;
+        p.rewards[g] = succ - neg;
+        const int32_t ha = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);          // :585-591
+        int32_t ha_next, la_next, unused;
+        subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
+        subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
+        const int64_t la = (int64_t)i + p.k_act;                                      // :610
+        put_slot(p, HGC_HA_GOAL, g, ha);
+        put_slot(p, HGC_HA_NEXT, g, ha_next);
+        put_slot(p, HGC_LA_GOAL, g, (int32_t)(la < (int64_t)fin ? la : (int64_t)fin));
+        put_slot(p, HGC_LA_NEXT, g, la_next);
       }
-      s_row[SLOT_IDX][t] = i;
-      const int32_t nxt = p.stacked_next ? i + 1 : (i + 1 < p.n_rows_ds ? i + 1 : p.n_rows_ds - 1);  // :82 / :231
-      s_row[SLOT_NEXT][t] = nxt;
+    }
 
-      if (p.kind != 2) {
-        const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
-        const int32_t fin = __ldg(p.term + tl);                            // final_state_idxs  :306,:505
-        const double neg = p.gc_negative ? 1.0 : 0.0;
-        if (p.kind == 0) {
-          const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);
-          const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);
-          s_row[GC_VALUE_GOAL][t] = vg;
-          s_row[GC_ACTOR_GOAL][t] = ag;
-          const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
-          p.masks[g] = 1.0 - succ;
-          p.rewards[g] = succ - neg;
+    if (p.crop_out != nullptr) {
+      int dy = -128, dx = -128;
+      if (p.aug_mode) {                                                               // :278-279, :621-622
+        double coin;
+        if (kInject) {
+          coin = p.in_coin;
         } else {
-          const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);          // :508-514
-          int32_t hv_next, hv_s, lv_next, lv_s;
-          subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
-          subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
-          s_row[HGC_HV_GOAL][t] = hv;
-          s_row[HGC_HV_NEXT][t] = hv_next;
-          s_row[HGC_LV_NEXT][t] = lv_next;
-          p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
-          p.hv_steps[g] = hv_s;
-          p.lv_steps[g] = lv_s;
-          const double hv_succ = hv_s < p.k_val ? 1.0 : 0.0;                            // :533
-          const double lv_succ = lv_s < p.k_lo ? 1.0 : 0.0;                             // :552
-          p.hv_masks[g] = 1.0 - hv_succ;
-          p.hv_rewards[g] = p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ);
-          double lv_mask = 1.0 - lv_succ;
-          double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
-          int32_t lvg = i;
-          if (p.has_low_goal) {                                                         // :563-576
-            lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g);
-            const double s = (i == lvg) ? 1.0 : 0.0;
-            lv_mask = 1.0 - s;
-            lv_rew = s - neg;
-          }
-          s_row[HGC_LV_GOAL][t] = lvg;
-          p.lv_masks[g] = lv_mask;
-          p.lv_rewards[g] = lv_rew;
-          const double succ = (i == hv) ? 1.0 : 0.0;                                    // :579-582
-          p.masks[g] = 1.0 - succ;
-          p.rewards[g] = succ - neg;
-          const int32_t ha = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);          // :585-591
-          int32_t ha_next, la_next, unused;
-          subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
-          subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
-          const int64_t la = (int64_t)i + p.k_act;                                      // :610
-          s_row[HGC_HA_GOAL][t] = ha;
-          s_row[HGC_HA_NEXT][t] = ha_next;
-          s_row[HGC_LA_GOAL][t] = (int32_t)(la < (int64_t)fin ? la : (int64_t)fin);
-          s_row[HGC_LA_NEXT][t] = la_next;
+          const uint4 c = draw4(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
+          coin = unit_double(c.x, c.y);
+        }
+        if (coin < p.p_aug) {                                                         // :333
+          const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
+          const int cy = kInject ? (int)p.in_crop[2 * g] : (int)__umulhi(w0.z, span);
+          const int cx = kInject ? (int)p.in_crop[2 * g + 1] : (int)__umulhi(w0.w, span);
+          dy = cy - p.crop_pad;
+          dx = cx - p.crop_pad;
         }
       }
-
-      if (p.vec_rows != nullptr) {
-        for (int v = 0; v < p.n_slots; ++v) {
-          const int32_t x = s_row[v][t];
-          p.vec_rows[(int64_t)v * p.total_rows + g] = x;
-          if (p.vec_init != nullptr) p.vec_init[(int64_t)v * p.total_rows + g] = trajectory_first_row(p, x);
-        }
-      }
-      if (p.crop_out != nullptr) {
-        int dy = -128, dx = -128;
-        if (p.aug_mode) {                                                               // :278-279, :621-622
-          double coin;
-          if (kInject) {
-            coin = p.in_coin;
-          } else {
-            const uint4 c = draw4(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
-            coin = unit_double(c.x, c.y);
-          }
-          if (coin < p.p_aug) {                                                         // :333
-            const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
-            const int cy = kInject ? (int)p.in_crop[2 * g] : (int)__umulhi(w0.z, span);
-            const int cx = kInject ? (int)p.in_crop[2 * g + 1] : (int)__umulhi(w0.w, span);
-            dy = cy - p.crop_pad;
-            dx = cx - p.crop_pad;
-          }
-        }
-        p.crop_out[2 * g] = (int8_t)dy;
-        p.crop_out[2 * g + 1] = (int8_t)dx;
-      }
+      p.crop_out[2 * g] = (int8_t)dy;
+      p.crop_out[2 * g + 1] = (int8_t)dx;
     }
-    __syncthreads();
+  }
+}
 
-    // ------------------------------- phase 2: row gathers -------------------------------
-    // An "item" is one warp-wide access: 32 >> lpr_log2 rows x (1 << lpr_log2) elements.  Items of all jobs are
-    // one flat list; every warp issues kGatherUnroll independent loads before the matching stores.
-    for (int it0 = warp; it0 < p.total_items; it0 += n_warps * kGatherUnroll) {
-      uint4 val[kGatherUnroll];
-      uint8_t* dptr[kGatherUnroll];
-      int vlog[kGatherUnroll];
+// ---------------------------------------------------------------------------------------------------------
+// Row gather.  Each warp owns 32 consecutive batch rows and walks the job list; lane l holds the source row of
+// batch row l for the current job and broadcasts it with a shuffle.  A warp-wide access covers 32 >> lpr_log2
+// rows of (1 << lpr_log2) elements (short rows) or one 32-element slice of one row (long rows).  Every warp
+// issues kU independent loads before the matching stores so that enough bytes are in flight to cover HBM
+// latency; there is no block-level synchronisation at all.
+// ---------------------------------------------------------------------------------------------------------
+struct GatherParams {
+  const int32_t* vec_rows;     // [slot][total_rows]
+  int64_t total_rows;
+  int32_t n_jobs;
+  RowJob jobs[kMaxRowJobs];
+};
+
+template <typename V>
+__device__ __forceinline__ V load_stream(const V* p) { return __ldg(p); }
+
+template <typename V>
+__global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __grid_constant__ GatherParams p) {
+  constexpr int kU = sizeof(V) >= 16 ? 4 : 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps_global = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_warp_tiles = (p.total_rows + 31) >> 5;
+
+#pragma unroll 1
+  for (int64_t wt = warp_global; wt < n_warp_tiles; wt += n_warps_global) {
+    const int64_t g0 = wt << 5;
+    const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+#pragma unroll 1
+    for (int j = 0; j < p.n_jobs; ++j) {
+      const RowJob& job = p.jobs[j];
+      const uint8_t* __restrict__ src = job.src;
+      uint8_t* __restrict__ dst = job.dst + (size_t)g0 * job.row_bytes;
+      const uint32_t stride = job.src_stride, row_bytes = job.row_bytes;
+      const int epr = job.epr;
+      const int32_t my_row = lane < n ? __ldg(p.vec_rows + (int64_t)job.slot * p.total_rows + g0 + lane) : 0;
+      if (job.n_coliter == 1) {
+        const int lpr_log2 = job.lpr_log2;
+        const int sub = lane >> lpr_log2;                       // row within the pass
+        const int col = lane & ((1 << lpr_log2) - 1);
+        const int rpp_log2 = 5 - lpr_log2;
+        const int n_pass = (n + (1 << rpp_log2) - 1) >> rpp_log2;
+        const bool col_ok = col < epr;
+#pragma unroll 1
+        for (int pass0 = 0; pass0 < n_pass; pass0 += kU) {
+          V val[kU];
 #pragma unroll
-      for (int u = 0; u < kGatherUnroll; ++u) {
-        vlog[u] = -1;
-        const int it = it0 + u * n_warps;
-        if (it < p.total_items) {
-          int j = 0;
-          while (it >= p.item_start[j + 1]) ++j;  // warp-uniform
-          const RowJob& job = p.jobs[j];
-          const int local = it - p.item_start[j];
-          const int pass = job.n_coliter == 1 ? local : local / job.n_coliter;
-          const int ci = local - pass * job.n_coliter;
-          const int row = (pass << (5 - job.lpr_log2)) + (lane >> job.lpr_log2);
-          const int col = (ci << job.lpr_log2) + (lane & ((1 << job.lpr_log2) - 1));
-          if (row < n && col < job.epr) {
-            const int32_t src_row = s_row[job.slot][row];
-            const uint8_t* sp = job.src + (size_t)src_row * job.src_stride + ((size_t)col << job.vec_log2);
-            dptr[u] = job.dst + (size_t)(g0 + row) * job.row_bytes + ((size_t)col << job.vec_log2);
-            vlog[u] = job.vec_log2;
-            switch (job.vec_log2) {
-              case 4: val[u] = __ldg(reinterpret_cast<const uint4*>(sp)); break;
-              case 3: { const uint2 q = __ldg(reinterpret_cast<const uint2*>(sp)); val[u].x = q.x; val[u].y = q.y; } break;
-              case 2: val[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp)); break;
-              case 1: val[u].x = __ldg(reinterpret_cast<const uint16_t*>(sp)); break;
-              default: val[u].x = __ldg(sp); break;
-            }
+          for (int u = 0; u < kU; ++u) {
+            const int row = ((pass0 + u) << rpp_log2) + sub;
+            const int32_t src_row = __shfl_sync(0xffffffffu, my_row, row & 31);
+            if (col_ok && row < n) val[u] = load_stream(reinterpret_cast<const V*>(src + (size_t)src_row * stride) + col);
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int row = ((pass0 + u) << rpp_log2) + sub;
+            if (col_ok && row < n) reinterpret_cast<V*>(dst + (size_t)row * row_bytes)[col] = val[u];
           }
         }
-      }
+      } else {
+        // long rows: 2 rows x kU/2 column slices per sweep
+        constexpr int kRowsPerSweep = 2, kSlices = kU / kRowsPerSweep;
+        const int n_coliter = job.n_coliter;
+#pragma unroll 1
+        for (int row0 = 0; row0 < n; row0 += kRowsPerSweep) {
+          const uint8_t* sp[kRowsPerSweep];
 #pragma unroll
-      for (int u = 0; u < kGatherUnroll; ++u) {
-        switch (vlog[u]) {
-          case 4: *reinterpret_cast<uint4*>(dptr[u]) = val[u]; break;
-          case 3: *reinterpret_cast<uint2*>(dptr[u]) = make_uint2(val[u].x, val[u].y); break;
-          case 2: *reinterpret_cast<uint32_t*>(dptr[u]) = val[u].x; break;
-          case 1: *reinterpret_cast<uint16_t*>(dptr[u]) = (uint16_t)val[u].x; break;
-          case 0: *dptr[u] = (uint8_t)val[u].x; break;
-          default: break;
+          for (int rr = 0; rr < kRowsPerSweep; ++rr)
+            sp[rr] = src + (size_t)__shfl_sync(0xffffffffu, my_row, (row0 + rr) & 31) * stride;
+#pragma unroll 1
+          for (int c0 = 0; c0 < n_coliter; c0 += kSlices) {
+            V val[kRowsPerSweep][kSlices];
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerSweep; ++rr)
+#pragma unroll
+              for (int c = 0; c < kSlices; ++c) {
+                const int col = ((c0 + c) << 5) + lane;
+                if (row0 + rr < n && col < epr) val[rr][c] = load_stream(reinterpret_cast<const V*>(sp[rr]) + col);
+              }
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerSweep; ++rr)
+#pragma unroll
+              for (int c = 0; c < kSlices; ++c) {
+                const int col = ((c0 + c) << 5) + lane;
+                if (row0 + rr < n && col < epr) reinterpret_cast<V*>(dst + (size_t)(row0 + rr) * row_bytes)[col] = val[rr][c];
+              }
+          }
         }
       }
     }
-    __syncthreads();
   }
 }
 

@@ -287,7 +287,9 @@ class _Sampler:
             idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64)
             if idxs.ndim != 1:
                 raise ValueError('idxs must be one-dimensional')
-            batch_size = len(idxs)  # datasets.py:74-76,298: len(idxs) rules
+            if len(idxs) % int(n_batches) != 0:
+                raise ValueError('len(idxs) must be a multiple of n_batches')
+            batch_size = len(idxs) // int(n_batches)  # datasets.py:74-76,298: len(idxs) rules
             idx_ptr = idxs.ctypes.data_as(C.c_void_p)
             keep.append(idxs)
         c_draws = None
@@ -454,9 +456,10 @@ class GCDataset:
             draws = self._host_draws(batch_size, idxs, evaluation)
         return self._sampler.sample(batch_size, idxs, evaluation, draws)
 
-    def sample_many(self, num_batches, batch_size, evaluation=False):
-        """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis."""
-        return self._sampler.sample(batch_size, None, evaluation, None, n_batches=num_batches)
+    def sample_many(self, num_batches, batch_size, evaluation=False, idxs=None):
+        """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis.
+        `idxs` (optional, num_batches * batch_size rows) plays the role of sample()'s `idxs`."""
+        return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches)
 
     # ---- checkpointable sampler state: one integer ----
     def state_dict(self):

@@ -1,0 +1,106 @@
+"""Host-side logic that needs no GPU: sharding, the host draw schedule, synthetic layouts, Philox restatement."""
+
+import numpy as np
+import pytest
+
+from ogbench_b200 import sharding, synthetic
+from oracle import philox_np
+from oracle.replay_oracle import OracleSampler, trajectory_bounds
+from tests.golden.make_golden import ragged, toy_fields
+
+
+def test_shard_bounds_are_trajectory_aligned_and_cover():
+    lengths = ragged(3, 57, 2, 40)
+    fields = toy_fields(3, lengths, (4,), 2, np.float32)
+    n = len(fields['terminals'])
+    for world in (1, 2, 3, 8):
+        bounds = sharding.shard_bounds(fields['terminals'], world)
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        ends = set((np.cumsum(lengths) - 1).tolist())
+        for (a, b), (c, _) in zip(bounds, bounds[1:] + [(n, n)]):
+            assert b == c and b > a
+            assert (b - 1) in ends
+        sizes = [b - a for a, b in bounds]
+        assert max(sizes) - min(sizes) <= 2 * lengths.max()
+        for rank in range(world):
+            shard = sharding.take_shard(fields, rank, world)
+            terminal_locs, _ = trajectory_bounds(shard['terminals'])
+            assert terminal_locs[-1] == len(shard['terminals']) - 1  # each shard is a valid dataset (datasets.py:188)
+
+
+def test_shard_more_ranks_than_trajectories_raises():
+    fields = toy_fields(1, np.array([5, 6]), (2,), 2, np.float32)
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(fields['terminals'], 3)
+
+
+def test_synthetic_layout_matches_compact_loader():
+    w = synthetic.WORKLOADS['c2']
+    f = synthetic.host_fields(w, episodes=3)
+    t, v = f['terminals'], f['valids']
+    assert f['observations'].shape == (3 * 1001, 29) and f['actions'].shape == (3 * 1001, 8)
+    assert t.sum() == 6 and v.sum() == 3 * 1000
+    assert np.array_equal(np.nonzero(t)[0], [999, 1000, 2000, 2001, 3001, 3002])
+    assert np.array_equal(np.nonzero(v == 0)[0], [1000, 2001, 3002])
+
+
+def test_algorithmic_bytes_formulas():
+    """one source row read + one output row written per unique index vector, plus the small fields."""
+    def gc_bytes(d, a):
+        return (4 * d + a + 8) + (4 * d + a + 8 + 16)
+    assert gc_bytes(8, 8) == synthetic.WORKLOADS['c1'].bytes_per_transition
+    assert gc_bytes(116, 32) == synthetic.WORKLOADS['c2'].bytes_per_transition
+    assert gc_bytes(220, 20) == synthetic.WORKLOADS['c5'].bytes_per_transition
+    assert (7 * 276 + 84 + 8) + (7 * 276 + 84 + 8 + 3 * 8 + 6 * 8) == synthetic.WORKLOADS['c3'].bytes_per_transition
+    assert (10 * 12288 + 28) + (4 * 36864 + 20 + 8 + 16) == synthetic.WORKLOADS['c4'].bytes_per_transition
+
+
+def test_philox_known_answer():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    out = philox_np.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(x) for x in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    f = 0xFFFFFFFF
+    out = philox_np.philox4x32_10(f, f, f, f, f, f)
+    assert [int(x) for x in out] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    out = philox_np.philox4x32_10(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0)
+    assert [int(x) for x in out] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_philox_draws_feed_the_oracle():
+    lengths = ragged(5, 20, 2, 50)
+    fields = toy_fields(5, lengths, (3,), 2, np.float32)
+    from tests.golden.make_golden import cfg
+    from oracle.replay_oracle import DrawsSource
+
+    config = cfg()
+    o = OracleSampler(fields, config, 'gc')
+    n_choices = len(o.valid_table)
+    draws, _ = philox_np.philox_draws(7, 3, 11, 64, n_choices, [(0, True, 0.99, False), (2, False, 0.99, False)], True, 0.0)
+    src = DrawsSource(draws)
+    batch = o.sample(64, source=src)
+    assert src.exhausted()
+    assert batch['observations'].shape == (64, 3)
+    assert draws.idx_pos.min() >= 0 and draws.idx_pos.max() < n_choices
+    assert draws.goals[0].offset.min() >= 1
+    d2, _ = philox_np.philox_draws(7, 4, 11, 64, n_choices, [(0, True, 0.99, False), (2, False, 0.99, False)], True, 0.0)
+    assert not np.array_equal(d2.idx_pos, draws.idx_pos)  # another stream id -> another stream
+
+
+def test_host_draw_schedule_matches_reference_order():
+    """rng='numpy' consumes np.random exactly as the reference does: checked against the golden draw logs without a GPU."""
+    from ogbench_b200.datasets import GCDataset, HGCDataset, _HostDraws
+    from tests.golden_util import case_names, load_case
+    from oracle.refshim import DrawRecorder
+
+    for name in case_names():
+        case = load_case(name)
+        cls = GCDataset if case['kind'] == 'gc' else HGCDataset
+        shell = cls.__new__(cls)  # the draw schedule is pure host logic; bypass the device-backed constructor
+        shell.config = case['cfg']
+        shell._n_choices = int(np.sum(case['fields']['valids'] > 0)) if 'valids' in case['fields'] else len(case['fields']['terminals'])
+        np.random.seed(case['meta']['seed'])
+        with DrawRecorder() as rec:
+            shell._host_draws(case['B'], case['idxs'], case['evaluation'])
+        assert [k for k, _ in rec.log] == case['meta']['draw_kinds'], name
+        for (_, got), (_, want) in zip(rec.log, case['log']):
+            assert np.array_equal(got, want), name
