@@ -37,7 +37,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only whe
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--config', default='c2', help='workload key (c1..c5), SURVEY.md 8(d); c2 is the headline config')
@@ -248,9 +248,10 @@ def run_gpu_arm(args):
         return handle, n.value
 
     # ---- device-resident throughput ----
+    prev = None
     for _ in range(max(args.warmup, 3)):
         h, _ = launch()
-        del h
+        prev = h  # same hand-over pattern as the timed loop, so both recycled output blocks exist before timing
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -260,7 +261,6 @@ def run_gpu_arm(args):
     launches = 0
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        prev = None
         for a, b in per_launch:
             a.record(stream)
             h, n = launch()

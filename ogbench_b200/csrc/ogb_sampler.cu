@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -605,8 +606,9 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
     }
     f.row_bytes = row;
     if (row == 0) return bail(fail(OGB_ERR_INVALID, "field '%s' has empty rows", in.name));
-    // resident row stride: rows <= 32 B stay dense, longer rows start on a 32-byte sector boundary
-    f.stride = row <= 32 ? row : round_up(row, 32);
+    // resident row stride: rows <= 16 B stay dense (they are copied by the index kernel, one thread per row);
+    // longer rows start on a 32-byte sector boundary, which also makes them 16-byte cp.async sources
+    f.stride = row <= 16 ? row : round_up(row, 32);
     if (f.stride > 0xFFFFFFFFull) return bail(fail(OGB_ERR_UNSUPPORTED, "field '%s': row too large", in.name));
     const size_t dense_bytes = (size_t)size * row, padded_bytes = (size_t)size * f.stride;
     cudaError_t e = cudaMalloc((void**)&f.dptr, padded_bytes);
@@ -989,7 +991,32 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       default: break;
     }
   }
-  {  // ---- launch 1: index algebra + scalar keys ----
+  // ---- classify the vector-valued keys: tiny rows ride along in the index kernel, the rest go to a gather launch ----
+  std::vector<size_t> async_keys, lsu_keys;
+  p.n_tiny = 0;
+  {
+    static const char* force = getenv("OGB_GATHER");  // "lsu" forces the register-staged kernel (A/B measurements)
+    for (size_t i = 0; i < plan.size(); ++i) {
+      if (plan[i].route != ROUTE_ROW || plan[i].alias_of >= 0) continue;
+      const Field& f = ds->fields[(size_t)plan[i].field];
+      if (f.row_bytes <= 16 && p.n_tiny < kMaxTinyJobs) {
+        TinyJob& t = p.tiny[p.n_tiny++];
+        const int v = largest_vec_log2(f.row_bytes, f.row_bytes);
+        t.src = f.dptr;
+        t.dst = base + b->offsets[i];
+        t.slot = (uint8_t)plan[i].slot;
+        t.size_log2 = (uint8_t)v;
+        t.n_elem = (uint8_t)(f.row_bytes >> v);
+      } else if (f.row_bytes > 16 && f.stride <= (size_t)kAsyncMaxStride && !(force && strcmp(force, "lsu") == 0)) {
+        async_keys.push_back(i);
+      } else {
+        lsu_keys.push_back(i);
+      }
+    }
+  }
+  p.write_vecs = (!async_keys.empty() || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
+
+  {  // ---- launch 1: index algebra, scalar keys, tiny rows ----
     const unsigned grid = (unsigned)std::min<int64_t>((total + kRelabelThreads - 1) / kRelabelThreads, (int64_t)ds->sm_count * 16);
     if (draws) relabel_index_kernel<true><<<grid, kRelabelThreads, 0, s->stream>>>(p);
     else relabel_index_kernel<false><<<grid, kRelabelThreads, 0, s->stream>>>(p);
@@ -997,29 +1024,47 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
     b->launches++;
   }
 
-  // ---- launch 2: row gathers of every vector-valued key.  One launch per element width in use; a width class that
-  // carries little of the traffic is folded into the next narrower one to save the launch. ----
-  {
-    std::vector<size_t> row_keys;
-    for (size_t i = 0; i < plan.size(); ++i)
-      if (plan[i].route == ROUTE_ROW && plan[i].alias_of < 0) row_keys.push_back(i);
+  // ---- launch 2: asynchronous row gather (cp.async ring per warp), all element widths in one launch ----
+  for (size_t q = 0; q < async_keys.size();) {
+    AsyncGatherParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.vec_rows = b->vec_rows;
+    ap.total_rows = total;
+    ap.stage_bytes = 4096;
+    auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
+    for (; q < async_keys.size() && ap.n_jobs < kMaxRowJobs; ++q) {
+      const KeyPlan& k = plan[async_keys[q]];
+      const Field& f = ds->fields[(size_t)k.field];
+      AsyncJob& job = ap.jobs[ap.n_jobs++];
+      const int v = largest_vec_log2(f.row_bytes, 16);
+      job.src = f.dptr;
+      job.dst = base + b->offsets[async_keys[q]];
+      job.stride = (uint32_t)f.stride;
+      job.row_bytes = (uint32_t)f.row_bytes;
+      job.cpr = (uint32_t)((f.row_bytes + 15) / 16);
+      job.cpr_magic = magic(job.cpr);
+      job.epr = (uint32_t)(f.row_bytes >> v);
+      job.epr_magic = magic(job.epr);
+      job.rows_per_item = (uint16_t)std::min<size_t>(32, (size_t)ap.stage_bytes / f.stride);
+      job.vec_log2 = (uint8_t)v;
+      job.slot = (uint8_t)k.slot;
+    }
+    const size_t smem = (size_t)kAsyncWarps * kAsyncStages * ap.stage_bytes;
+    OGB_CUDA(cudaFuncSetAttribute(gather_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t n_warp_tiles = (total + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * 2);
+    gather_rows_async_kernel<<<grid, kAsyncWarps * 32, smem, s->stream>>>(ap);
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed"));
+    b->launches++;
+  }
+
+  // ---- launch 2b: register-staged gather for what the asynchronous kernel does not take (very long rows) ----
+  if (!lsu_keys.empty()) {
+    const std::vector<size_t>& row_keys = lsu_keys;
     std::vector<int> vec_of(row_keys.size());
-    size_t bytes_by_vec[5] = {0, 0, 0, 0, 0}, bytes_all = 0;
     for (size_t q = 0; q < row_keys.size(); ++q) {
       const Field& f = ds->fields[(size_t)plan[row_keys[q]].field];
       vec_of[q] = largest_vec_log2(f.row_bytes, f.stride);
-      bytes_by_vec[vec_of[q]] += f.row_bytes;
-      bytes_all += f.row_bytes;
-    }
-    for (int v = 4; v > 0; --v) {  // fold light classes downwards
-      if (bytes_by_vec[v] == 0 || bytes_by_vec[v] * 2 >= bytes_all) continue;
-      int lower = v - 1;
-      while (lower > 0 && bytes_by_vec[lower] == 0) --lower;
-      if (bytes_by_vec[lower] == 0) continue;
-      for (size_t q = 0; q < row_keys.size(); ++q)
-        if (vec_of[q] == v) vec_of[q] = lower;
-      bytes_by_vec[lower] += bytes_by_vec[v];
-      bytes_by_vec[v] = 0;
     }
     const int64_t n_warp_tiles = (total + 31) / 32;
     const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + 7) / 8, (int64_t)ds->sm_count * 32);

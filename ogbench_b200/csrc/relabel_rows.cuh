@@ -17,6 +17,7 @@ namespace ogb {
 constexpr int kMaxSlots = 10;
 constexpr int kMaxRowJobs = 24;
 constexpr int kRelabelThreads = 256;
+constexpr int kGatherMinBlocks = 4;   // resident CTAs per SM the gather kernel is compiled for (register cap 64)
 
 // index-vector slots
 enum : int {
@@ -53,6 +54,19 @@ struct RowJob {
   uint8_t lpr_log2;     // lanes per row = 1 << lpr_log2 (<= 32)
   uint8_t slot;         // which index vector names the source rows
   uint8_t pad_;
+};
+
+// A field whose whole row is at most 16 bytes (terminals, valids, 2-D observations ...) is gathered by the index
+// kernel itself: the thread that computed row g's index vectors copies those few bytes straight away.
+constexpr int kMaxTinyJobs = 16;
+struct TinyJob {
+  const uint8_t* src;
+  uint8_t* dst;
+  uint8_t slot;
+  uint8_t size_log2;   // element size
+  uint8_t n_elem;      // row = n_elem elements (<= 16 bytes in total)
+  uint8_t pad_;
+  uint32_t pad2_;
 };
 
 struct RelabelParams {
@@ -106,6 +120,10 @@ struct RelabelParams {
   int32_t* vec_rows;           // row index vectors, consumed by the gather kernels
   int32_t* vec_init;           // first row of each row's trajectory segment (frame stacking only; may be null)
   int8_t* crop_out;            // [total_rows][2] (dy, dx) or -128 when the batch is not augmented (may be null)
+  // ---- rows of <= 16 bytes, copied by the index kernel ----
+  int32_t n_tiny;
+  int32_t write_vecs;          // 0: no later kernel needs the index vectors (everything was tiny) and debug is off
+  TinyJob tiny[kMaxTinyJobs];
 };
 
 __device__ __forceinline__ int32_t valid_row(const RelabelParams& p, int64_t pos) {
@@ -166,9 +184,17 @@ __device__ __forceinline__ int32_t trajectory_first_row(const RelabelParams& p, 
   return t == 0 ? 0 : __ldg(p.term + t - 1) + 1;
 }
 
-__device__ __forceinline__ void put_slot(const RelabelParams& p, const int slot, const int64_t g, const int32_t x) {
-  p.vec_rows[(int64_t)slot * p.total_rows + g] = x;
+__device__ __forceinline__ void put_slot(const RelabelParams& p, int32_t* sr, const int slot, const int64_t g, const int32_t x) {
+  sr[slot] = x;  // `slot` is a compile-time constant at every call site, so sr[] stays in registers
+  if (p.write_vecs) p.vec_rows[(int64_t)slot * p.total_rows + g] = x;
   if (p.vec_init != nullptr) p.vec_init[(int64_t)slot * p.total_rows + g] = trajectory_first_row(p, x);
+}
+
+__device__ __forceinline__ int32_t pick_slot(const int32_t* sr, const int slot) {
+  int32_t x = sr[0];
+#pragma unroll
+  for (int v = 1; v < kMaxSlots; ++v) x = (slot == v) ? sr[v] : x;
+  return x;
 }
 
 template <bool kInject>
@@ -177,6 +203,9 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
     const int64_t kb = g / p.batch;
     const uint32_t r = (uint32_t)(g - kb * p.batch);
     const uint64_t batch_id = p.batch0 + (uint64_t)kb;
+    int32_t sr[kMaxSlots];
+#pragma unroll
+    for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
 
     uint4 w0 = make_uint4(0, 0, 0, 0);
     if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
@@ -187,9 +216,9 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
       const int64_t pos = kInject ? p.in_idx_pos[g] : bounded_u64(w0.x, w0.y, (uint64_t)p.n_choices);
       i = valid_row(p, pos);                                            // datasets.py:65-70
     }
-    put_slot(p, SLOT_IDX, g, i);
+    put_slot(p, sr, SLOT_IDX, g, i);
     const int32_t nxt = p.stacked_next ? i + 1 : (i + 1 < p.n_rows_ds ? i + 1 : p.n_rows_ds - 1);  // :82 / :231
-    put_slot(p, SLOT_NEXT, g, nxt);
+    put_slot(p, sr, SLOT_NEXT, g, nxt);
 
     if (p.kind != 2) {
       const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
@@ -198,8 +227,8 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
       if (p.kind == 0) {
         const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);
         const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);
-        put_slot(p, GC_VALUE_GOAL, g, vg);
-        put_slot(p, GC_ACTOR_GOAL, g, ag);
+        put_slot(p, sr, GC_VALUE_GOAL, g, vg);
+        put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
         const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
         p.masks[g] = 1.0 - succ;
         p.rewards[g] = succ - neg;
@@ -208,9 +237,9 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         int32_t hv_next, hv_s, lv_next, lv_s;
         subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
         subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
-        put_slot(p, HGC_HV_GOAL, g, hv);
-        put_slot(p, HGC_HV_NEXT, g, hv_next);
-        put_slot(p, HGC_LV_NEXT, g, lv_next);
+        put_slot(p, sr, HGC_HV_GOAL, g, hv);
+        put_slot(p, sr, HGC_HV_NEXT, g, hv_next);
+        put_slot(p, sr, HGC_LV_NEXT, g, lv_next);
         p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
         p.hv_steps[g] = hv_s;
         p.lv_steps[g] = lv_s;
@@ -222,7 +251,7 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
         if (p.has_low_goal) {                                                         // :563-576
           const int32_t lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g);
-          put_slot(p, HGC_LV_GOAL, g, lvg);
+          put_slot(p, sr, HGC_LV_GOAL, g, lvg);
           const double s = (i == lvg) ? 1.0 : 0.0;
           lv_mask = 1.0 - s;
           lv_rew = s - neg;
@@ -237,10 +266,34 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
         subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
         const int64_t la = (int64_t)i + p.k_act;                                      // :610
-        put_slot(p, HGC_HA_GOAL, g, ha);
-        put_slot(p, HGC_HA_NEXT, g, ha_next);
-        put_slot(p, HGC_LA_GOAL, g, (int32_t)(la < (int64_t)fin ? la : (int64_t)fin));
-        put_slot(p, HGC_LA_NEXT, g, la_next);
+        put_slot(p, sr, HGC_HA_GOAL, g, ha);
+        put_slot(p, sr, HGC_HA_NEXT, g, ha_next);
+        put_slot(p, sr, HGC_LA_GOAL, g, (int32_t)(la < (int64_t)fin ? la : (int64_t)fin));
+        put_slot(p, sr, HGC_LA_NEXT, g, la_next);
+      }
+    }
+
+    // rows of <= 16 bytes: this thread copies them now (datasets.py:78-83 for the per-transition fields)
+#pragma unroll 1
+    for (int j = 0; j < p.n_tiny; ++j) {
+      const TinyJob& job = p.tiny[j];
+      const int row_bytes = (int)job.n_elem << job.size_log2;
+      const uint8_t* sp = job.src + (size_t)pick_slot(sr, job.slot) * row_bytes;
+      uint8_t* dp = job.dst + (size_t)g * row_bytes;
+      switch (job.size_log2) {
+        case 4: *reinterpret_cast<uint4*>(dp) = __ldg(reinterpret_cast<const uint4*>(sp)); break;
+        case 3:
+          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint2*>(dp)[e] = __ldg(reinterpret_cast<const uint2*>(sp) + e);
+          break;
+        case 2:
+          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
+          break;
+        case 1:
+          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
+          break;
+        default:
+          for (int e = 0; e < job.n_elem; ++e) dp[e] = __ldg(sp + e);
+          break;
       }
     }
 
@@ -282,12 +335,27 @@ struct GatherParams {
   RowJob jobs[kMaxRowJobs];
 };
 
-template <typename V>
-__device__ __forceinline__ V load_stream(const V* p) { return __ldg(p); }
+// read-once data: do not allocate in L1 (keeps the small index / table lines resident)
+__device__ __forceinline__ uint32_t load_stream(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint2 load_stream(const uint2* p) {
+  uint2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint4 load_stream(const uint4* p) {
+  uint4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint16_t load_stream(const uint16_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint8_t load_stream(const uint8_t* p) { return __ldg(p); }
 
 template <typename V>
-__global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __grid_constant__ GatherParams p) {
-  constexpr int kU = sizeof(V) >= 16 ? 4 : 8;
+struct GatherTuning {
+  static constexpr int kU = sizeof(V) >= 16 ? 4 : 8;  // independent loads in flight per warp
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kRelabelThreads, kGatherMinBlocks) gather_rows_kernel(const __grid_constant__ GatherParams p) {
+  constexpr int kU = GatherTuning<V>::kU;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps_global = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -297,14 +365,17 @@ __global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __gr
   for (int64_t wt = warp_global; wt < n_warp_tiles; wt += n_warps_global) {
     const int64_t g0 = wt << 5;
     const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+    // lane l holds the source row of batch row g0 + l; the vector of the next job is fetched one job ahead
+    int32_t next_row = lane < n ? __ldg(p.vec_rows + (int64_t)p.jobs[0].slot * p.total_rows + g0 + lane) : 0;
 #pragma unroll 1
     for (int j = 0; j < p.n_jobs; ++j) {
       const RowJob& job = p.jobs[j];
+      const int32_t my_row = next_row;
+      if (j + 1 < p.n_jobs) next_row = lane < n ? __ldg(p.vec_rows + (int64_t)p.jobs[j + 1].slot * p.total_rows + g0 + lane) : 0;
       const uint8_t* __restrict__ src = job.src;
       uint8_t* __restrict__ dst = job.dst + (size_t)g0 * job.row_bytes;
       const uint32_t stride = job.src_stride, row_bytes = job.row_bytes;
       const int epr = job.epr;
-      const int32_t my_row = lane < n ? __ldg(p.vec_rows + (int64_t)job.slot * p.total_rows + g0 + lane) : 0;
       if (job.n_coliter == 1) {
         const int lpr_log2 = job.lpr_log2;
         const int sub = lane >> lpr_log2;                       // row within the pass
@@ -312,31 +383,36 @@ __global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __gr
         const int rpp_log2 = 5 - lpr_log2;
         const int n_pass = (n + (1 << rpp_log2) - 1) >> rpp_log2;
         const bool col_ok = col < epr;
+        // lanes beyond the row (col >= epr) and rows beyond the tile re-read a valid element instead of being
+        // predicated off: no extra sectors are touched and every val[] register is unconditionally defined
+        const uint32_t src_off = (uint32_t)(col_ok ? col : epr - 1) * (uint32_t)sizeof(V);
+        const uint32_t dst_off = (uint32_t)sub * row_bytes + (uint32_t)col * (uint32_t)sizeof(V);
+        const uint32_t pass_bytes = row_bytes << rpp_log2;
 #pragma unroll 1
         for (int pass0 = 0; pass0 < n_pass; pass0 += kU) {
           V val[kU];
 #pragma unroll
           for (int u = 0; u < kU; ++u) {
-            const int row = ((pass0 + u) << rpp_log2) + sub;
-            const int32_t src_row = __shfl_sync(0xffffffffu, my_row, row & 31);
-            if (col_ok && row < n) val[u] = load_stream(reinterpret_cast<const V*>(src + (size_t)src_row * stride) + col);
+            const int row = min(((pass0 + u) << rpp_log2) + sub, n - 1);
+            const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, my_row, row);
+            val[u] = load_stream(reinterpret_cast<const V*>(src + (size_t)src_row * stride + src_off));
           }
 #pragma unroll
           for (int u = 0; u < kU; ++u) {
             const int row = ((pass0 + u) << rpp_log2) + sub;
-            if (col_ok && row < n) reinterpret_cast<V*>(dst + (size_t)row * row_bytes)[col] = val[u];
+            if (col_ok && row < n) *reinterpret_cast<V*>(dst + (uint32_t)(pass0 + u) * pass_bytes + dst_off) = val[u];
           }
         }
       } else {
-        // long rows: 2 rows x kU/2 column slices per sweep
-        constexpr int kRowsPerSweep = 2, kSlices = kU / kRowsPerSweep;
+        // long rows: 2 rows x up to 4 column slices per sweep
+        constexpr int kRowsPerSweep = 2, kSlices = (kU > 8 ? 8 : kU) / kRowsPerSweep;
         const int n_coliter = job.n_coliter;
 #pragma unroll 1
         for (int row0 = 0; row0 < n; row0 += kRowsPerSweep) {
           const uint8_t* sp[kRowsPerSweep];
 #pragma unroll
           for (int rr = 0; rr < kRowsPerSweep; ++rr)
-            sp[rr] = src + (size_t)__shfl_sync(0xffffffffu, my_row, (row0 + rr) & 31) * stride;
+            sp[rr] = src + (size_t)(uint32_t)__shfl_sync(0xffffffffu, my_row, min(row0 + rr, n - 1)) * stride;
 #pragma unroll 1
           for (int c0 = 0; c0 < n_coliter; c0 += kSlices) {
             V val[kRowsPerSweep][kSlices];
@@ -344,8 +420,8 @@ __global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __gr
             for (int rr = 0; rr < kRowsPerSweep; ++rr)
 #pragma unroll
               for (int c = 0; c < kSlices; ++c) {
-                const int col = ((c0 + c) << 5) + lane;
-                if (row0 + rr < n && col < epr) val[rr][c] = load_stream(reinterpret_cast<const V*>(sp[rr]) + col);
+                const int col = min(((c0 + c) << 5) + lane, epr - 1);
+                val[rr][c] = load_stream(reinterpret_cast<const V*>(sp[rr]) + col);
               }
 #pragma unroll
             for (int rr = 0; rr < kRowsPerSweep; ++rr)
@@ -358,6 +434,170 @@ __global__ void __launch_bounds__(kRelabelThreads) gather_rows_kernel(const __gr
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row gather, asynchronous variant (the default for rows of 17 .. kAsyncMaxStride bytes).
+//
+// The register-staged kernel above keeps one register per in-flight load, which caps the bytes a warp can have
+// in flight.  Here the source rows go HBM -> shared memory with cp.async (LDGSTS, 16 bytes per lane, L1
+// bypassed) into a per-warp ring of kAsyncStages stages, so several KB per warp are in flight without holding
+// registers, and the drain is shared-memory loads + *flat* coalesced stores: the dense output tile of a job is
+// one contiguous span, so lanes store consecutive elements no matter how long a row is.
+// Work item = (warp tile of 32 batch rows, job, sub-range of rows that fits one stage).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAsyncStages = 3;
+constexpr int kAsyncWarps = 8;
+constexpr int kAsyncMaxStride = 4096;
+
+struct AsyncJob {
+  const uint8_t* src;
+  uint8_t* dst;
+  uint32_t stride;        // resident row stride, multiple of 16
+  uint32_t row_bytes;
+  uint32_t cpr;           // 16-byte chunks copied per row = ceil(row_bytes / 16)
+  uint32_t cpr_magic;     // ceil(2^32 / cpr), or 0 when cpr == 1: e / cpr == umulhi(e, magic) for e * cpr < 2^32
+  uint32_t epr;           // output elements per row (row_bytes >> vec_log2)
+  uint32_t epr_magic;
+  uint16_t rows_per_item; // rows of one stage
+  uint8_t vec_log2;
+  uint8_t slot;
+};
+
+struct AsyncGatherParams {
+  const int32_t* vec_rows;
+  int64_t total_rows;
+  int32_t n_jobs;
+  int32_t stage_bytes;
+  AsyncJob jobs[kMaxRowJobs];
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t magic) { return magic ? __umulhi(e, magic) : e; }
+
+struct ItemCursor {
+  int64_t wt;   // warp tile
+  int32_t j;    // job
+  int32_t sub;  // first row of the sub-range within the warp tile
+};
+
+__global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
+  extern __shared__ __align__(128) uint8_t smem_ring[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * kAsyncWarps + warp;
+  const int64_t n_warps_global = (int64_t)gridDim.x * kAsyncWarps;
+  const int64_t n_warp_tiles = (p.total_rows + 31) >> 5;
+  uint8_t* ring = smem_ring + (size_t)warp * kAsyncStages * p.stage_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+
+  auto advance = [&](ItemCursor& c) {
+    c.sub += p.jobs[c.j].rows_per_item;
+    if (c.sub >= 32) {
+      c.sub = 0;
+      if (++c.j == p.n_jobs) { c.j = 0; c.wt += n_warps_global; }
+    }
+  };
+  // lane l keeps the source row of batch row (wt*32 + l) for the job being issued
+  int32_t issue_rows = 0;
+  int64_t issue_rows_wt = -1;
+  int32_t issue_rows_job = -1;
+
+  auto issue = [&](const ItemCursor& c, int stage) {
+    if (c.wt < n_warp_tiles) {
+      const AsyncJob& job = p.jobs[c.j];
+      const int64_t g0 = c.wt << 5;
+      const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+      if (issue_rows_wt != c.wt || issue_rows_job != c.j) {
+        issue_rows = __ldg(p.vec_rows + (int64_t)job.slot * p.total_rows + g0 + min(lane, n - 1));
+        issue_rows_wt = c.wt;
+        issue_rows_job = c.j;
+      }
+      const int rows = min((int)job.rows_per_item, n - c.sub);     // may be <= 0 for the ragged last tile
+      const uint32_t n_chunks = rows > 0 ? (uint32_t)rows * job.cpr : 0u;
+      const uint32_t base = ring_u32 + (uint32_t)stage * (uint32_t)p.stage_bytes;
+      for (uint32_t e0 = 0; e0 < n_chunks; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const uint32_t r = min(fast_div(e, job.cpr_magic), (uint32_t)rows - 1);
+        const int32_t src_row = __shfl_sync(0xffffffffu, issue_rows, c.sub + (int)r);
+        if (e < n_chunks) {
+          const uint32_t ch = e - r * job.cpr;
+          cp_async16(base + r * job.stride + (ch << 4), job.src + (size_t)(uint32_t)src_row * job.stride + (ch << 4));
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  auto drain = [&](const ItemCursor& c, int stage) {
+    const AsyncJob& job = p.jobs[c.j];
+    const int64_t g0 = c.wt << 5;
+    const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+    const int rows = min((int)job.rows_per_item, n - c.sub);
+    if (rows <= 0) return;
+    const uint8_t* sbase = ring + (size_t)stage * p.stage_bytes;
+    uint8_t* dbase = job.dst + (size_t)(g0 + c.sub) * job.row_bytes;       // dense: the item's output is one span
+    const uint32_t n_elem = (uint32_t)rows * job.epr;
+    switch (job.vec_log2) {
+      case 4:
+        for (uint32_t e = lane; e < n_elem; e += 32) {
+          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
+          reinterpret_cast<uint4*>(dbase)[e] = *reinterpret_cast<const uint4*>(sbase + r * job.stride + (col << 4));
+        }
+        break;
+      case 3:
+        for (uint32_t e = lane; e < n_elem; e += 32) {
+          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
+          reinterpret_cast<uint2*>(dbase)[e] = *reinterpret_cast<const uint2*>(sbase + r * job.stride + (col << 3));
+        }
+        break;
+      case 2:
+        for (uint32_t e = lane; e < n_elem; e += 32) {
+          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
+          reinterpret_cast<uint32_t*>(dbase)[e] = *reinterpret_cast<const uint32_t*>(sbase + r * job.stride + (col << 2));
+        }
+        break;
+      case 1:
+        for (uint32_t e = lane; e < n_elem; e += 32) {
+          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
+          reinterpret_cast<uint16_t*>(dbase)[e] = *reinterpret_cast<const uint16_t*>(sbase + r * job.stride + (col << 1));
+        }
+        break;
+      default:
+        for (uint32_t e = lane; e < n_elem; e += 32) {
+          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
+          dbase[e] = sbase[r * job.stride + col];
+        }
+        break;
+    }
+  };
+
+  ItemCursor head{warp_global, 0, 0};  // next item to issue
+  ItemCursor tail{warp_global, 0, 0};  // next item to drain
+  int head_stage = 0, tail_stage = 0;
+#pragma unroll 1
+  for (int s = 0; s < kAsyncStages - 1; ++s) {
+    issue(head, head_stage);
+    if (head.wt < n_warp_tiles) advance(head);
+    head_stage = head_stage + 1 == kAsyncStages ? 0 : head_stage + 1;
+  }
+#pragma unroll 1
+  while (tail.wt < n_warp_tiles) {
+    issue(head, head_stage);
+    if (head.wt < n_warp_tiles) advance(head);
+    head_stage = head_stage + 1 == kAsyncStages ? 0 : head_stage + 1;
+    cp_async_wait<kAsyncStages - 1>();   // everything but the newest kAsyncStages-1 groups has landed
+    __syncwarp();                        // ... for every lane of this warp
+    drain(tail, tail_stage);
+    __syncwarp();                        // the stage may be overwritten by the next issue
+    advance(tail);
+    tail_stage = tail_stage + 1 == kAsyncStages ? 0 : tail_stage + 1;
   }
 }
 
