@@ -151,6 +151,8 @@ int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host); /* de
 int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host);       /* debug: [rows,2] applied (cy,cx), -1 if none */
 /* DLPack export of key i (DLManagedTensor*, legacy v0 ABI); the deleter drops one reference on the batch. */
 int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out_dl_managed_tensor);
+int ogb_batch_mark_escaped(ogb_batch* b);                         /* a raw device pointer was handed out (e.g. __cuda_array_interface__):
+                                                                     the block is recycled only after a device-wide sync */
 int ogb_batch_retain(ogb_batch* b);
 int ogb_batch_release(ogb_batch* b);
 

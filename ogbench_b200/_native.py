@@ -98,6 +98,7 @@ SIGNATURES = [
     ('ogb_batch_index_vector', C.c_int, [_P, C.c_int32, _P]),
     ('ogb_batch_crop_shifts', C.c_int, [_P, _P]),
     ('ogb_batch_dlpack', C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    ('ogb_batch_mark_escaped', C.c_int, [_P]),
     ('ogb_batch_retain', C.c_int, [_P]),
     ('ogb_batch_release', C.c_int, [_P]),
     ('ogb_host_alloc', C.c_int, [C.c_size_t, C.POINTER(_P)]),

@@ -45,6 +45,7 @@ struct FramesParams {
   const int32_t* vec_init;   // [slot][total_rows] first row of the trajectory segment (may be null when fs == 1)
   const int8_t* crop;        // [total_rows][2] (dy, dx), -128 = not augmented; may be null
   int64_t total_rows;
+  int64_t row_begin, row_end; // rows this launch handles
   int32_t H, W;              // image rows / pixels per row
   int32_t inner_bytes;       // C * itemsize
   int32_t band_rows;         // TMA kernel: rows per CTA item
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kFramesThreads) gather_frames_tma_kernel(const
   const int64_t item = blockIdx.x;
   const int band = (int)(item % p.n_bands);
   const int j = (int)((item / p.n_bands) % p.n_jobs);
-  const int64_t g = item / ((int64_t)p.n_bands * p.n_jobs);
+  const int64_t g = p.row_begin + item / ((int64_t)p.n_bands * p.n_jobs);
   const FrameJob& job = p.jobs[j];
 
   int dy = 0, dx = 0;
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(256) gather_frames_generic_kernel(const __grid
   const int fs = job.fs;
   const int chunks_inner = p.inner_bytes >> vec_log2;
   const int64_t per_row = (int64_t)p.H * p.W * fs * chunks_inner;
-  const int64_t total = p.total_rows * per_row;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t total = p.row_end * per_row;
+  for (int64_t e = p.row_begin * per_row + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = e / per_row;
     int64_t rem = e - g * per_row;
     const int ci = (int)(rem % chunks_inner); rem /= chunks_inner;

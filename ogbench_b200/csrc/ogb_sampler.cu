@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -237,8 +238,16 @@ struct ogb_sampler {
   std::mutex mu;
   // Batch blocks are recycled through this small per-sampler cache instead of going back to the driver: a block
   // released by the consumer is handed to a later sample() on the same stream (stream order makes that safe).
+  cudaStream_t aux_stream = nullptr;           // index kernels of chunked launches
+  std::vector<cudaEvent_t> chunk_events;       // ring of join events (index kernel -> gathers)
+  int next_event = 0;
   std::mutex cache_mu;
-  std::vector<std::pair<size_t, uint8_t*>> block_cache;
+  struct CachedBlock {
+    size_t bytes;
+    uint8_t* ptr;
+    std::vector<cudaEvent_t> free_after;   // the block may be rewritten once these have fired
+  };
+  std::vector<CachedBlock> block_cache;
   size_t cache_bytes = 0;
 };
 
@@ -259,12 +268,16 @@ struct ogb_batch {
   int launches = 0;
   cudaEvent_t ready = nullptr;
   std::vector<cudaStream_t> consumers;
+  bool main_stream_consumer = false;  // somebody took the batch on the sampler's own stream
+  bool escaped = false;               // a raw pointer left through __cuda_array_interface__: consumers unknown
   std::mutex mu;
 };
 
 namespace {
 
 constexpr size_t kMaxCachedBlocks = 6;
+constexpr int kMaxChunks = 8;
+constexpr int64_t kOverlapMinRows = 32768;   // below this a call is latency bound and stays on one stream
 
 size_t block_size_class(size_t bytes) {  // round up to 1/8-octave steps so that similar requests share blocks
   size_t cls = 4096;
@@ -273,14 +286,16 @@ size_t block_size_class(size_t bytes) {  // round up to 1/8-octave steps so that
   return step == 0 ? cls : (bytes + step - 1) / step * step;
 }
 
-int block_take(ogb_sampler* s, size_t bytes, uint8_t** out, size_t* out_bytes) {
+int block_take(ogb_sampler* s, size_t bytes, uint8_t** out, size_t* out_bytes, std::vector<cudaEvent_t>* free_after) {
   const size_t want = block_size_class(bytes);
+  free_after->clear();
   {
     std::lock_guard<std::mutex> lock(s->cache_mu);
     for (size_t i = 0; i < s->block_cache.size(); ++i)
-      if (s->block_cache[i].first == want) {
-        *out = s->block_cache[i].second;
+      if (s->block_cache[i].bytes == want) {
+        *out = s->block_cache[i].ptr;
         *out_bytes = want;
+        free_after->swap(s->block_cache[i].free_after);
         s->cache_bytes -= want;
         s->block_cache.erase(s->block_cache.begin() + (long)i);
         return 0;
@@ -288,15 +303,18 @@ int block_take(ogb_sampler* s, size_t bytes, uint8_t** out, size_t* out_bytes) {
   }
   cudaError_t e = cudaMalloc((void**)out, want);
   if (e != cudaSuccess) {  // drop the cache and retry once before giving up
-    std::vector<std::pair<size_t, uint8_t*>> drop;
+    std::vector<ogb_sampler::CachedBlock> drop;
     {
       std::lock_guard<std::mutex> lock(s->cache_mu);
       drop.swap(s->block_cache);
       s->cache_bytes = 0;
     }
     cudaGetLastError();
-    cudaStreamSynchronize(s->stream);
-    for (auto& blk : drop) cudaFree(blk.second);
+    cudaDeviceSynchronize();
+    for (auto& blk : drop) {
+      for (cudaEvent_t ev : blk.free_after) cudaEventDestroy(ev);
+      cudaFree(blk.ptr);
+    }
     e = cudaMalloc((void**)out, want);
   }
   if (e != cudaSuccess) { *out = nullptr; return fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for a batch block: %s", want, cudaGetErrorString(e)); }
@@ -304,19 +322,30 @@ int block_take(ogb_sampler* s, size_t bytes, uint8_t** out, size_t* out_bytes) {
   return 0;
 }
 
-void block_give(ogb_sampler* s, uint8_t* block, size_t bytes) {
-  uint8_t* evict = nullptr;
+int ensure_aux(ogb_sampler* s) {
+  if (s->aux_stream) return 0;
+  OGB_CUDA(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+  s->chunk_events.resize(1 + kMaxChunks + 1);
+  for (auto& ev : s->chunk_events) OGB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  return 0;
+}
+
+void block_give(ogb_sampler* s, uint8_t* block, size_t bytes, std::vector<cudaEvent_t>&& free_after) {
+  ogb_sampler::CachedBlock evict{0, nullptr, {}};
   {
     std::lock_guard<std::mutex> lock(s->cache_mu);
-    s->block_cache.emplace_back(bytes, block);
+    s->block_cache.push_back({bytes, block, std::move(free_after)});
     s->cache_bytes += bytes;
     if (s->block_cache.size() > kMaxCachedBlocks) {
-      evict = s->block_cache.front().second;
-      s->cache_bytes -= s->block_cache.front().first;
+      evict = std::move(s->block_cache.front());
+      s->cache_bytes -= evict.bytes;
       s->block_cache.erase(s->block_cache.begin());
     }
   }
-  if (evict) { cudaStreamSynchronize(s->stream); cudaFree(evict); }
+  if (evict.ptr) {
+    for (cudaEvent_t ev : evict.free_after) { cudaEventSynchronize(ev); cudaEventDestroy(ev); }
+    cudaFree(evict.ptr);
+  }
 }
 
 void dataset_unref(ogb_dataset* ds) {
@@ -333,7 +362,12 @@ void sampler_unref(ogb_sampler* s) {
   if (s->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(s->ds->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  for (auto& blk : s->block_cache) cudaFree(blk.second);
+  if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
+  for (auto& ev : s->chunk_events) cudaEventDestroy(ev);
+  for (auto& blk : s->block_cache) {
+    for (cudaEvent_t ev : blk.free_after) cudaEventDestroy(ev);
+    cudaFree(blk.ptr);
+  }
   if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
   if (s->d_term) cudaFree(s->d_term);
   if (s->d_term_bucket) cudaFree(s->d_term_bucket);
@@ -347,17 +381,26 @@ void batch_unref(ogb_batch* b) {
   if (b->refs.fetch_sub(1) != 1) return;
   ogb_sampler* s = b->sampler;
   cudaSetDevice(s->ds->device);
-  // consumers that took the batch on another stream (DLPack protocol) may still be reading it: order the free
+  // The block goes back to the sampler's cache together with the events after which it may be rewritten: the
+  // batch's own `ready` event, plus one event per consumer stream that took the batch through the DLPack protocol.
+  std::vector<cudaEvent_t> free_after;
+  if (b->ready) {
+    free_after.push_back(b->ready);
+  } else if (b->block) {  // sample() failed half-way: nothing is known about in-flight work on the block
+    cudaStreamSynchronize(s->stream);
+    if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
+  }
+  if (b->escaped) cudaDeviceSynchronize();
+  if (b->main_stream_consumer) b->consumers.push_back(s->stream);
   for (cudaStream_t c : b->consumers) {
     cudaEvent_t ev;
     if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
       cudaEventRecord(ev, c);
-      cudaStreamWaitEvent(s->stream, ev, 0);
-      cudaEventDestroy(ev);
+      free_after.push_back(ev);
     }
   }
-  if (b->block) block_give(s, b->block, b->block_bytes);
-  if (b->ready) cudaEventDestroy(b->ready);
+  if (b->block) block_give(s, b->block, b->block_bytes, std::move(free_after));
+  else for (cudaEvent_t ev : free_after) cudaEventDestroy(ev);
   delete b;
   sampler_unref(s);
 }
@@ -774,6 +817,7 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   std::lock_guard<std::mutex> lock(s->mu);
   if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks may still be in flight on the old stream
+  if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
   if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
   s->stream = (cudaStream_t)cuda_stream;
   s->owns_stream = false;
@@ -896,8 +940,24 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   }
   b->block_bytes = std::max<size_t>(cursor, 256);
   auto bail = [&](int code) { batch_unref(b); return code; };
+  // Phase-one work (uploads of validation draws, the index kernel) goes to `first`: for big launches that is the
+  // auxiliary stream, so that the index kernel of this call overlaps the gathers of the previous call, which are
+  // still running on the main stream.  The recycled block only has to wait for its own previous owner.
+  static const char* no_overlap = getenv("OGB_NO_OVERLAP");
+  const bool use_aux = !no_overlap && total >= kOverlapMinRows;
+  if (use_aux) {
+    int rc = ensure_aux(s);
+    if (rc) return bail(rc);
+  }
+  cudaStream_t first = use_aux ? s->aux_stream : s->stream;
   {
-    int rc = block_take(s, b->block_bytes, &b->block, &b->block_bytes);
+    std::vector<cudaEvent_t> free_after;
+    int rc = block_take(s, b->block_bytes, &b->block, &b->block_bytes, &free_after);
+    for (cudaEvent_t ev : free_after) {
+      cudaStreamWaitEvent(first, ev, 0);
+      if (first != s->stream) cudaStreamWaitEvent(s->stream, ev, 0);
+      cudaEventDestroy(ev);
+    }
     if (rc) return bail(rc);
   }
   uint8_t* base = b->block;
@@ -951,7 +1011,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   p.crop_out = b->crop;
 
   auto h2d = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
-    return cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, s->stream);
+    return cudaMemcpyAsync(base + off, src, bytes, cudaMemcpyHostToDevice, first);
   };
   if (idxs) {
     if (h2d(off_idxs, idxs, (size_t)total * 8) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of idxs failed"));
@@ -1016,21 +1076,35 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   }
   p.write_vecs = (!async_keys.empty() || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
 
-  {  // ---- launch 1: index algebra, scalar keys, tiny rows ----
-    const unsigned grid = (unsigned)std::min<int64_t>((total + kRelabelThreads - 1) / kRelabelThreads, (int64_t)ds->sm_count * 16);
-    if (draws) relabel_index_kernel<true><<<grid, kRelabelThreads, 0, s->stream>>>(p);
-    else relabel_index_kernel<false><<<grid, kRelabelThreads, 0, s->stream>>>(p);
-    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "relabel_index_kernel launch failed"));
-    b->launches++;
-  }
+  // ---- prepare every launch once; each is then issued per row chunk ----
+  typedef std::function<int(int64_t, int64_t, cudaStream_t)> LaunchFn;
+  std::vector<LaunchFn> gather_launches;
 
-  // ---- launch 2: asynchronous row gather (cp.async ring per warp), all element widths in one launch ----
+  LaunchFn index_launch = [&, p](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
+    p.row_begin = begin;
+    p.row_end = end;
+    const unsigned grid = (unsigned)std::min<int64_t>((end - begin + kRelabelThreads - 1) / kRelabelThreads, (int64_t)ds->sm_count * 16);
+    if (draws) relabel_index_kernel<true><<<grid, kRelabelThreads, 0, st>>>(p);
+    else relabel_index_kernel<false><<<grid, kRelabelThreads, 0, st>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "relabel_index_kernel launch failed");
+    b->launches++;
+    return 0;
+  };
+
+  // asynchronous row gather (cp.async ring per warp), all element widths in one launch
   for (size_t q = 0; q < async_keys.size();) {
     AsyncGatherParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.vec_rows = b->vec_rows;
     ap.total_rows = total;
-    ap.stage_bytes = 4096;
+    size_t max_stride = 0;
+    const size_t q0 = q;
+    for (size_t t = q0; t < async_keys.size() && t < q0 + kMaxRowJobs; ++t)
+      max_stride = std::max(max_stride, ds->fields[(size_t)plan[async_keys[t]].field].stride);
+    static const int env_stage = getenv("OGB_STAGE_BYTES") ? atoi(getenv("OGB_STAGE_BYTES")) : 0;
+    static const int env_flat = getenv("OGB_DRAIN_FLAT") ? atoi(getenv("OGB_DRAIN_FLAT")) : 1;
+    ap.stage_bytes = env_stage ? std::max<int>(env_stage, (int)max_stride) : 4096;
+    ap.flat_drain = env_flat;
     auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
     for (; q < async_keys.size() && ap.n_jobs < kMaxRowJobs; ++q) {
       const KeyPlan& k = plan[async_keys[q]];
@@ -1045,20 +1119,28 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       job.cpr_magic = magic(job.cpr);
       job.epr = (uint32_t)(f.row_bytes >> v);
       job.epr_magic = magic(job.epr);
-      job.rows_per_item = (uint16_t)std::min<size_t>(32, (size_t)ap.stage_bytes / f.stride);
+      size_t rpi = std::min<size_t>(32, (size_t)ap.stage_bytes / f.stride);
+      if (rpi > 4) rpi &= ~(size_t)3;   // items start on 16-byte boundaries of the dense output (16-byte drain stores)
+      job.rows_per_item = (uint16_t)rpi;
       job.vec_log2 = (uint8_t)v;
       job.slot = (uint8_t)k.slot;
     }
     const size_t smem = (size_t)kAsyncWarps * kAsyncStages * ap.stage_bytes;
     OGB_CUDA(cudaFuncSetAttribute(gather_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t n_warp_tiles = (total + 31) / 32;
-    const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * 2);
-    gather_rows_async_kernel<<<grid, kAsyncWarps * 32, smem, s->stream>>>(ap);
-    if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed"));
-    b->launches++;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
+      ap.row_begin = begin;
+      ap.row_end = end;
+      const int64_t n_warp_tiles = (end - begin + 31) / 32;
+      const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * ctas_per_sm);
+      gather_rows_async_kernel<<<grid, kAsyncWarps * 32, smem, st>>>(ap);
+      if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed");
+      b->launches++;
+      return 0;
+    });
   }
 
-  // ---- launch 2b: register-staged gather for what the asynchronous kernel does not take (very long rows) ----
+  // register-staged gather for what the asynchronous kernel does not take (very long rows)
   if (!lsu_keys.empty()) {
     const std::vector<size_t>& row_keys = lsu_keys;
     std::vector<int> vec_of(row_keys.size());
@@ -1066,8 +1148,6 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       const Field& f = ds->fields[(size_t)plan[row_keys[q]].field];
       vec_of[q] = largest_vec_log2(f.row_bytes, f.stride);
     }
-    const int64_t n_warp_tiles = (total + 31) / 32;
-    const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + 7) / 8, (int64_t)ds->sm_count * 32);
     for (int v = 4; v >= 0; --v) {
       size_t q = 0;
       while (q < row_keys.size()) {
@@ -1094,20 +1174,27 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
           job.slot = (uint8_t)k.slot;
         }
         if (gp.n_jobs == 0) break;
-        switch (v) {
-          case 4: gather_rows_kernel<uint4><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
-          case 3: gather_rows_kernel<uint2><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
-          case 2: gather_rows_kernel<uint32_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
-          case 1: gather_rows_kernel<uint16_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
-          default: gather_rows_kernel<uint8_t><<<grid, kRelabelThreads, 0, s->stream>>>(gp); break;
-        }
-        if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_rows_kernel launch failed"));
-        b->launches++;
+        gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
+          gp.row_begin = begin;
+          gp.row_end = end;
+          const int64_t n_warp_tiles = (end - begin + 31) / 32;
+          const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + 7) / 8, (int64_t)ds->sm_count * 32);
+          switch (v) {
+            case 4: gather_rows_kernel<uint4><<<grid, kRelabelThreads, 0, st>>>(gp); break;
+            case 3: gather_rows_kernel<uint2><<<grid, kRelabelThreads, 0, st>>>(gp); break;
+            case 2: gather_rows_kernel<uint32_t><<<grid, kRelabelThreads, 0, st>>>(gp); break;
+            case 1: gather_rows_kernel<uint16_t><<<grid, kRelabelThreads, 0, st>>>(gp); break;
+            default: gather_rows_kernel<uint8_t><<<grid, kRelabelThreads, 0, st>>>(gp); break;
+          }
+          if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "gather_rows_kernel launch failed");
+          b->launches++;
+          return 0;
+        });
       }
     }
   }
 
-  // ---- image keys: frame stacking + crop fused into the gather ----
+  // image keys: frame stacking + crop fused into the gather
   if (any_frames) {
     std::vector<size_t> frame_keys;
     for (size_t i = 0; i < plan.size(); ++i)
@@ -1151,25 +1238,51 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
         int rc = get_tmap(s, ka.field, rb, &tm);
         if (rc) return bail(rc);
         const size_t smem = 2 * (size_t)ka.fs * rb * fp.W * 3;
-        const int64_t n_items = total * fp.n_jobs * fp.n_bands;
-        if (n_items > 0x7fffffff) return bail(fail(OGB_ERR_UNSUPPORTED, "too many frame tiles in one launch"));
-        switch (ka.fs) {
-          case 1: rc = launch_frames_tma<1>(tm, fp, n_items, smem, s->stream); break;
-          case 2: rc = launch_frames_tma<2>(tm, fp, n_items, smem, s->stream); break;
-          case 3: rc = launch_frames_tma<3>(tm, fp, n_items, smem, s->stream); break;
-          default: rc = launch_frames_tma<4>(tm, fp, n_items, smem, s->stream); break;
-        }
-        if (rc) return bail(rc);
-        b->launches++;
+        const int fs = ka.fs;
+        gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
+          fp.row_begin = begin;
+          fp.row_end = end;
+          const int64_t n_items = (end - begin) * fp.n_jobs * fp.n_bands;
+          if (n_items > 0x7fffffff) return fail(OGB_ERR_UNSUPPORTED, "too many frame tiles in one launch");
+          int rc2;
+          switch (fs) {
+            case 1: rc2 = launch_frames_tma<1>(tm, fp, n_items, smem, st); break;
+            case 2: rc2 = launch_frames_tma<2>(tm, fp, n_items, smem, st); break;
+            case 3: rc2 = launch_frames_tma<3>(tm, fp, n_items, smem, st); break;
+            default: rc2 = launch_frames_tma<4>(tm, fp, n_items, smem, st); break;
+          }
+          if (rc2) return rc2;
+          b->launches++;
+          return 0;
+        });
       } else {
         const int v = largest_vec_log2((size_t)fp.inner_bytes, f.stride);
-        for (int jj = 0; jj < fp.n_jobs; ++jj) {
-          gather_frames_generic_kernel<<<ds->sm_count * 8, 256, 0, s->stream>>>(fp, jj, v);
-          if (cudaGetLastError() != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "gather_frames_generic_kernel launch failed"));
-          b->launches++;
-        }
+        gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
+          fp.row_begin = begin;
+          fp.row_end = end;
+          for (int jj = 0; jj < fp.n_jobs; ++jj) {
+            gather_frames_generic_kernel<<<ds->sm_count * 8, 256, 0, st>>>(fp, jj, v);
+            if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "gather_frames_generic_kernel launch failed");
+            b->launches++;
+          }
+          return 0;
+        });
       }
     }
+  }
+
+  // ---- issue: index kernel on `first`, gathers on the main stream behind it ----
+  {
+    int rc = index_launch(0, total, first);
+    if (rc) return bail(rc);
+    if (first != s->stream) {
+      cudaEvent_t ev = s->chunk_events[s->next_event];
+      s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
+      if (cudaEventRecord(ev, first) != cudaSuccess || cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess)
+        return bail(fail(OGB_ERR_CUDA, "stream join failed"));
+    }
+    for (size_t q = 0; q < gather_launches.size() && !rc; ++q) rc = gather_launches[q](0, total, s->stream);
+    if (rc) return bail(rc);
   }
   if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
     return bail(fail(OGB_ERR_CUDA, "ready event failed"));
@@ -1220,7 +1333,7 @@ int ogb_batch_sync(ogb_batch* b) {
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   cudaStream_t c = (cudaStream_t)consumer_stream;
-  if (c == b->sampler->stream) return 0;
+  if (c == b->sampler->stream) { b->main_stream_consumer = true; return 0; }
   OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
   OGB_CUDA(cudaStreamWaitEvent(c, b->ready, 0));
   std::lock_guard<std::mutex> lock(b->mu);
@@ -1301,6 +1414,11 @@ int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) {
   t->deleter = dl_deleter;
   b->refs.fetch_add(1);
   *out = t;
+  return 0;
+}
+int ogb_batch_mark_escaped(ogb_batch* b) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  b->escaped = true;
   return 0;
 }
 int ogb_batch_retain(ogb_batch* b) {

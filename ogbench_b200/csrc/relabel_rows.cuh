@@ -103,7 +103,8 @@ struct RelabelParams {
   const int64_t* given_idxs;
   // ---- launch shape ----
   int64_t batch;               // rows per sample() call
-  int64_t total_rows;          // batch * n_batches
+  int64_t total_rows;          // batch * n_batches (also the stride of the [slot][row] index vectors)
+  int64_t row_begin, row_end;  // rows this launch handles (a big launch is split into chunks, see ogb_sampler.cu)
   int32_t n_slots;
   int32_t pad0_;
   // ---- scalar outputs (float64 / int64 like the reference) ----
@@ -199,7 +200,7 @@ __device__ __forceinline__ int32_t pick_slot(const int32_t* sr, const int slot) 
 
 template <bool kInject>
 __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.total_rows; g += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t g = p.row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.row_end; g += (int64_t)gridDim.x * blockDim.x) {
     const int64_t kb = g / p.batch;
     const uint32_t r = (uint32_t)(g - kb * p.batch);
     const uint64_t batch_id = p.batch0 + (uint64_t)kb;
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
 struct GatherParams {
   const int32_t* vec_rows;     // [slot][total_rows]
   int64_t total_rows;
+  int64_t row_begin, row_end;  // row_begin is a multiple of 32
   int32_t n_jobs;
   RowJob jobs[kMaxRowJobs];
 };
@@ -359,12 +361,12 @@ __global__ void __launch_bounds__(kRelabelThreads, kGatherMinBlocks) gather_rows
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps_global = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_warp_tiles = (p.total_rows + 31) >> 5;
+  const int64_t n_warp_tiles = (p.row_end + 31) >> 5;
 
 #pragma unroll 1
-  for (int64_t wt = warp_global; wt < n_warp_tiles; wt += n_warps_global) {
+  for (int64_t wt = (p.row_begin >> 5) + warp_global; wt < n_warp_tiles; wt += n_warps_global) {
     const int64_t g0 = wt << 5;
-    const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+    const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
     // lane l holds the source row of batch row g0 + l; the vector of the next job is fetched one job ahead
     int32_t next_row = lane < n ? __ldg(p.vec_rows + (int64_t)p.jobs[0].slot * p.total_rows + g0 + lane) : 0;
 #pragma unroll 1
@@ -468,8 +470,11 @@ struct AsyncJob {
 struct AsyncGatherParams {
   const int32_t* vec_rows;
   int64_t total_rows;
+  int64_t row_begin, row_end;  // row_begin is a multiple of 32
   int32_t n_jobs;
   int32_t stage_bytes;
+  int32_t flat_drain;          // 1: flat element index (coalesced 128-byte stores), 0: row by row
+  int32_t pad_;
   AsyncJob jobs[kMaxRowJobs];
 };
 
@@ -482,6 +487,68 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t magic) { return magic ? __umulhi(e, magic) : e; }
 
+// flat drain: the item's dense output is one contiguous span, lanes store consecutive elements (full 128-byte lines)
+template <typename V>
+__device__ __forceinline__ void drain_flat(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const uint32_t n_elem,
+                                           const uint32_t stride, const uint32_t epr, const uint32_t epr_magic, const int lane) {
+  for (uint32_t e = lane; e < n_elem; e += 32) {
+    const uint32_t r = fast_div(e, epr_magic), col = e - r * epr;
+    reinterpret_cast<V*>(dbase)[e] = *reinterpret_cast<const V*>(sbase + r * stride + col * (uint32_t)sizeof(V));
+  }
+}
+
+// 4-byte elements, the common case (float32 rows whose size is not a multiple of 16): each lane assembles 16
+// consecutive output bytes from four shared-memory words (they straddle at most one row boundary) and issues one
+// 16-byte store, so a warp-wide store covers 512 contiguous bytes of the dense output.
+__device__ __forceinline__ void drain_flat_quads(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const uint32_t n_words,
+                                                 const uint32_t stride, const uint32_t epr, const uint32_t epr_magic, const int lane) {
+  const uint32_t n_quads = n_words >> 2;
+  const uint32_t row_gap = stride - epr * 4u;             // padding bytes between two rows in the stage
+  for (uint32_t q = lane; q < n_quads; q += 32) {
+    const uint32_t w0 = q << 2;
+    const uint32_t r = fast_div(w0, epr_magic);
+    uint32_t col = w0 - r * epr;
+    uint32_t off = r * stride + col * 4u;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = *reinterpret_cast<const uint32_t*>(sbase + off);
+      off += 4u;
+      if (++col == epr) { col = 0; off += row_gap; }
+    }
+    reinterpret_cast<uint4*>(dbase)[q] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  for (uint32_t e = (n_quads << 2) + lane; e < n_words; e += 32) {   // ragged last tile only
+    const uint32_t r = fast_div(e, epr_magic), col = e - r * epr;
+    reinterpret_cast<uint32_t*>(dbase)[e] = *reinterpret_cast<const uint32_t*>(sbase + r * stride + col * 4u);
+  }
+}
+
+template <typename V>
+__device__ __forceinline__ void drain_rows(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const int rows,
+                                           const uint32_t stride, const uint32_t row_bytes, const uint32_t epr, const int lane) {
+  if (epr <= 32) {
+    const bool ok = (uint32_t)lane < epr;
+    const uint32_t off = (uint32_t)lane * (uint32_t)sizeof(V);
+    int r = 0;
+    for (; r + 4 <= rows; r += 4) {
+      V v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ok) v[q] = *reinterpret_cast<const V*>(sbase + (uint32_t)(r + q) * stride + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ok) *reinterpret_cast<V*>(dbase + (uint32_t)(r + q) * row_bytes + off) = v[q];
+    }
+    for (; r < rows; ++r)
+      if (ok) *reinterpret_cast<V*>(dbase + (uint32_t)r * row_bytes + off) = *reinterpret_cast<const V*>(sbase + (uint32_t)r * stride + off);
+  } else {
+    for (int r = 0; r < rows; ++r)
+      for (uint32_t c = lane; c < epr; c += 32)
+        reinterpret_cast<V*>(dbase + (uint32_t)r * row_bytes)[c] = reinterpret_cast<const V*>(sbase + (uint32_t)r * stride)[c];
+  }
+}
+
 struct ItemCursor {
   int64_t wt;   // warp tile
   int32_t j;    // job
@@ -493,7 +560,8 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_global = (int64_t)blockIdx.x * kAsyncWarps + warp;
   const int64_t n_warps_global = (int64_t)gridDim.x * kAsyncWarps;
-  const int64_t n_warp_tiles = (p.total_rows + 31) >> 5;
+  const int64_t n_warp_tiles = (p.row_end + 31) >> 5;
+  const int64_t first_tile = (p.row_begin >> 5) + warp_global;
   uint8_t* ring = smem_ring + (size_t)warp * kAsyncStages * p.stage_bytes;
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
@@ -513,7 +581,7 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(con
     if (c.wt < n_warp_tiles) {
       const AsyncJob& job = p.jobs[c.j];
       const int64_t g0 = c.wt << 5;
-      const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+      const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
       if (issue_rows_wt != c.wt || issue_rows_job != c.j) {
         issue_rows = __ldg(p.vec_rows + (int64_t)job.slot * p.total_rows + g0 + min(lane, n - 1));
         issue_rows_wt = c.wt;
@@ -538,48 +606,37 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(con
   auto drain = [&](const ItemCursor& c, int stage) {
     const AsyncJob& job = p.jobs[c.j];
     const int64_t g0 = c.wt << 5;
-    const int n = (int)(p.total_rows - g0 < 32 ? p.total_rows - g0 : 32);
+    const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
     const int rows = min((int)job.rows_per_item, n - c.sub);
     if (rows <= 0) return;
     const uint8_t* sbase = ring + (size_t)stage * p.stage_bytes;
-    uint8_t* dbase = job.dst + (size_t)(g0 + c.sub) * job.row_bytes;       // dense: the item's output is one span
-    const uint32_t n_elem = (uint32_t)rows * job.epr;
+    uint8_t* dbase = job.dst + (size_t)(g0 + c.sub) * job.row_bytes;
+    if (p.flat_drain) {
+      const uint32_t n_elem = (uint32_t)rows * job.epr;
+      switch (job.vec_log2) {
+        case 4: drain_flat<uint4>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
+        case 3: drain_flat<uint2>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
+        case 2:
+          if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_flat_quads(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
+          else drain_flat<uint32_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
+          break;
+        case 1: drain_flat<uint16_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
+        default: drain_flat<uint8_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
+      }
+      return;
+    }
+    // one warp-wide shared load + global store per 32 elements of a row; rows are unrolled by 4 for ILP
     switch (job.vec_log2) {
-      case 4:
-        for (uint32_t e = lane; e < n_elem; e += 32) {
-          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
-          reinterpret_cast<uint4*>(dbase)[e] = *reinterpret_cast<const uint4*>(sbase + r * job.stride + (col << 4));
-        }
-        break;
-      case 3:
-        for (uint32_t e = lane; e < n_elem; e += 32) {
-          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
-          reinterpret_cast<uint2*>(dbase)[e] = *reinterpret_cast<const uint2*>(sbase + r * job.stride + (col << 3));
-        }
-        break;
-      case 2:
-        for (uint32_t e = lane; e < n_elem; e += 32) {
-          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
-          reinterpret_cast<uint32_t*>(dbase)[e] = *reinterpret_cast<const uint32_t*>(sbase + r * job.stride + (col << 2));
-        }
-        break;
-      case 1:
-        for (uint32_t e = lane; e < n_elem; e += 32) {
-          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
-          reinterpret_cast<uint16_t*>(dbase)[e] = *reinterpret_cast<const uint16_t*>(sbase + r * job.stride + (col << 1));
-        }
-        break;
-      default:
-        for (uint32_t e = lane; e < n_elem; e += 32) {
-          const uint32_t r = fast_div(e, job.epr_magic), col = e - r * job.epr;
-          dbase[e] = sbase[r * job.stride + col];
-        }
-        break;
+      case 4: drain_rows<uint4>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
+      case 3: drain_rows<uint2>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
+      case 2: drain_rows<uint32_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
+      case 1: drain_rows<uint16_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
+      default: drain_rows<uint8_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
     }
   };
 
-  ItemCursor head{warp_global, 0, 0};  // next item to issue
-  ItemCursor tail{warp_global, 0, 0};  // next item to drain
+  ItemCursor head{first_tile, 0, 0};  // next item to issue
+  ItemCursor tail{first_tile, 0, 0};  // next item to drain
   int head_stage = 0, tail_stage = 0;
 #pragma unroll 1
   for (int s = 0; s < kAsyncStages - 1; ++s) {

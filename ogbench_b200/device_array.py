@@ -110,7 +110,8 @@ class DeviceArray:
 
     @property
     def __cuda_array_interface__(self):
-        self._batch.sync()  # the interface carries no stream: hand over only finished data
+        self._batch.sync()  # the interface carries no stream: hand over only finished data ...
+        _native.check(_native.lib().ogb_batch_mark_escaped(self._batch.ptr))  # ... and recycle the block conservatively
         return {'shape': self.shape, 'typestr': self.dtype.str, 'data': (self.ptr, False), 'version': 3, 'strides': None}
 
     def numpy(self) -> np.ndarray:

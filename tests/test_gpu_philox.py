@@ -1,0 +1,242 @@
+"""On-device RNG mode: bit-level checks against the numpy restatement of the device's Philox draws, determinism /
+stream independence, multi-batch launches, and distributional agreement with the reference's numpy RNG."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import philox_np
+from oracle.replay_oracle import DrawsSource, OracleSampler
+from tests.golden.make_golden import cfg, ragged, toy_fields
+from tests.gpu_util import device_sampler, to_host
+
+pytestmark = pytest.mark.gpu
+
+
+def goal_sets_for(config, kind):
+    sets = [(0, bool(config['value_geom_sample']), config['discount'], config['value_p_curgoal'] == 1.0)]
+    if kind == 'hgc' and config.get('low_discount') is not None:
+        sets.append((1, True, config['low_discount'], config['value_p_curgoal'] == 1.0))
+    sets.append((2, bool(config['actor_geom_sample']), config['discount'], config['actor_p_curgoal'] == 1.0))
+    return sets
+
+
+def test_philox_words_match_numpy():
+    from ogbench_b200 import _native
+
+    n = 1000
+    out = np.empty((n, 4), dtype=np.uint32)
+    for seed, stream, batch, purpose in [(0, 0, 0, 0), (0xDEADBEEFCAFEF00D, 77, (1 << 40) + 5, 3), (123, 0xFFFFFF, 9, 7)]:
+        _native.check(_native.lib().ogb_philox_fill(seed, stream, batch, purpose, n, 0, out.ctypes.data_as(C.c_void_p)))
+        want = philox_np.draw4(seed, stream, batch, np.arange(n), purpose)
+        for k in range(4):
+            assert np.array_equal(out[:, k].astype(np.uint64), want[k]), (seed, k)
+
+
+CASES = [
+    ('gc', (29,), None, {}, np.float32),
+    ('gc', (3,), None, dict(value_geom_sample=False, actor_geom_sample=True, actor_p_curgoal=0.2, actor_p_trajgoal=0.3,
+                            actor_p_randomgoal=0.5, gc_negative=False), np.float32),
+    ('hgc', (7,), None, dict(subgoal_steps=6, discount=0.995), np.float32),
+    ('hgc', (7,), None, dict(subgoal_steps=6, low_discount=0.9, value_subgoal_steps=3), np.float32),
+    ('gc', (16, 16, 3), 3, dict(p_aug=0.7), np.uint8),
+    ('hgc', (16, 16, 3), 2, dict(p_aug=1.0, subgoal_steps=2), np.uint8),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[f'{c[0]}-{"x".join(map(str, c[1]))}-{i}' for i, c in enumerate(CASES)])
+def test_philox_mode_is_the_oracle_on_philox_draws(case):
+    """The kernel's draws are a pure function of (seed, stream, batch counter, row): rebuild them in numpy, run the
+    oracle on them and demand the identical batch.  Rows whose geometric draw sits within 1e-9 of an integer boundary
+    (where device log vs numpy log may differ in the last bit) are exempt; there are essentially none."""
+    kind, obs_shape, fs, over, dtype = case
+    pixel = dtype == np.uint8
+    lengths = ragged(5, 10 if pixel else 120, 2, 25 if pixel else 200)
+    fields = toy_fields(5, lengths, obs_shape, 4, dtype)
+    config = cfg(frame_stack=fs, **over)
+    seed, stream_id = 0x1234ABCD5678, 5
+    sampler = device_sampler(fields, config, kind, seed=seed, stream_id=stream_id)
+    oracle = OracleSampler(fields, config, kind)
+    n_choices = len(oracle.valid_table)
+    B = 24 if pixel else 512
+    for call in range(3):
+        evaluation = call == 2
+        got = to_host(sampler.sample(B, evaluation=evaluation))
+        aug = config['p_aug'] is not None and not evaluation
+        draws, knife = philox_np.philox_draws(seed, stream_id, call, B, n_choices, goal_sets_for(config, kind), aug,
+                                              config['p_aug'] or 0.0)
+        src = DrawsSource(draws)
+        want = oracle.sample(B, evaluation=evaluation, source=src)
+        assert src.exhausted()
+        ok = ~knife
+        assert ok.mean() > 0.999
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+            assert np.array_equal(got[k][ok], want[k][ok]), (k, call)
+
+
+def test_sample_many_equals_successive_calls():
+    lengths = ragged(7, 60, 2, 90)
+    fields = toy_fields(7, lengths, (11,), 3, np.float32)
+    config = cfg(subgoal_steps=5)
+    a = device_sampler(fields, config, 'hgc', seed=9)
+    b = device_sampler(fields, config, 'hgc', seed=9)
+    K, B = 5, 96
+    many = to_host(a.sample_many(K, B))
+    for k in range(K):
+        one = to_host(b.sample(B))
+        for key in one:
+            assert many[key].shape == (K,) + one[key].shape
+            assert np.array_equal(many[key][k], one[key]), (key, k)
+    assert a.state_dict() == b.state_dict() == {'counter': K}
+
+
+def test_counter_checkpoint_and_stream_independence():
+    lengths = ragged(8, 40, 2, 60)
+    fields = toy_fields(8, lengths, (5,), 2, np.float32)
+    config = cfg()
+    s0 = device_sampler(fields, config, 'gc', seed=1, stream_id=0)
+    first = to_host(s0.sample(256))
+    state = s0.state_dict()
+    second = to_host(s0.sample(256))
+    s0.load_state_dict(state)
+    again = to_host(s0.sample(256))
+    assert all(np.array_equal(second[k], again[k]) for k in second)          # resume reproduces the stream
+    assert not np.array_equal(first['observations'], second['observations'])
+    s1 = device_sampler(fields, config, 'gc', seed=1, stream_id=1)           # another rank: another stream
+    other = to_host(s1.sample(256))
+    assert not np.array_equal(first['observations'], other['observations'])
+    s2 = device_sampler(fields, config, 'gc', seed=1, stream_id=0)           # same key: same stream
+    same = to_host(s2.sample(256))
+    assert all(np.array_equal(first[k], same[k]) for k in first)
+
+
+def test_distribution_matches_reference_rng():
+    """Device Philox mode vs the oracle on numpy's MT19937: same distribution of transitions, goal kinds and offsets."""
+    from scipy import stats
+
+    lengths = np.full(400, 251)
+    fields = toy_fields(9, lengths, (2,), 2, np.float32)
+    fields['observations'][:, 0] = np.arange(len(fields['observations']))    # row id readable from the batch
+    config = cfg()
+    n = len(fields['terminals'])
+    B = 200_000
+    dev = to_host(device_sampler(fields, config, 'gc', seed=3).sample(B))
+    np.random.seed(0)
+    ref = OracleSampler(fields, config, 'gc').sample(B)
+
+    def rows(batch, key):
+        return batch[key][:, 0].astype(np.int64)
+
+    for batch in (dev, ref):
+        i, vg, ag = rows(batch, 'observations'), rows(batch, 'value_goals'), rows(batch, 'actor_goals')
+        assert fields['valids'][i].all()                                      # only valid rows are drawn
+        assert np.array_equal(rows(batch, 'next_observations'), i + 1)
+        traj = i // 251
+        assert (ag // 251 == traj).all() and ((ag > i) | (i % 251 == 249)).all()  # actor goals: future rows of the same trajectory
+        assert np.array_equal(batch['masks'], (vg != i).astype(np.float64))
+    # transition indices: uniform over valid rows (chi-square on 100 bins, and two-sample KS against the reference)
+    i_dev, i_ref = rows(dev, 'observations'), rows(ref, 'observations')
+    hist = np.histogram(i_dev, bins=100, range=(0, n))[0]
+    assert stats.chisquare(hist).pvalue > 1e-4
+    assert stats.ks_2samp(i_dev, i_ref).pvalue > 1e-4
+    # goal mix: P(goal == current) = p_cur + (tiny chance of a coincidence); same-trajectory future fraction
+    for key, p_cur in (('value_goals', 0.2), ('actor_goals', 0.0)):
+        f_dev = np.mean(rows(dev, key) == i_dev)
+        f_ref = np.mean(rows(ref, key) == i_ref)
+        assert abs(f_dev - f_ref) < 0.005 and abs(f_dev - p_cur) < 0.01, key
+    # value-goal offsets of same-trajectory future goals: geometric(0.01) clipped at the trajectory end
+    def future_offsets(batch):
+        i, g = rows(batch, 'observations'), rows(batch, 'value_goals')
+        m = (g > i) & (g // 251 == i // 251)
+        return (g - i)[m]
+    assert stats.ks_2samp(future_offsets(dev), future_offsets(ref)).pvalue > 1e-4
+    # actor goals are uniform in the remainder of the trajectory
+    def actor_frac(batch):
+        i, g = rows(batch, 'observations'), rows(batch, 'actor_goals')
+        final = (i // 251) * 251 + 249
+        m = final - i > 20
+        return ((g - i - 1) / (final - i - 1 + 1e-9))[m]
+    assert stats.ks_2samp(actor_frac(dev), actor_frac(ref)).pvalue > 1e-4
+
+
+def test_crop_shift_distribution():
+    lengths = ragged(10, 8, 3, 12)
+    fields = toy_fields(10, lengths, (16, 16, 3), 2, np.uint8)
+    config = cfg(frame_stack=None, p_aug=0.5)
+    s = device_sampler(fields, config, 'gc', seed=11)
+    from ogbench_b200 import _native
+
+    coins, shifts = [], []
+    for _ in range(300):
+        h = s._sampler.sample_native(64)
+        out = np.empty((64, 2), dtype=np.int64)
+        _native.check(_native.lib().ogb_batch_crop_shifts(h.ptr, out.ctypes.data_as(C.c_void_p)))
+        applied = out[0, 0] >= 0
+        assert ((out >= 0).all() if applied else (out == -1).all())       # one coin per batch
+        coins.append(applied)
+        if applied:
+            shifts.append(out)
+    assert 0.4 < np.mean(coins) < 0.6
+    shifts = np.concatenate(shifts)
+    assert shifts.min() == 0 and shifts.max() == 6
+    counts = np.stack([np.bincount(shifts[:, k], minlength=7) for k in range(2)])
+    assert (np.abs(counts / counts.sum(1, keepdims=True) - 1 / 7) < 0.02).all()
+
+
+def test_warp_searchsorted_matches_numpy():
+    from ogbench_b200 import _native
+
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 2, 31, 32, 33, 1000, 4097):
+        table = np.sort(rng.integers(0, max(4 * n, 4), size=n)).astype(np.int64)   # with duplicates
+        keys = np.concatenate([rng.integers(-2, max(4 * n, 4) + 2, size=500), table[:50]]).astype(np.int64)
+        for side, flag in (('left', 0), ('right', 1)):
+            out = np.empty(len(keys), dtype=np.int64)
+            _native.check(_native.lib().ogb_searchsorted_warp(
+                table.ctypes.data_as(C.c_void_p), n, keys.ctypes.data_as(C.c_void_p), len(keys), flag, 0, out.ctypes.data_as(C.c_void_p)))
+            assert np.array_equal(out, np.searchsorted(table, keys, side=side)), (n, side)
+
+
+def test_dlpack_handoff_to_torch():
+    import torch
+
+    lengths = ragged(12, 30, 2, 50)
+    fields = toy_fields(12, lengths, (6,), 2, np.float32)
+    s = device_sampler(fields, cfg(), 'gc', seed=2)
+    batch = s.sample(128)
+    host = to_host(batch)
+    consumer = torch.cuda.Stream()
+    with torch.cuda.stream(consumer):
+        tensors = {k: torch.from_dlpack(v) for k, v in batch.items()}
+    del batch                                                   # the DLPack capsules keep the block alive
+    for _ in range(4):
+        s.sample(128)                                           # recycled blocks must not clobber exported tensors
+    consumer.synchronize()
+    for k, t in tensors.items():
+        assert t.is_cuda and tuple(t.shape) == host[k].shape
+        assert np.array_equal(t.cpu().numpy(), host[k]), k
+    assert tensors['masks'].dtype == torch.float64 and tensors['observations'].dtype == torch.float32
+
+
+def test_full_size_properties_c2():
+    """BASELINE shape (1,001,000 x 29): size-independent properties on a 1M-transition launch."""
+    from ogbench_b200 import Dataset, GCDataset, synthetic
+
+    w = synthetic.WORKLOADS['c2']
+    fields = synthetic.host_fields(w)
+    fields['observations'][:, 0] = np.arange(w.rows, dtype=np.float32)      # exact in float32 (< 2^24)
+    s = GCDataset(Dataset.create(**fields), w.config, seed=5)
+    out = to_host(s.sample_many(64, w.batch))
+    i = out['observations'][..., 0].astype(np.int64)
+    assert np.array_equal(out['observations'], fields['observations'][i])   # gathers are exact copies
+    assert np.array_equal(out['actions'], fields['actions'][i])
+    assert (out['valids'] == 1).all() and np.array_equal(out['terminals'], fields['terminals'][i])
+    assert np.array_equal(out['next_observations'][..., 0].astype(np.int64), i + 1)
+    vg, ag = out['value_goals'][..., 0].astype(np.int64), out['actor_goals'][..., 0].astype(np.int64)
+    final = (i // w.steps) * w.steps + w.steps - 2
+    assert ((ag > i) | (i == final)).all() and (ag <= final).all()
+    assert np.array_equal(out['masks'], (vg != i).astype(np.float64)) and np.array_equal(out['rewards'], out['masks'] * -1.0)
+    assert np.array_equal(out['value_goals'], fields['observations'][vg])
