@@ -213,15 +213,11 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from ogbench_b200 import Dataset, GCDataset, HGCDataset, _native, synthetic
+    from ogbench_b200 import Dataset, GCDataset, HGCDataset, _native, dist_util, synthetic
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world, local = dist_util.env_rank()
     torch.cuda.set_device(local)
+    dist_util.init('nccl', device=torch.device('cuda', local))
     w = synthetic.WORKLOADS[args.config]
     L = args.batches_per_launch or default_batches_per_launch(w)
 
@@ -237,8 +233,7 @@ def run_gpu_arm(args):
     lib = _native.lib()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dist_util.barrier()
         torch.cuda.synchronize(local)
 
     def launch():
@@ -274,12 +269,9 @@ def run_gpu_arm(args):
     del prev
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_launch]))
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f'cuda:{local}')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = dist_util.reduce_scalar(elapsed_ms, 'max', device=f'cuda:{local}')   # slowest rank
     per_step = w.batch * L
-    value = world * args.steps * per_step / (elapsed_ms * 1e-3)
+    value = dist_util.reduce_scalar(args.steps * per_step, 'sum', device=f'cuda:{local}') / (elapsed_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ----
     e2e = None
@@ -307,10 +299,7 @@ def run_gpu_arm(args):
             del out
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=f'cuda:{local}')
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        dt = dist_util.reduce_scalar(dt, 'max', device=f'cuda:{local}')
         e2e = {'value': world * steps_e * rows / dt, 'unit': UNIT, 'h2d_bytes_per_step': rows * 8, 'd2h_bytes_per_step': int(d2h),
                'steps': steps_e, 'batches_per_step': Le, 'api': "GCDataset(..., output='numpy').sample_many(L, B, idxs=host)"}
         lib.ogb_host_free(pinned)
