@@ -13,38 +13,53 @@ namespace ogb {
 // oracle/philox_np.py restates exactly this for the tests.
 // ---------------------------------------------------------------------------------------------------------
 enum Purpose : uint32_t {
-  PURPOSE_IDX = 0,      // .x,.y -> transition index position; .z -> crop cy; .w -> crop cx
-  PURPOSE_GOAL_A = 1,   // + 2*goal_set: .x,.y -> random-goal position; .z,.w -> geometric / uniform-distance U
-  PURPOSE_GOAL_B = 2,   // + 2*goal_set: .x,.y -> u_traj; .z,.w -> u_cur
+  PURPOSE_IDX = 0,      // .x,.y -> transition index position; .z -> crop shift (cy, cx jointly)
+  PURPOSE_GOAL = 1,     // + goal_set (0 value, 1 low-value, 2 actor): .x,.y -> random-goal position; .z,.w -> geometric / distance U
+  PURPOSE_MIX = 4,      // 32-bit uniforms of the goal mix: .x value u_traj, .y value u_cur, .z actor u_traj, .w actor u_cur
+  PURPOSE_MIX_LOW = 5,  // .x low-value u_traj, .y low-value u_cur
   PURPOSE_COIN = 7      // row = 0xFFFFFFFF: .x,.y -> the per-batch augmentation coin
 };
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+// The ten round keys (key + i * Weyl constant) are the same for every thread: the host computes them once and the
+// kernel reads them from the constant bank, which removes two adds per round from every draw.
+struct RngKey {
+  uint32_t round_key[10][2];
+  uint32_t stream;
+  uint32_t pad_;
+};
+
+__host__ inline RngKey make_rng_key(uint64_t seed, uint32_t stream) {
+  RngKey k;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    k.round_key[i][0] = k0;
+    k.round_key[i][1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  k.stream = stream;
+  k.pad_ = 0;
+  return k;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const RngKey& key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
   for (int round = 0; round < 10; ++round) {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(M0, c.x), hi1 = __umulhi(M1, c.z);
-#else
-    const uint32_t hi0 = (uint32_t)(((uint64_t)M0 * c.x) >> 32), hi1 = (uint32_t)(((uint64_t)M1 * c.z) >> 32);
-#endif
-    const uint32_t lo0 = M0 * c.x, lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
+    const uint64_t p0 = (uint64_t)M0 * c.x, p1 = (uint64_t)M1 * c.z;   // one IMAD.WIDE each
+    c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ key.round_key[round][0], (uint32_t)p1,
+                   (uint32_t)(p0 >> 32) ^ c.w ^ key.round_key[round][1], (uint32_t)p0);
   }
   return c;
 }
 
-struct RngKey {
-  uint64_t seed;
-  uint32_t stream;
-};
-
 __device__ __forceinline__ uint4 draw4(const RngKey& key, uint64_t batch, uint32_t row, uint32_t purpose) {
   const uint4 ctr = make_uint4(row, (uint32_t)batch, (uint32_t)(batch >> 32), purpose | (key.stream << 8));
-  return philox4x32_10(ctr, make_uint2((uint32_t)key.seed, (uint32_t)(key.seed >> 32)));
+  return philox4x32_10(ctr, key);
 }
+
+// 32-bit uniform in [0, 1) as a double (exact), for the goal-mix coins
+__device__ __forceinline__ double unit_from_word(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
 
 // uniform integer in [0, n): 64-bit multiply-shift, bias < n / 2^64
 __device__ __forceinline__ int64_t bounded_u64(uint32_t hi, uint32_t lo, uint64_t n) {
@@ -56,9 +71,17 @@ __device__ __forceinline__ double unit_double(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-// geometric(p) by inversion, support [1, inf): ceil(log(1-U) / log(1-p)); log_1mp = log(1-p) comes from the host
+// geometric(p) by inversion, support [1, inf): ceil(log(1-U) / log(1-p)); log_1mp = log(1-p) comes from the host.
+// The float32 estimate decides unless the quotient lies close enough to an integer that float error could change
+// the ceiling; only then (a few rows in a thousand) is the float64 expression evaluated.  Both branches return
+// the value of the float64 expression.
 __device__ __forceinline__ int64_t geometric_from_unit(double u, double log_1mp) {
-  const double x = ceil(log(1.0 - u) / log_1mp);
+  const float qf = __fdividef(log1pf(-(float)u), (float)log_1mp);
+  const float cf = ceilf(qf);
+  const float margin = 1e-4f * (1.0f + qf);        // relative float error of the quotient is < 1e-5 for u < 0.99
+  double x;
+  if (u < 0.99 && cf - qf > margin && qf - (cf - 1.0f) > margin) x = (double)cf;
+  else x = ceil(log(1.0 - u) / log_1mp);
   return x < 1.0 ? 1 : (int64_t)x;
 }
 

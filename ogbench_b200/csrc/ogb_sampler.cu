@@ -152,7 +152,7 @@ __global__ void searchsorted_warp_kernel(const int64_t* __restrict__ table, int6
   }
 }
 
-__global__ void philox_fill_kernel(ogb::RngKey key, uint64_t batch, uint32_t purpose, int64_t n, uint4* out) {
+__global__ void philox_fill_kernel(const __grid_constant__ ogb::RngKey key, uint64_t batch, uint32_t purpose, int64_t n, uint4* out) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
     out[r] = ogb::draw4(key, batch, (uint32_t)r, purpose);
 }
@@ -1000,8 +1000,8 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   p.aug_mode = aug_mode;
   p.crop_pad = cfg.crop_padding;
   p.p_aug = cfg.p_aug;
-  p.key.seed = s->seed;
-  p.key.stream = s->stream_id;
+  p.key = make_rng_key(s->seed, s->stream_id);
+  p.need_mix = (!cur_only[0] || !cur_only[2]) ? 1 : 0;
   p.batch0 = s->counter;
   p.batch = batch_size;
   p.total_rows = total;
@@ -1464,7 +1464,7 @@ int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t 
   OGB_CUDA(cudaSetDevice(device));
   uint4* d = nullptr;
   OGB_CUDA(cudaMalloc((void**)&d, std::max<int64_t>(n, 1) * 16));
-  ogb::RngKey key{seed, stream_id};
+  const ogb::RngKey key = ogb::make_rng_key(seed, stream_id);
   if (n > 0) philox_fill_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256>>>(key, batch, purpose, n, d);
   OGB_CUDA(cudaGetLastError());
   OGB_CUDA(cudaMemcpy(out_host, d, (size_t)n * 16, cudaMemcpyDeviceToHost));

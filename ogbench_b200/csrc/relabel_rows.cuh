@@ -90,6 +90,7 @@ struct RelabelParams {
   int32_t k_val, k_act, k_lo;
   int32_t gc_negative;
   int32_t stacked_next;        // frame_stack set: next_observations uses un-clamped idx+1 (datasets.py:231)
+  int32_t need_mix;            // some goal set has 0 < p_cur < 1 or a real traj/random choice: draw the mix uniforms
   int32_t aug_mode;            // draw the per-batch coin (p_aug is not None and not evaluation)
   int32_t crop_pad;
   double p_aug;
@@ -134,39 +135,34 @@ __device__ __forceinline__ int32_t valid_row(const RelabelParams& p, int64_t pos
   return j + lower_bound_bucketed(p.gap_c, p.gap_bucket, p.gap_shift, j + 1);  // upper_bound(c, j)
 }
 
+// `mix` carries the two 32-bit goal-mix uniforms of this goal set (Philox mode; ignored when draws are injected).
 template <bool kInject>
 __device__ __forceinline__ int32_t pick_goal(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
-                                             const uint64_t batch_id, const uint32_t r, const int64_t g) {
+                                             const uint64_t batch_id, const uint32_t r, const int64_t g, const uint2 mix) {
   const GoalSpec& s = p.goal[gs];
-  int64_t rand_pos, offset = 0;
-  double dist = 0.0, u_traj = 0.0, u_cur = 0.0;
+  if (s.cur_only) return i;                                  // p_curgoal == 1.0  (datasets.py:317-318)
   if (kInject) {
     const GoalInject& in = p.in_goal[gs];
-    rand_pos = in.rand_pos[g];
-    if (s.geom) offset = in.offset[g]; else dist = in.dist[g];
-    if (!s.cur_only) { u_traj = in.u_traj[g]; u_cur = in.u_cur[g]; }
-  } else {
-    const uint4 a = draw4(p.key, batch_id, r, PURPOSE_GOAL_A + 2u * (uint32_t)gs);
-    rand_pos = bounded_u64(a.x, a.y, (uint64_t)p.n_choices);
-    const double u = unit_double(a.z, a.w);
-    if (s.geom) offset = geometric_from_unit(u, s.log_1mp); else dist = u;
-    if (!s.cur_only) {
-      const uint4 b = draw4(p.key, batch_id, r, PURPOSE_GOAL_B + 2u * (uint32_t)gs);
-      u_traj = unit_double(b.x, b.y);
-      u_cur = unit_double(b.z, b.w);
+    if (in.u_cur[g] < s.p_cur) return i;                     // np.where(rand < p_cur, idxs, ...)  :325
+    if (!(in.u_traj[g] < s.thr_traj)) return valid_row(p, in.rand_pos[g]);   // random goal  :303,:320-322
+    if (s.geom) {                                            // :309-310
+      const int64_t t = (int64_t)i + in.offset[g];
+      return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
     }
+    const int32_t lo = (i + 1 < fin) ? i + 1 : fin;          // :313-316 -- float64, no FMA contraction, half-even
+    const double d = in.dist[g];
+    return (int32_t)rint(__dadd_rn(__dmul_rn((double)lo, d), __dmul_rn((double)fin, __dsub_rn(1.0, d))));
   }
-  if (s.cur_only) return i;
-  if (u_cur < s.p_cur) return i;                      // np.where(rand < p_cur, idxs, ...)  :325
-  if (!(u_traj < s.thr_traj)) return valid_row(p, rand_pos);  // random goal  :303,:320-322
-  if (s.geom) {                                       // :309-310
-    const int64_t t = (int64_t)i + offset;
+  if (unit_from_word(mix.y) < s.p_cur) return i;
+  const uint4 a = draw4(p.key, batch_id, r, PURPOSE_GOAL + (uint32_t)gs);
+  if (!(unit_from_word(mix.x) < s.thr_traj)) return valid_row(p, bounded_u64(a.x, a.y, (uint64_t)p.n_choices));
+  const double u = unit_double(a.z, a.w);
+  if (s.geom) {
+    const int64_t t = (int64_t)i + geometric_from_unit(u, s.log_1mp);
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
   }
-  // :313-316 -- float64, separate multiply/add (no FMA contraction), round-half-even
   const int32_t lo = (i + 1 < fin) ? i + 1 : fin;
-  const double x = __dadd_rn(__dmul_rn((double)lo, dist), __dmul_rn((double)fin, __dsub_rn(1.0, dist)));
-  return (int32_t)rint(x);
+  return (int32_t)rint(__dadd_rn(__dmul_rn((double)lo, u), __dmul_rn((double)fin, __dsub_rn(1.0, u))));
 }
 
 // datasets.py:478-491
@@ -222,19 +218,21 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
     put_slot(p, sr, SLOT_NEXT, g, nxt);
 
     if (p.kind != 2) {
+      uint4 mix = make_uint4(0, 0, 0, 0);
+      if (!kInject && p.need_mix) mix = draw4(p.key, batch_id, r, PURPOSE_MIX);
       const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
       const int32_t fin = __ldg(p.term + tl);                            // final_state_idxs  :306,:505
       const double neg = p.gc_negative ? 1.0 : 0.0;
       if (p.kind == 0) {
-        const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);
-        const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);
+        const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g, make_uint2(mix.x, mix.y));
+        const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g, make_uint2(mix.z, mix.w));
         put_slot(p, sr, GC_VALUE_GOAL, g, vg);
         put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
         const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
         p.masks[g] = 1.0 - succ;
         p.rewards[g] = succ - neg;
       } else {
-        const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g);          // :508-514
+        const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g, make_uint2(mix.x, mix.y));   // :508-514
         int32_t hv_next, hv_s, lv_next, lv_s;
         subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
         subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
@@ -251,7 +249,9 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         double lv_mask = 1.0 - lv_succ;
         double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
         if (p.has_low_goal) {                                                         // :563-576
-          const int32_t lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g);
+          uint4 mix_low = make_uint4(0, 0, 0, 0);
+          if (!kInject) mix_low = draw4(p.key, batch_id, r, PURPOSE_MIX_LOW);
+          const int32_t lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g, make_uint2(mix_low.x, mix_low.y));
           put_slot(p, sr, HGC_LV_GOAL, g, lvg);
           const double s = (i == lvg) ? 1.0 : 0.0;
           lv_mask = 1.0 - s;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         const double succ = (i == hv) ? 1.0 : 0.0;                                    // :579-582
         p.masks[g] = 1.0 - succ;
         p.rewards[g] = succ - neg;
-        const int32_t ha = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g);          // :585-591
+        const int32_t ha = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g, make_uint2(mix.z, mix.w));   // :585-591
         int32_t ha_next, la_next, unused;
         subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
         subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
@@ -310,8 +310,9 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         }
         if (coin < p.p_aug) {                                                         // :333
           const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
-          const int cy = kInject ? (int)p.in_crop[2 * g] : (int)__umulhi(w0.z, span);
-          const int cx = kInject ? (int)p.in_crop[2 * g + 1] : (int)__umulhi(w0.w, span);
+          const uint32_t joint = __umulhi(w0.z, span * span);            // (cy, cx) jointly uniform on span x span
+          const int cy = kInject ? (int)p.in_crop[2 * g] : (int)(joint / span);
+          const int cx = kInject ? (int)p.in_crop[2 * g + 1] : (int)(joint % span);
           dy = cy - p.crop_pad;
           dx = cx - p.crop_pad;
         }

@@ -18,7 +18,7 @@ M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
 MASK32 = np.uint64(0xFFFFFFFF)
 
-PURPOSE_IDX, PURPOSE_GOAL_A, PURPOSE_GOAL_B, PURPOSE_COIN = 0, 1, 2, 7
+PURPOSE_IDX, PURPOSE_GOAL, PURPOSE_MIX, PURPOSE_MIX_LOW, PURPOSE_COIN = 0, 1, 4, 5, 7
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -80,8 +80,11 @@ def philox_draws(seed, stream, batch_index, batch_size, n_choices, goal_sets, au
     if not idxs_given:
         d.idx_pos = bounded_u64(w[0], w[1], n_choices)
     knife = np.zeros(batch_size, dtype=bool)
+    mix = draw4(seed, stream, batch_index, rows, PURPOSE_MIX)          # value (x, y) and actor (z, w) mix uniforms
+    mix_low = draw4(seed, stream, batch_index, rows, PURPOSE_MIX_LOW)
+    two32 = 4294967296.0
     for slot, geom, discount, cur_only in goal_sets:
-        a = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL_A + 2 * slot)
+        a = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL + slot)
         g = GoalDraws(rand_pos=bounded_u64(a[0], a[1], n_choices))
         u = unit_double(a[2], a[3])
         if geom:
@@ -90,14 +93,15 @@ def philox_draws(seed, stream, batch_index, batch_size, n_choices, goal_sets, au
         else:
             g.dist = u
         if not cur_only:
-            b = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL_B + 2 * slot)
-            g.u_traj = unit_double(b[0], b[1])
-            g.u_cur = unit_double(b[2], b[3])
+            words = {0: (mix[0], mix[1]), 1: (mix_low[0], mix_low[1]), 2: (mix[2], mix[3])}[slot]
+            g.u_traj = words[0].astype(np.float64) / two32
+            g.u_cur = words[1].astype(np.float64) / two32
         d.goals.append(g)
     if aug:
         c = draw4(seed, stream, batch_index, np.array([0xFFFFFFFF], dtype=np.uint64), PURPOSE_COIN)
         d.aug_coin = float(unit_double(c[0], c[1])[0])
         if d.aug_coin < p_aug:
             span = np.uint64(2 * padding + 1)
-            d.crop = np.stack([(w[2] * span) >> np.uint64(32), (w[3] * span) >> np.uint64(32)], axis=1).astype(np.int64)
+            joint = (w[2] * span * span) >> np.uint64(32)                 # (cy, cx) jointly uniform on span x span
+            d.crop = np.stack([joint // span, joint % span], axis=1).astype(np.int64)
     return d, knife
