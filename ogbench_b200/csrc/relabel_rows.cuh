@@ -573,20 +573,33 @@ __global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(con
       if (++c.j == p.n_jobs) { c.j = 0; c.wt += n_warps_global; }
     }
   };
-  // lane l keeps the source row of batch row (wt*32 + l) for the job being issued
-  int32_t issue_rows = 0;
-  int64_t issue_rows_wt = -1;
-  int32_t issue_rows_job = -1;
+  // lane l keeps the source row of batch row (wt*32 + l) for the (tile, job) pair being issued; the vector of the
+  // pair after it is fetched one pair ahead, so its L2/HBM latency is hidden behind a whole job of work
+  auto load_rows = [&](int64_t wt, int j) -> int32_t {
+    if (wt >= n_warp_tiles) return 0;
+    const int64_t g0 = wt << 5;
+    const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
+    return __ldg(p.vec_rows + (int64_t)p.jobs[j].slot * p.total_rows + g0 + min(lane, n - 1));
+  };
+  int32_t issue_rows = load_rows(first_tile, 0);
+  int64_t pref_wt = p.n_jobs > 1 ? first_tile : first_tile + n_warps_global;
+  int32_t pref_job = p.n_jobs > 1 ? 1 : 0;
+  int32_t pref_rows = load_rows(pref_wt, pref_job);
+  int64_t issue_rows_wt = first_tile;
+  int32_t issue_rows_job = 0;
 
   auto issue = [&](const ItemCursor& c, int stage) {
     if (c.wt < n_warp_tiles) {
       const AsyncJob& job = p.jobs[c.j];
       const int64_t g0 = c.wt << 5;
       const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
-      if (issue_rows_wt != c.wt || issue_rows_job != c.j) {
-        issue_rows = __ldg(p.vec_rows + (int64_t)job.slot * p.total_rows + g0 + min(lane, n - 1));
+      if (issue_rows_wt != c.wt || issue_rows_job != c.j) {   // entering the next pair: rotate the prefetched vector in
+        issue_rows = pref_rows;
         issue_rows_wt = c.wt;
         issue_rows_job = c.j;
+        pref_job = c.j + 1 < p.n_jobs ? c.j + 1 : 0;
+        pref_wt = pref_job ? c.wt : c.wt + n_warps_global;
+        pref_rows = load_rows(pref_wt, pref_job);
       }
       const int rows = min((int)job.rows_per_item, n - c.sub);     // may be <= 0 for the ragged last tile
       const uint32_t n_chunks = rows > 0 ? (uint32_t)rows * job.cpr : 0u;
