@@ -39,7 +39,8 @@ typedef enum {
 typedef enum {
   OGB_KIND_GC = 0,    /* GCDataset.sample,  datasets.py:213-294 (non-TRL) */
   OGB_KIND_HGC = 1,   /* HGCDataset.sample, datasets.py:496-643 */
-  OGB_KIND_PLAIN = 2  /* Dataset.sample / get_subset, datasets.py:72-83 */
+  OGB_KIND_PLAIN = 2, /* Dataset.sample / get_subset, datasets.py:72-83 (also ReplayBuffer.sample, :86-146) */
+  OGB_KIND_ATC = 3    /* ATCDataset.sample, datasets.py:369-464 */
 } ogb_kind;
 
 /* One dataset field as handed to Dataset.create(**fields) (datasets.py:45-57): C-contiguous, rows on axis 0. */
@@ -72,6 +73,8 @@ typedef struct {
   const double* neg_reward_lut;  /* [lut_len] -(1 - discount**s)/(1 - discount), numpy-built (datasets.py:537-539) */
   const double* pow_lut;         /* [lut_len] discount**s, numpy-built (datasets.py:541) */
   int32_t dedup_keys;            /* 1: keys that the reference fills with equal values share one buffer */
+  int32_t trl;                   /* config['agent_name'] in (trl, latent_trl, discrete_latent_trl), datasets.py:254-276:
+                                    1 = with the valid_idxs override of :198-204, 2 = without it (lost at :211), 0 = off */
 } ogb_config;
 
 /* Validation mode: the reference's own random draws, in its call order.  Host pointers,
@@ -90,6 +93,7 @@ typedef struct {
   int32_t has_aug_coin;
   double aug_coin;           /* rand(), datasets.py:279 / :622 */
   const int64_t* crop;       /* [batch,2] randint(0, 2*padding+1), datasets.py:333; NULL unless the coin passed */
+  const int64_t* trl_midpoints; /* randint(idxs, value_goal_idxs), datasets.py:259 (TRL samplers only) */
 } ogb_draws;
 
 typedef struct {
@@ -125,6 +129,7 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
                        ogb_sampler** out);
 int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream);    /* launch on the caller's stream instead */
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep_index_vectors);
+int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out);   /* len(dataset.valid_idxs) as this sampler sees it (TRL overrides it) */
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out);
 int ogb_sampler_copy_bounds(const ogb_sampler* s, int64_t* terminal_locs, int64_t* initial_locs); /* host out */
 int ogb_sampler_get_counter(const ogb_sampler* s, uint64_t* out); /* checkpointable RNG position */
@@ -138,6 +143,17 @@ int ogb_sampler_destroy(ogb_sampler* s);
  * after enqueueing on the sampler's stream. */
 int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs,
                        int32_t evaluation, const ogb_draws* draws, ogb_batch** out);
+
+/* get_observations / get_goal_observations (datasets.py:341-357): one-key batch with rows `idxs` (host) of the
+ * observations (frame-stacked as configured; which = 0) or of the goal representation (which = 1). */
+int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out);
+
+/* ATCDataset (datasets.py:369-464), for samplers created with OGB_KIND_ATC.  The anchor set of a temporal offset k
+ * (get_valid_atc_idxs, :417-436) is built once per k and cached, like the reference's _atc_valid_cache. */
+int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out);
+int ogb_sampler_copy_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out_host);
+int ogb_sampler_sample_atc(ogb_sampler* s, int64_t batch_size, int32_t n_batches, int64_t k, int32_t evaluation,
+                           const ogb_draws* draws, ogb_batch** out);
 
 int ogb_batch_num_keys(const ogb_batch* b, int32_t* out);
 int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out);

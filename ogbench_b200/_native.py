@@ -14,7 +14,7 @@ OGB_MAX_NDIM = 6
 OGB_MAX_SLOTS = 10
 
 OGB_OK, OGB_ERR_INVALID, OGB_ERR_ASSERT, OGB_ERR_INDEX, OGB_ERR_CUDA, OGB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-KIND_GC, KIND_HGC, KIND_PLAIN = 0, 1, 2
+KIND_GC, KIND_HGC, KIND_PLAIN, KIND_ATC = 0, 1, 2, 3
 
 _DTYPES = [
     (np.uint8, 0), (np.int8, 1), (np.int16, 2), (np.int32, 3), (np.int64, 4), (np.float16, 5), (np.float32, 6),
@@ -43,6 +43,7 @@ class Config(C.Structure):
         ('lut_len', C.c_int32),
         ('neg_reward_lut', C.POINTER(C.c_double)), ('pow_lut', C.POINTER(C.c_double)),
         ('dedup_keys', C.c_int32),
+        ('trl', C.c_int32),
     ]
 
 
@@ -53,7 +54,7 @@ class GoalDraws(C.Structure):
 
 class Draws(C.Structure):
     _fields_ = [('idx_pos', C.c_void_p), ('goals', GoalDraws * 3), ('has_aug_coin', C.c_int32),
-                ('aug_coin', C.c_double), ('crop', C.c_void_p)]
+                ('aug_coin', C.c_double), ('crop', C.c_void_p), ('trl_midpoints', C.c_void_p)]
 
 
 class KeyInfo(C.Structure):
@@ -81,12 +82,17 @@ SIGNATURES = [
     ('ogb_sampler_create', C.c_int, [_P, C.POINTER(Config), C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
     ('ogb_sampler_set_stream', C.c_int, [_P, _P]),
     ('ogb_sampler_set_debug', C.c_int, [_P, C.c_int32]),
+    ('ogb_sampler_num_choices', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_num_terminals', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_copy_bounds', C.c_int, [_P, _P, _P]),
     ('ogb_sampler_get_counter', C.c_int, [_P, C.POINTER(C.c_uint64)]),
     ('ogb_sampler_set_counter', C.c_int, [_P, C.c_uint64]),
     ('ogb_sampler_destroy', C.c_int, [_P]),
     ('ogb_sampler_sample', C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.POINTER(Draws), C.POINTER(_P)]),
+    ('ogb_sampler_gather', C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(_P)]),
+    ('ogb_sampler_num_atc_anchors', C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
+    ('ogb_sampler_copy_atc_anchors', C.c_int, [_P, C.c_int64, _P]),
+    ('ogb_sampler_sample_atc', C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.POINTER(Draws), C.POINTER(_P)]),
     ('ogb_batch_num_keys', C.c_int, [_P, C.POINTER(C.c_int32)]),
     ('ogb_batch_key_info', C.c_int, [_P, C.c_int32, C.POINTER(KeyInfo)]),
     ('ogb_batch_nbytes', C.c_int, [_P, C.POINTER(C.c_size_t)]),

@@ -17,6 +17,7 @@ enum Purpose : uint32_t {
   PURPOSE_GOAL = 1,     // + goal_set (0 value, 1 low-value, 2 actor): .x,.y -> random-goal position; .z,.w -> geometric / distance U
   PURPOSE_MIX = 4,      // 32-bit uniforms of the goal mix: .x value u_traj, .y value u_cur, .z actor u_traj, .w actor u_cur
   PURPOSE_MIX_LOW = 5,  // .x low-value u_traj, .y low-value u_cur
+  PURPOSE_TRL_MID = 6,  // .x,.y -> TRL midpoint position in [idx, value goal)
   PURPOSE_COIN = 7      // row = 0xFFFFFFFF: .x,.y -> the per-batch augmentation coin
 };
 

@@ -160,7 +160,7 @@ __global__ void philox_fill_kernel(const __grid_constant__ ogb::RngKey key, uint
 enum Route { ROUTE_ROW = 0, ROUTE_FRAMES = 1, ROUTE_SCALAR = 2 };
 enum ScalarKind {
   SC_MASKS = 0, SC_REWARDS, SC_HV_OFFSETS, SC_HV_STEPS, SC_HV_MASKS, SC_HV_REWARDS, SC_LV_STEPS, SC_LV_MASKS, SC_LV_REWARDS,
-  SC_COUNT
+  SC_TRL_OFFSETS, SC_TRL_MID_OFFSETS, SC_COUNT
 };
 
 struct KeyPlan {
@@ -204,6 +204,7 @@ struct ogb_dataset {
   int32_t* d_gap_bucket = nullptr;
   int gap_shift = 0;
   std::vector<uint8_t> terminals_host;  // terminals > 0, one byte per row (tiny next to the data)
+  std::vector<uint8_t> valid_host;      // valids > 0 (empty when the dataset has no 'valids')
   size_t resident_bytes = 0;
   int sm_count = 148;
 
@@ -238,6 +239,12 @@ struct ogb_sampler {
   std::mutex mu;
   // Batch blocks are recycled through this small per-sampler cache instead of going back to the driver: a block
   // released by the consumer is handed to a later sample() on the same stream (stream order makes that safe).
+  struct AtcTable {
+    std::vector<int32_t> host;
+    int32_t* dev = nullptr;
+  };
+  std::map<int64_t, AtcTable> atc_tables;      // ATC anchor rows per temporal offset k (datasets.py:417-436)
+  AtcTable trl_rows;                           // TRL: valid_idxs override = every non-terminal row (datasets.py:198-204)
   cudaStream_t aux_stream = nullptr;           // index kernels of chunked launches
   std::vector<cudaEvent_t> chunk_events;       // ring of join events (index kernel -> gathers)
   int next_event = 0;
@@ -369,6 +376,8 @@ void sampler_unref(ogb_sampler* s) {
     cudaFree(blk.ptr);
   }
   if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
+  for (auto& kv : s->atc_tables) if (kv.second.dev) cudaFree(kv.second.dev);
+  if (s->trl_rows.dev) cudaFree(s->trl_rows.dev);
   if (s->d_term) cudaFree(s->d_term);
   if (s->d_term_bucket) cudaFree(s->d_term_bucket);
   if (s->d_neg_lut) cudaFree(s->d_neg_lut);
@@ -497,12 +506,32 @@ std::vector<KeyPlan> build_plan(const ogb_sampler* s, bool evaluation) {
     if (s->cfg.low_subgoal_steps == s->cfg.value_subgoal_steps) pb.slot_canon[HGC_LV_NEXT] = HGC_HV_NEXT;
     if (s->cfg.low_subgoal_steps == s->cfg.actor_subgoal_steps) pb.slot_canon[HGC_LA_NEXT] = HGC_HA_NEXT;
   }
+  if (s->kind == OGB_KIND_ATC) {                    // datasets.py:406-413
+    pb.obs_key("observations", SLOT_IDX, true);
+    pb.obs_key("positive_observations", SLOT_NEXT, true);
+    return pb.keys;
+  }
   pb.base_keys();
   if (s->kind == OGB_KIND_GC) {                     // datasets.py:248-252, aug list :280
     pb.goal_key("value_goals", GC_VALUE_GOAL, true);
     pb.goal_key("actor_goals", GC_ACTOR_GOAL, true);
     pb.scalar_key("masks", SC_MASKS, OGB_F64);
     pb.scalar_key("rewards", SC_REWARDS, OGB_F64);
+    if (s->cfg.trl) {                               // datasets.py:254-276, aug list :281-291
+      const int actions = s->ds->find("actions");
+      pb.obs_key("value_goal_observations", GC_VALUE_GOAL, true);
+      pb.obs_key("actor_goal_observations", GC_VALUE_GOAL, true);   // the reference gathers value_goal_idxs here too (:262)
+      pb.scalar_key("value_offsets", SC_TRL_OFFSETS, OGB_I64);
+      pb.scalar_key("value_midpoint_offsets", SC_TRL_MID_OFFSETS, OGB_I64);
+      pb.obs_key("value_midpoint_observations", GC_TRL_MID, true);
+      if (actions >= 0) {
+        pb.field_key("value_midpoint_actions", actions, GC_TRL_MID, false);
+        pb.field_key("next_actions", actions, GC_TRL_PLUS1, false);
+      }
+      pb.goal_key("value_midpoint_goals", GC_TRL_MID, true);
+      pb.goal_key("value_cur_goals", SLOT_IDX, true);
+      pb.goal_key("value_next_goals", GC_TRL_PLUS1, true);
+    }
   } else if (s->kind == OGB_KIND_HGC) {             // datasets.py:526-619, aug list :625-640
     pb.obs_key("high_value_reps", SLOT_IDX, false);
     pb.goal_key("high_value_goals", HGC_HV_GOAL, true);
@@ -704,6 +733,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
     std::vector<uint8_t> valid;
     rc = host_copy_1d(ds->valids_field, &valid);
     if (rc) return bail(rc);
+    ds->valid_host = valid;
     std::vector<int32_t> table, gaps;
     for (int64_t r = 0; r < size; ++r) {
       if (valid[(size_t)r]) table.push_back((int32_t)r);
@@ -752,10 +782,14 @@ int ogb_dataset_destroy(ogb_dataset* ds) {
 
 int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uint64_t seed, uint32_t stream_id, ogb_sampler** out) {
   if (!ds || !cfg || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_create: null argument");
-  if (kind < OGB_KIND_GC || kind > OGB_KIND_PLAIN) return fail(OGB_ERR_INVALID, "unknown sampler kind %d", kind);
+  if (kind < OGB_KIND_GC || kind > OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "unknown sampler kind %d", kind);
   if (stream_id >= (1u << 24)) return fail(OGB_ERR_INVALID, "stream_id must be < 2^24");
   OGB_CUDA(cudaSetDevice(ds->device));
-  if (kind != OGB_KIND_PLAIN) {
+  if (kind == OGB_KIND_ATC) {
+    if (ds->terminals_field < 0) return fail(OGB_ERR_INVALID, "KeyError: 'terminals'");
+    if (cfg->frame_stack > 0 && ds->next_obs_field >= 0)
+      return fail(OGB_ERR_ASSERT, "frame_stack needs a compact dataset: 'next_observations' present (datasets.py:396)");
+  } else if (kind != OGB_KIND_PLAIN) {
     if (ds->terminals_field < 0) return fail(OGB_ERR_INVALID, "KeyError: 'terminals'");
     auto close1 = [](double x) { return std::fabs(x - 1.0) <= 1e-8 + 1e-5; };  // np.isclose(x, 1.0)
     if (!close1(cfg->value_p_curgoal + cfg->value_p_trajgoal + cfg->value_p_randomgoal))
@@ -799,6 +833,13 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
     int rc = upload_vector(s->term_host, &s->d_term);
     if (!rc) rc = upload_vector(bucket, &s->d_term_bucket);
     if (rc) return bail(rc);
+    if (kind == OGB_KIND_GC && cfg->trl == 1) {  // datasets.py:198-204: arange(cur, terminal) for every terminal row
+      for (int64_t r = 0; r < ds->size; ++r)
+        if (!ds->terminals_host[(size_t)r]) s->trl_rows.host.push_back((int32_t)r);
+      if (s->trl_rows.host.empty()) return bail(fail(OGB_ERR_INVALID, "TRL: the dataset has no non-terminal row"));
+      rc = upload_vector(s->trl_rows.host, &s->trl_rows.dev);
+      if (rc) return bail(rc);
+    }
     if (kind == OGB_KIND_HGC) {
       std::vector<double> neg(cfg->neg_reward_lut, cfg->neg_reward_lut + cfg->lut_len), pw(cfg->pow_lut, cfg->pow_lut + cfg->lut_len);
       rc = upload_vector(neg, &s->d_neg_lut);
@@ -806,7 +847,7 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
       if (rc) return bail(rc);
     }
   }
-  s->n_slots = kind == OGB_KIND_GC ? ogb::GC_NUM_SLOTS : (kind == OGB_KIND_HGC ? ogb::HGC_NUM_SLOTS : 2);
+  s->n_slots = kind == OGB_KIND_GC ? (cfg->trl ? ogb::GC_TRL_NUM_SLOTS : ogb::GC_NUM_SLOTS) : (kind == OGB_KIND_HGC ? ogb::HGC_NUM_SLOTS : 2);
   s->plan[0] = build_plan(s, false);
   s->plan[1] = build_plan(s, true);
   *out = s;
@@ -826,6 +867,12 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->debug = keep != 0;
+  return 0;
+}
+int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  if (s->trl_rows.dev) *out = (int64_t)s->trl_rows.host.size();
+  else *out = s->ds->valid_mode == 0 ? s->ds->size : s->ds->n_valid;
   return 0;
 }
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out) {
@@ -857,8 +904,23 @@ int ogb_sampler_destroy(ogb_sampler* s) {
   return 0;
 }
 
-int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
-                       const ogb_draws* draws, ogb_batch** out) {
+}  // extern "C"
+
+namespace {
+
+// What one launch sequence computes: the sampler's own plan (sample) or a derived one (gather, ATC).
+struct RunSpec {
+  int kind;                              // index-kernel behaviour: OGB_KIND_*
+  const std::vector<KeyPlan>* plan;
+  int n_slots;
+  int64_t next_offset = 1;               // SLOT_NEXT = idx + next_offset (ATC: the temporal offset k)
+  const int32_t* choice_table = nullptr; // ATC: anchor rows for this k (replaces the valid-row table)
+  int64_t n_choices = -1;
+  bool trl = false;
+};
+
+int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
+               const ogb_draws* draws, ogb_batch** out) {
   using namespace ogb;
   if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
   if (batch_size < 1 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size and n_batches must be >= 1");
@@ -867,18 +929,18 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   const ogb_config& cfg = s->cfg;
   const int64_t total = batch_size * (int64_t)n_batches;
   if (total > (int64_t)1 << 31) return fail(OGB_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
-  const bool stacked_next = cfg.frame_stack > 0 && s->kind != OGB_KIND_PLAIN;
+  const bool stacked_next = (cfg.frame_stack > 0 && spec.kind != OGB_KIND_PLAIN) || spec.kind == OGB_KIND_ATC;
   if (idxs) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
     for (int64_t r = 0; r < total; ++r)
-      if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + 1 >= ds->size))
+      if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + spec.next_offset >= ds->size))
         return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
   }
-  const int64_t n_choices = ds->valid_mode == 0 ? ds->size : ds->n_valid;
-  const bool aug_mode = cfg.has_p_aug && !evaluation && s->kind != OGB_KIND_PLAIN;
-  const int n_goal_sets = s->kind == OGB_KIND_PLAIN ? 0 : 3;
+  const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->size : ds->n_valid);
+  const bool aug_mode = cfg.has_p_aug && !evaluation && spec.kind != OGB_KIND_PLAIN;
+  const int n_goal_sets = (spec.kind == OGB_KIND_GC || spec.kind == OGB_KIND_HGC) ? 3 : 0;
   const bool geom[3] = {cfg.value_geom_sample != 0, true, cfg.actor_geom_sample != 0};
   const bool cur_only[3] = {cfg.value_p_curgoal == 1.0, cfg.value_p_curgoal == 1.0, cfg.actor_p_curgoal == 1.0};
-  const bool goal_used[3] = {true, s->kind == OGB_KIND_HGC && cfg.has_low_discount, true};
+  const bool goal_used[3] = {true, spec.kind == OGB_KIND_HGC && cfg.has_low_discount, true};
   if (draws) {
     if (!idxs && !draws->idx_pos) return fail(OGB_ERR_INVALID, "validation mode needs idx_pos or idxs");
     for (int gs = 0; gs < n_goal_sets; ++gs) {
@@ -898,7 +960,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   OGB_CUDA(cudaSetDevice(ds->device));
   std::lock_guard<std::mutex> lock(s->mu);
 
-  const std::vector<KeyPlan>& plan = s->plan[evaluation ? 1 : 0];
+  const std::vector<KeyPlan>& plan = *spec.plan;
   bool any_frames = false;
   for (const KeyPlan& k : plan) any_frames |= (k.route == ROUTE_FRAMES && k.alias_of < 0);
   const bool want_crop = any_frames;
@@ -913,7 +975,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   b->total_rows = total;
   b->keys = plan;
   b->offsets.assign(plan.size(), 0);
-  b->n_slots = s->n_slots;
+  b->n_slots = spec.n_slots;
   size_t cursor = 0;
   for (size_t i = 0; i < plan.size(); ++i) {
     if (plan[i].alias_of >= 0) continue;
@@ -924,9 +986,10 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
     if (plan[i].alias_of >= 0) b->offsets[i] = b->offsets[(size_t)plan[i].alias_of];
   b->keys_bytes = cursor;
   auto carve = [&](size_t bytes) { size_t off = cursor; cursor = round_up(cursor + bytes, 256); return off; };
+  size_t off_trl_mid = 0;
   size_t off_rows = 0, off_init = 0, off_crop = 0, off_idxs = 0, off_draw_i64[1 + 3 * 2 + 1] = {0}, off_draw_f64[3 * 3] = {0};
-  off_rows = carve((size_t)s->n_slots * total * 4);
-  if (want_init) off_init = carve((size_t)s->n_slots * total * 4);
+  off_rows = carve((size_t)spec.n_slots * total * 4);
+  if (want_init) off_init = carve((size_t)spec.n_slots * total * 4);
   if (want_crop) off_crop = carve((size_t)total * 2);
   if (idxs) off_idxs = carve((size_t)total * 8);
   if (draws) {
@@ -937,6 +1000,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       for (int q = 0; q < 3; ++q) off_draw_f64[3 * gs + q] = carve((size_t)batch_size * 8);
     }
     off_draw_i64[7] = carve((size_t)batch_size * 16);
+    if (spec.trl) off_trl_mid = carve((size_t)batch_size * 8);
   }
   b->block_bytes = std::max<size_t>(cursor, 256);
   auto bail = [&](int code) { batch_unref(b); return code; };
@@ -971,11 +1035,13 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   p.term = s->d_term;
   p.term_bucket = s->d_term_bucket;
   p.term_shift = s->term_shift;
-  p.valid_table = ds->d_valid_table;
+  p.valid_table = spec.choice_table ? spec.choice_table : ds->d_valid_table;
   p.gap_c = ds->d_gap_c;
   p.gap_bucket = ds->d_gap_bucket;
   p.gap_shift = ds->gap_shift;
-  p.valid_mode = ds->valid_mode;
+  p.valid_mode = spec.choice_table ? 1 : ds->valid_mode;
+  p.next_offset = (int32_t)spec.next_offset;
+  p.trl = spec.trl ? 1 : 0;
   p.n_choices = n_choices;
   p.n_rows_ds = (int32_t)ds->size;
   const double p_cur[3] = {cfg.value_p_curgoal, cfg.value_p_curgoal, cfg.actor_p_curgoal};
@@ -990,7 +1056,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   }
   p.neg_lut = s->d_neg_lut;
   p.pow_lut = s->d_pow_lut;
-  p.kind = s->kind;
+  p.kind = spec.kind;
   p.has_low_goal = goal_used[1];
   p.k_val = cfg.value_subgoal_steps;
   p.k_act = cfg.actor_subgoal_steps;
@@ -1005,7 +1071,7 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   p.batch0 = s->counter;
   p.batch = batch_size;
   p.total_rows = total;
-  p.n_slots = s->n_slots;
+  p.n_slots = spec.n_slots;
   p.vec_rows = b->vec_rows;
   p.vec_init = b->vec_init;
   p.crop_out = b->crop;
@@ -1031,6 +1097,11 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       if (d.u_cur && e == cudaSuccess) { e = h2d(off_draw_f64[3 * gs + 2], d.u_cur, (size_t)batch_size * 8); p.in_goal[gs].u_cur = (const double*)(base + off_draw_f64[3 * gs + 2]); }
     }
     if (draws->crop && e == cudaSuccess) { e = h2d(off_draw_i64[7], draws->crop, (size_t)batch_size * 16); p.in_crop = (const int64_t*)(base + off_draw_i64[7]); }
+    if (spec.trl && e == cudaSuccess) {
+      if (!draws->trl_midpoints) return bail(fail(OGB_ERR_INVALID, "validation mode: TRL midpoint draws are missing"));
+      e = h2d(off_trl_mid, draws->trl_midpoints, (size_t)batch_size * 8);
+      p.in_trl_mid = (const int64_t*)(base + off_trl_mid);
+    }
     p.in_coin = draws->has_aug_coin ? draws->aug_coin : 2.0;
     if (p.aug_mode && !(p.in_coin < p.p_aug)) p.in_crop = nullptr;
     if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of validation draws failed: %s", cudaGetErrorString(e)));
@@ -1048,6 +1119,8 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
       case SC_LV_STEPS: p.lv_steps = (int64_t*)ptr; break;
       case SC_LV_MASKS: p.lv_masks = (double*)ptr; break;
       case SC_LV_REWARDS: p.lv_rewards = (double*)ptr; break;
+      case SC_TRL_OFFSETS: p.trl_offsets = (int64_t*)ptr; break;
+      case SC_TRL_MID_OFFSETS: p.trl_mid_offsets = (int64_t*)ptr; break;
       default: break;
     }
   }
@@ -1289,6 +1362,112 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
   if (!draws) s->counter += (uint64_t)n_batches;
   *out = b;
   return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
+                       const ogb_draws* draws, ogb_batch** out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
+  if (s->kind == OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "an ATC sampler is sampled with ogb_sampler_sample_atc");
+  RunSpec spec;
+  spec.kind = s->kind;
+  spec.plan = &s->plan[evaluation ? 1 : 0];
+  spec.n_slots = s->n_slots;
+  spec.trl = s->cfg.trl != 0 && s->kind == OGB_KIND_GC;
+  if (s->trl_rows.dev) {
+    spec.choice_table = s->trl_rows.dev;
+    spec.n_choices = (int64_t)s->trl_rows.host.size();
+  }
+  return run_sample(s, spec, batch_size, n_batches, idxs, evaluation, draws, out);
+}
+
+// get_observations / get_goal_observations (datasets.py:341-357): rows `idxs` of the observations (frame-stacked as
+// the sampler's config says) or of the goal representation.
+int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out) {
+  if (!s || !idxs || !out || n < 1) return fail(OGB_ERR_INVALID, "ogb_sampler_gather: bad argument");
+  if (which < 0 || which > 1) return fail(OGB_ERR_INVALID, "which must be 0 (observations) or 1 (goal observations)");
+  PlanBuilder pb;
+  pb.ds = s->ds;
+  pb.cfg = &s->cfg;
+  pb.crop_possible = false;
+  for (int v = 0; v < ogb::kMaxSlots; ++v) pb.slot_canon[v] = v;
+  if (which == 0) pb.obs_key("observations", ogb::SLOT_IDX, false);
+  else pb.goal_key("goal_observations", ogb::SLOT_IDX, false);
+  RunSpec spec;
+  spec.kind = OGB_KIND_PLAIN;
+  spec.plan = &pb.keys;
+  spec.n_slots = 2;
+  const int fs = s->cfg.frame_stack;
+  if (fs > 0 && s->term_host.empty()) return fail(OGB_ERR_INVALID, "frame stacking needs trajectory boundaries");
+  return run_sample(s, spec, n, 1, idxs, 1, nullptr, out);
+}
+
+namespace {
+// get_valid_atc_idxs (datasets.py:417-436): anchors i with i + k < size and i + k <= final_state(i), valid rows only
+int atc_anchors(ogb_sampler* s, int64_t k, const std::vector<int32_t>** host, const int32_t** dev) {
+  auto it = s->atc_tables.find(k);
+  if (it == s->atc_tables.end()) {
+    const ogb_dataset* ds = s->ds;
+    ogb_sampler::AtcTable t;
+    size_t ti = 0;
+    for (int64_t i = 0; i < ds->size; ++i) {
+      while (ti < s->term_host.size() && s->term_host[ti] < i) ++ti;   // final_state(i) = first terminal >= i
+      if (!ds->valid_host.empty() && !ds->valid_host[(size_t)i]) continue;
+      if (i + k >= ds->size || ti >= s->term_host.size()) continue;
+      if (i + k <= (int64_t)s->term_host[ti]) t.host.push_back((int32_t)i);
+    }
+    if (t.host.empty()) return fail(OGB_ERR_INVALID, "No valid ATC indices found for k=%lld.", (long long)k);
+    int rc = upload_vector(t.host, &t.dev);
+    if (rc) return rc;
+    it = s->atc_tables.emplace(k, std::move(t)).first;
+  }
+  if (host) *host = &it->second.host;
+  if (dev) *dev = it->second.dev;
+  return 0;
+}
+}  // namespace
+
+int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
+  std::lock_guard<std::mutex> lock(s->mu);
+  const std::vector<int32_t>* host;
+  OGB_TRY(atc_anchors(s, k, &host, nullptr));
+  *out = (int64_t)host->size();
+  return 0;
+}
+int ogb_sampler_copy_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(s->mu);
+  const std::vector<int32_t>* host;
+  OGB_TRY(atc_anchors(s, k, &host, nullptr));
+  for (size_t i = 0; i < host->size(); ++i) out[i] = (*host)[i];
+  return 0;
+}
+
+// ATCDataset.sample (datasets.py:401-415): anchor rows for the temporal offset k, observations at idx and idx + k
+int ogb_sampler_sample_atc(ogb_sampler* s, int64_t batch_size, int32_t n_batches, int64_t k, int32_t evaluation,
+                           const ogb_draws* draws, ogb_batch** out) {
+  if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  if (s->kind != OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "not an ATC sampler");
+  if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
+  const std::vector<int32_t>* host;
+  const int32_t* dev;
+  {
+    std::lock_guard<std::mutex> lock(s->mu);
+    OGB_TRY(atc_anchors(s, k, &host, &dev));
+  }
+  RunSpec spec;
+  spec.kind = OGB_KIND_ATC;
+  spec.plan = &s->plan[evaluation ? 1 : 0];
+  spec.n_slots = 2;
+  spec.next_offset = k;
+  spec.choice_table = dev;
+  spec.n_choices = (int64_t)host->size();
+  return run_sample(s, spec, batch_size, n_batches, nullptr, evaluation, draws, out);
 }
 
 int ogb_batch_num_keys(const ogb_batch* b, int32_t* out) {

@@ -23,6 +23,7 @@ constexpr int kGatherMinBlocks = 4;   // resident CTAs per SM the gather kernel 
 enum : int {
   SLOT_IDX = 0, SLOT_NEXT = 1,
   GC_VALUE_GOAL = 2, GC_ACTOR_GOAL = 3, GC_NUM_SLOTS = 4,
+  GC_TRL_MID = 4, GC_TRL_PLUS1 = 5, GC_TRL_NUM_SLOTS = 6,
   HGC_HV_GOAL = 2, HGC_HV_NEXT = 3, HGC_LV_NEXT = 4, HGC_HA_GOAL = 5, HGC_HA_NEXT = 6, HGC_LA_GOAL = 7,
   HGC_LA_NEXT = 8, HGC_LV_GOAL = 9, HGC_NUM_SLOTS = 10
 };
@@ -85,7 +86,12 @@ struct RelabelParams {
   GoalSpec goal[3];            // value, low-value, actor
   const double* neg_lut;       // -(1 - discount**s)/(1 - discount)
   const double* pow_lut;       // discount**s
-  int32_t kind;                // 0 GC, 1 HGC, 2 PLAIN
+  int32_t kind;                // 0 GC, 1 HGC, 2 PLAIN, 3 ATC
+  int32_t next_offset;         // SLOT_NEXT = idx + next_offset (1; the temporal offset k for ATC)
+  int32_t trl;                 // TRL branch of GCDataset.sample (datasets.py:254-276)
+  const int64_t* in_trl_mid;   // injected randint(idxs, value_goal_idxs)
+  int64_t* trl_offsets;
+  int64_t* trl_mid_offsets;
   int32_t has_low_goal;
   int32_t k_val, k_act, k_lo;
   int32_t gc_negative;
@@ -214,10 +220,11 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
       i = valid_row(p, pos);                                            // datasets.py:65-70
     }
     put_slot(p, sr, SLOT_IDX, g, i);
-    const int32_t nxt = p.stacked_next ? i + 1 : (i + 1 < p.n_rows_ds ? i + 1 : p.n_rows_ds - 1);  // :82 / :231
+    const int32_t nxt = p.stacked_next ? i + p.next_offset                                           // :231 / :408
+                                       : (i + p.next_offset < p.n_rows_ds ? i + p.next_offset : p.n_rows_ds - 1);  // :82
     put_slot(p, sr, SLOT_NEXT, g, nxt);
 
-    if (p.kind != 2) {
+    if (p.kind == 0 || p.kind == 1) {
       uint4 mix = make_uint4(0, 0, 0, 0);
       if (!kInject && p.need_mix) mix = draw4(p.key, batch_id, r, PURPOSE_MIX);
       const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
@@ -231,6 +238,20 @@ __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __
         const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
         p.masks[g] = 1.0 - succ;
         p.rewards[g] = succ - neg;
+        if (p.trl) {                                                     // :259-267
+          const int64_t span = vg > i ? (int64_t)vg - i : 1;             // the reference asserts idxs != value_goal_idxs
+          int32_t mid;
+          if (kInject) {
+            mid = (int32_t)p.in_trl_mid[g];
+          } else {
+            const uint4 t = draw4(p.key, batch_id, r, PURPOSE_TRL_MID);
+            mid = i + (int32_t)bounded_u64(t.x, t.y, (uint64_t)span);    // randint(idxs, value_goal_idxs): [i, vg)
+          }
+          put_slot(p, sr, GC_TRL_MID, g, mid);
+          put_slot(p, sr, GC_TRL_PLUS1, g, i + 1);
+          p.trl_offsets[g] = (int64_t)vg - i;
+          p.trl_mid_offsets[g] = (int64_t)mid - i;
+        }
       } else {
         const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g, make_uint2(mix.x, mix.y));   // :508-514
         int32_t hv_next, hv_s, lv_next, lv_s;

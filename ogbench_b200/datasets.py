@@ -204,7 +204,7 @@ class _Sampler:
     """Thin owner of an ogb_sampler handle; builds the C config from the reference's config mapping."""
 
     def __init__(self, dataset: Dataset, config, kind: int, device: int = 0, seed: int = 0, stream_id: int = 0,
-                 dedup: bool = True, output: str = 'device'):
+                 dedup: bool = True, output: str = 'device', crop_padding: int = 3):
         assert output in ('device', 'numpy')
         self.dataset = dataset
         self.kind = kind
@@ -213,8 +213,14 @@ class _Sampler:
         self._keepalive = []
         cfg = _native.Config()
         cfg.dedup_keys = int(dedup)
-        cfg.crop_padding = 3  # GCDataset.augment, datasets.py:331
-        if kind != _native.KIND_PLAIN:
+        cfg.crop_padding = crop_padding  # 3 in GCDataset.augment (datasets.py:331); ATC: config['augment_padding'] (:440)
+        if kind == _native.KIND_ATC:
+            p_aug = config['p_aug']
+            cfg.has_p_aug = int(p_aug is not None)
+            cfg.p_aug = float(p_aug) if p_aug is not None else 0.0
+            fs = config['frame_stack']
+            cfg.frame_stack = int(fs) if fs is not None else 0
+        elif kind != _native.KIND_PLAIN:
             cfg.discount = float(config['discount'])
             for side in ('value', 'actor'):
                 for part in ('cur', 'traj', 'random'):
@@ -226,6 +232,7 @@ class _Sampler:
             cfg.p_aug = float(p_aug) if p_aug is not None else 0.0
             fs = config['frame_stack']
             cfg.frame_stack = int(fs) if fs is not None else 0
+            cfg.trl = int(kind == _native.KIND_GC and config.get('agent_name') in TRL_AGENTS)
         if kind == _native.KIND_HGC:
             # datasets.py:515-518, :543, :592-594 -- the optional overrides, resolved as the reference resolves them
             high = config.get('high_subgoal_steps', config['subgoal_steps'])
@@ -300,6 +307,33 @@ class _Sampler:
                                              C.byref(c_draws) if c_draws is not None else None, C.byref(out)))
         return BatchHandle(out, self.device, None)
 
+    def num_choices(self) -> int:
+        n = C.c_int64()
+        _native.check(_native.lib().ogb_sampler_num_choices(self.ptr, C.byref(n)))
+        return n.value
+
+    def gather(self, which: int, idxs):
+        """get_observations (which=0) / get_goal_observations (which=1) for explicit rows; returns one array."""
+        idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64).reshape(-1)
+        out = C.c_void_p()
+        _native.check(_native.lib().ogb_sampler_gather(self.ptr, which, idxs.ctypes.data_as(C.c_void_p), len(idxs), C.byref(out)))
+        return next(iter(self.wrap(BatchHandle(out, self.device, None)).values()))
+
+    def sample_atc(self, batch_size, k, evaluation=False, draws=None, n_batches=1):
+        keep = []
+        c_draws = _pack_draws(draws, keep) if draws is not None else None
+        out = C.c_void_p()
+        _native.check(_native.lib().ogb_sampler_sample_atc(self.ptr, int(batch_size), int(n_batches), int(k), int(bool(evaluation)),
+                                                           C.byref(c_draws) if c_draws is not None else None, C.byref(out)))
+        return self.wrap(BatchHandle(out, self.device, None))
+
+    def atc_anchors(self, k) -> np.ndarray:
+        n = C.c_int64()
+        _native.check(_native.lib().ogb_sampler_num_atc_anchors(self.ptr, int(k), C.byref(n)))
+        out = np.empty(n.value, dtype=np.int64)
+        _native.check(_native.lib().ogb_sampler_copy_atc_anchors(self.ptr, int(k), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def wrap(self, handle: BatchHandle) -> Dict[str, Any]:
         lib = _native.lib()
         n = C.c_int32()
@@ -354,6 +388,7 @@ def _pack_draws(draws, keep) -> _native.Draws:
     d.has_aug_coin = int(draws.aug_coin is not None)
     d.aug_coin = float(draws.aug_coin) if draws.aug_coin is not None else 0.0
     d.crop = ptr(getattr(draws, 'crop', None), np.int64)
+    d.trl_midpoints = ptr(getattr(draws, 'trl_midpoints', None), np.int64)
     return d
 
 
@@ -372,6 +407,7 @@ class _HostDraws:
         self.goals = []
         self.aug_coin = None
         self.crop = None
+        self.trl_midpoints = None
 
     def goal(self, n_choices, batch, geom, discount, p_cur):
         g = self._Goal()
@@ -414,17 +450,16 @@ class GCDataset:
         # datasets.py:191-196 (checked before touching the device, like the reference's __post_init__)
         assert np.isclose(config['value_p_curgoal'] + config['value_p_trajgoal'] + config['value_p_randomgoal'], 1.0)
         assert np.isclose(config['actor_p_curgoal'] + config['actor_p_trajgoal'] + config['actor_p_randomgoal'], 1.0)
-        if config.get('agent_name') in TRL_AGENTS:
-            raise NotImplementedError('the TRL branch of GCDataset (datasets.py:198-204,254-276) is not built yet')
+        self._trl = self._KIND == _native.KIND_GC and config.get('agent_name') in TRL_AGENTS
+        if self._trl:
+            # datasets.py:254-257 asserts idxs != value_goal_idxs on every call; with any current/random goal mass that
+            # assert fires at random in the reference, so such configs are refused here instead of failing mid-training
+            if config['value_p_curgoal'] != 0.0 or config['value_p_randomgoal'] != 0.0:
+                raise NotImplementedError('TRL sampling needs value_p_curgoal == value_p_randomgoal == 0 (datasets.py:257)')
         self._sampler = _Sampler(dataset, config, self._KIND, device=device, seed=seed, stream_id=stream_id,
                                  dedup=dedup, output=output)
         self.terminal_locs, self.initial_locs = self._sampler.bounds()
-        self._n_choices = len(dataset.valid_idxs) if hasattr(dataset, 'valid_idxs') else self._num_choices_native()
-
-    def _num_choices_native(self):
-        n = C.c_int64()
-        _native.check(_native.lib().ogb_dataset_num_valid(self._sampler._nds.ptr, C.byref(n)))
-        return n.value if n.value >= 0 else self.size
+        self._n_choices = self._sampler.num_choices()  # len(valid_idxs); every non-terminal row for TRL (:198-204)
 
     # ---- the reference's draw order, host side (rng='numpy') ----
     def _goal_sets(self):
@@ -438,6 +473,9 @@ class GCDataset:
             d.idx_pos = np.random.randint(self._n_choices, size=batch_size)      # datasets.py:226 -> :68/:70
         for geom, discount, p_cur in self._goal_sets():
             d.goal(self._n_choices, batch_size, geom, discount, p_cur)
+        if self._trl:
+            # :259 randint(idxs, value_goal_idxs) needs the goal rows themselves, which only exist on the device
+            raise NotImplementedError("rng='numpy' is not available for TRL samplers; pass recorded draws instead")
         if self.config['p_aug'] is not None and not evaluation:                  # :278-279 / :621-622
             d.aug_coin = np.random.rand()
             if d.aug_coin < self.config['p_aug']:
@@ -460,6 +498,20 @@ class GCDataset:
         """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis.
         `idxs` (optional, num_batches * batch_size rows) plays the role of sample()'s `idxs`."""
         return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches)
+
+    # ---- reference helpers that other scripts call (impls/pretrain_atc.py:195, pretrain_vae.py:162) ----
+    def get_observations(self, idxs):
+        """Return the observations for the given indices, frame-stacked as configured (datasets.py:341-346)."""
+        return self._sampler.gather(0, idxs)
+
+    def get_goal_observations(self, idxs):
+        """Return goal observations: `oracle_reps` if the dataset has them, else observations (datasets.py:348-357)."""
+        return self._sampler.gather(1, idxs)
+
+    def get_stacked_observations(self, idxs):
+        """Return the frame-stacked observations for the given indices (datasets.py:359-366)."""
+        assert self.config['frame_stack'] is not None
+        return self._sampler.gather(0, idxs)
 
     # ---- checkpointable sampler state: one integer ----
     def state_dict(self):
@@ -484,3 +536,53 @@ class HGCDataset(GCDataset):
             sets.append((True, cfg['low_discount'], cfg['value_p_curgoal']))
         sets.append((cfg['actor_geom_sample'], cfg['discount'], cfg['actor_p_curgoal']))
         return sets
+
+
+class ATCDataset:
+    """Dataset class for ATC pretraining, device-resident (reference: datasets.py:369-464).
+
+    Samples anchor/positive observation pairs (o_t, o_{t+k}) from the same trajectory, with frame stacking and the
+    random-shift augmentation fused into the gather.  Config keys: frame_stack, p_aug, augment_padding (default 4).
+    """
+
+    def __init__(self, dataset: Dataset, config: Any, preprocess_frame_stack: bool = True, *, device: int = 0,
+                 seed: int = 0, stream_id: int = 0, rng: str = 'philox', output: str = 'device'):
+        if not isinstance(dataset, Dataset):
+            dataset = Dataset.create(freeze=False, **dataset)
+        assert rng in ('philox', 'numpy')
+        self.dataset = dataset
+        self.config = config
+        self.preprocess_frame_stack = preprocess_frame_stack
+        self.rng = rng
+        self.size = dataset.size
+        self._padding = int(config.get('augment_padding', 4))                      # datasets.py:440
+        self._sampler = _Sampler(dataset, config, _native.KIND_ATC, device=device, seed=seed, stream_id=stream_id,
+                                 output=output, crop_padding=self._padding)
+        self.terminal_locs, self.initial_locs = self._sampler.bounds()
+
+    def get_valid_atc_idxs(self, k):
+        """Return valid anchor indices for a given temporal offset k (datasets.py:417-436; cached per k natively)."""
+        return self._sampler.atc_anchors(k)
+
+    def get_observations(self, idxs):
+        return self._sampler.gather(0, idxs)
+
+    def _host_draws(self, batch_size, k, evaluation) -> _HostDraws:
+        d = _HostDraws()
+        n = C.c_int64()
+        _native.check(_native.lib().ogb_sampler_num_atc_anchors(self._sampler.ptr, int(k), C.byref(n)))
+        d.idx_pos = np.random.randint(0, n.value, size=batch_size)               # np.random.choice(valid_idxs, size=B)  :404
+        if self.config['p_aug'] is not None and not evaluation:                  # :411-412
+            d.aug_coin = np.random.rand()
+            if d.aug_coin < self.config['p_aug']:
+                d.crop = np.random.randint(0, 2 * self._padding + 1, (batch_size, 2))  # :442
+        return d
+
+    def sample(self, batch_size, k, evaluation=False, *, draws=None):
+        """Sample a batch of anchor/positive observations from the same trajectory (datasets.py:401-415)."""
+        if draws is None and self.rng == 'numpy':
+            draws = self._host_draws(batch_size, k, evaluation)
+        return self._sampler.sample_atc(batch_size, k, evaluation, draws)
+
+    def sample_many(self, num_batches, batch_size, k, evaluation=False):
+        return self._sampler.sample_atc(batch_size, k, evaluation, None, n_batches=num_batches)

@@ -163,7 +163,7 @@ class DrawRecorder:
         self._saved = {}
 
     def __enter__(self):
-        for name in ('randint', 'geometric', 'rand'):
+        for name in ('randint', 'geometric', 'rand', 'choice'):
             self._saved[name] = getattr(np.random, name)
 
         def randint(*args, **kwargs):
@@ -181,7 +181,14 @@ class DrawRecorder:
             self.log.append(('rand', np.array(out, copy=True)))
             return out
 
-        np.random.randint, np.random.geometric, np.random.rand = randint, geometric, rand
+        def choice(a, size=None, **kwargs):
+            # legacy RandomState.choice(a, size) without p is a[randint(0, len(a), size)]: log it as that randint
+            assert not kwargs
+            pos = self._saved['randint'](0, len(a), size=size)
+            self.log.append(('randint', np.array(pos, copy=True)))
+            return np.asarray(a)[pos]
+
+        np.random.randint, np.random.geometric, np.random.rand, np.random.choice = randint, geometric, rand, choice
         return self
 
     def __exit__(self, *exc):

@@ -53,6 +53,7 @@ class Draws:
 
     idx_pos: Optional[np.ndarray] = None  # int64[B]; None when the caller passed idxs
     goals: List[GoalDraws] = dataclasses.field(default_factory=list)  # value, [low_value], actor
+    trl_midpoints: Optional[np.ndarray] = None  # int64[B] randint(idxs, value_goal_idxs), TRL agents only (:259)
     aug_coin: Optional[float] = None  # scalar rand(); None when p_aug is None or evaluation
     crop: Optional[np.ndarray] = None  # int64[B,2] in [0, 2*padding]; None unless aug_coin < p_aug
 
@@ -65,6 +66,9 @@ class NumpyGlobalSource:
 
     def randint_box(self, low, high, shape):
         return np.random.randint(low, high, shape)
+
+    def randint_between(self, low, high):
+        return np.random.randint(low, high)
 
     def geometric(self, p, size):
         return np.random.geometric(p=p, size=size)
@@ -100,6 +104,11 @@ class ReplaySource:
         assert tuple(out.shape) == tuple(shape)
         return out
 
+    def randint_between(self, low, high):
+        out = self._pop('randint')
+        assert out.shape == np.shape(low)
+        return out
+
     def geometric(self, p, size):
         return self._pop('geometric')
 
@@ -130,6 +139,8 @@ class DrawsSource:
             q.append(g.offset if g.offset is not None else g.dist)
             if g.u_traj is not None:
                 q.extend([g.u_traj, g.u_cur])
+        if draws.trl_midpoints is not None:
+            q.append(draws.trl_midpoints)
         if draws.aug_coin is not None:
             q.append(draws.aug_coin)
         if draws.crop is not None:
@@ -146,6 +157,9 @@ class DrawsSource:
         return self._pop()
 
     def randint_box(self, low, high, shape):
+        return self._pop()
+
+    def randint_between(self, low, high):
         return self._pop()
 
     def geometric(self, p, size):
@@ -285,8 +299,14 @@ class OracleSampler:
         assert self.terminal_locs[-1] == self.size - 1  # :188
         assert np.isclose(config['value_p_curgoal'] + config['value_p_trajgoal'] + config['value_p_randomgoal'], 1.0)
         assert np.isclose(config['actor_p_curgoal'] + config['actor_p_trajgoal'] + config['actor_p_randomgoal'], 1.0)
-        if config.get('agent_name') in TRL_AGENTS:
-            raise NotImplementedError('TRL branch (datasets.py:198-204,254-276) is a "next" row, SURVEY.md 8(f) f2')
+        self.trl = kind == 'gc' and config.get('agent_name') in TRL_AGENTS
+        if self.trl:
+            # datasets.py:198-204: valid_idxs becomes every non-terminal row.  (With frame_stack AND
+            # preprocess_frame_stack=True the reference rebuilds its Dataset at :211 and loses this override again; it
+            # then trips its own assert at :256 as soon as a final state is drawn, so that mode is not restated.)
+            mask = np.ones(self.size, dtype=bool)
+            mask[self.terminal_locs] = False
+            self.valid_table = np.nonzero(mask)[0]
         if config['frame_stack'] is not None:
             assert 'next_observations' not in fields  # :208
         self.last_draws: Optional[Draws] = None
@@ -380,7 +400,26 @@ class OracleSampler:
         batch['masks'] = 1.0 - success
         batch['rewards'] = success - (1.0 if cfg['gc_negative'] else 0.0)
         self.last_index_vectors = dict(idxs=idxs, final=final, value_goal=value_goal, actor_goal=actor_goal)
-        self._maybe_crop(batch, ['observations', 'next_observations', 'value_goals', 'actor_goals'], evaluation, source)
+        aug_keys = ['observations', 'next_observations', 'value_goals', 'actor_goals']
+        if self.trl:  # datasets.py:254-276
+            assert (idxs != final).all()
+            assert (idxs != value_goal).all()
+            mid = np.asarray(source.randint_between(idxs, value_goal), dtype=np.int64)
+            self.last_draws.trl_midpoints = mid
+            batch['value_goal_observations'] = self._obs(value_goal)
+            batch['actor_goal_observations'] = self._obs(value_goal)   # value_goal_idxs again, as in the reference (:262)
+            batch['value_offsets'] = value_goal - idxs
+            batch['value_midpoint_offsets'] = mid - idxs
+            batch['value_midpoint_observations'] = self._obs(mid)
+            batch['value_midpoint_actions'] = self.fields['actions'][mid]
+            batch['next_actions'] = self.fields['actions'][idxs + 1]
+            batch['value_midpoint_goals'] = self._goal(mid)
+            batch['value_cur_goals'] = self._goal(idxs)
+            batch['value_next_goals'] = self._goal(idxs + 1)
+            self.last_index_vectors['mid'] = mid
+            aug_keys += ['value_goal_observations', 'actor_goal_observations', 'value_midpoint_observations',
+                         'value_midpoint_goals', 'value_cur_goals', 'value_next_goals']
+        self._maybe_crop(batch, aug_keys, evaluation, source)
         return batch
 
     def _sample_hgc(self, idxs, evaluation, source):
@@ -454,4 +493,58 @@ class OracleSampler:
             evaluation,
             source,
         )
+        return batch
+
+
+class OracleATCSampler:
+    """numpy restatement of ATCDataset (datasets.py:369-464): anchor / positive observation pairs (o_t, o_{t+k})."""
+
+    def __init__(self, fields: Dict[str, np.ndarray], config: Any):
+        self.fields = fields
+        self.config = config
+        self.size = dataset_size(fields)
+        self.valid_table = valid_row_table(fields)
+        self.terminal_locs, self.initial_locs = trajectory_bounds(fields['terminals'])
+        assert self.terminal_locs[-1] == self.size - 1  # :391
+        if config['frame_stack'] is not None:
+            assert 'next_observations' not in fields  # :396
+        self._cache = {}
+        self.last_draws: Optional[Draws] = None
+
+    def valid_anchors(self, k):
+        """datasets.py:417-436"""
+        if k not in self._cache:
+            cand = self.valid_table if self.valid_table is not None else np.arange(self.size)
+            cand = cand[cand + k < self.size]
+            cand = cand[cand + k <= final_rows(self.terminal_locs, cand)]
+            if len(cand) == 0:
+                raise ValueError(f'No valid ATC indices found for k={k}.')
+            self._cache[k] = cand
+        return self._cache[k]
+
+    def _obs(self, idxs):
+        fs = self.config['frame_stack']
+        if fs is None:
+            return self.fields['observations'][idxs]
+        return stacked_frames(self.fields['observations'], self.initial_locs, idxs, fs)
+
+    def sample(self, batch_size, k, evaluation=False, source=None):
+        """datasets.py:401-415; np.random.choice(valid, size=B) consumes randint(0, len(valid), B)."""
+        source = NumpyGlobalSource() if source is None else source
+        self.last_draws = Draws()
+        anchors = self.valid_anchors(k)
+        pos = np.asarray(source.randint(len(anchors), batch_size), dtype=np.int64)
+        self.last_draws.idx_pos = pos
+        idxs = anchors[pos]
+        batch = {'observations': self._obs(idxs), 'positive_observations': self._obs(idxs + k)}
+        if self.config['p_aug'] is not None and not evaluation:
+            coin = source.rand_scalar()
+            self.last_draws.aug_coin = coin
+            if coin < self.config['p_aug']:
+                padding = self.config.get('augment_padding', 4)  # :440
+                crop = np.asarray(source.randint_box(0, 2 * padding + 1, (batch_size, 2)), dtype=np.int64)
+                self.last_draws.crop = crop
+                for key in ('observations', 'positive_observations'):
+                    if batch[key].ndim == 4:
+                        batch[key] = shifted_edge_crop(batch[key], crop, padding)
         return batch

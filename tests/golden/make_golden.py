@@ -116,6 +116,26 @@ def cases():
     yield dict(name='gc_pixel64_fs3_aug', kind='gc',
                fields=toy_fields(22, ragged(13, 3, 3, 8), obs_shape=(64, 64, 3), act_dim=5, obs_dtype=np.uint8),
                cfg=cfg(frame_stack=3, p_aug=1.0), B=3, seed=122)
+    trl = dict(agent_name='trl', value_p_curgoal=0.0, value_p_trajgoal=1.0, value_p_randomgoal=0.0, value_geom_sample=True,
+               actor_p_curgoal=0.0, actor_p_trajgoal=0.5, actor_p_randomgoal=0.5, actor_geom_sample=True, discount=0.999)
+    Lt = ragged(14, 9, 4, 60)   # TRL needs trajectories with at least one non-terminal row before the final state
+    yield dict(name='trl_state', kind='gc', fields=toy_fields(24, Lt, **st), cfg=cfg(**trl), B=64, seed=124)
+    yield dict(name='trl_state_oracle_reps', kind='gc', fields=toy_fields(25, Lt, oracle_rep_dim=3, **st),
+               cfg=cfg(**dict(trl, agent_name='latent_trl')), B=48, seed=125)
+    yield dict(name='trl_pixel_fs3_aug', kind='gc', fields=toy_fields(26, ragged(15, 5, 4, 9), **px),
+               cfg=cfg(frame_stack=3, p_aug=1.0, **trl), B=6, seed=126, preprocess=[False])
+    yield dict(name='trl_pixel_fs3_coinfail', kind='gc', fields=toy_fields(27, ragged(15, 5, 4, 9), **px),
+               cfg=cfg(frame_stack=3, p_aug=0.0, **dict(trl, agent_name='discrete_latent_trl')), B=6, seed=127, preprocess=[False])
+    atc = dict(frame_stack=3, p_aug=1.0)
+    yield dict(name='atc_pixel_fs3_aug', kind='atc', fields=toy_fields(28, Lp, **px), cfg=dict(atc), B=8, seed=128, k=2)
+    yield dict(name='atc_pixel_pad2_eval', kind='atc', fields=toy_fields(29, Lp, **px), cfg=dict(atc, augment_padding=2), B=8, seed=129,
+               k=1, evaluation=True)
+    yield dict(name='atc_pixel_pad2_aug', kind='atc', fields=toy_fields(30, Lp, **px), cfg=dict(atc, augment_padding=2, frame_stack=None),
+               B=8, seed=130, k=3)
+    yield dict(name='atc_state_noaug', kind='atc', fields=toy_fields(31, L, **st), cfg=dict(frame_stack=None, p_aug=None), B=32, seed=131, k=7)
+    yield dict(name='atc_pixel64_fs3_aug', kind='atc',
+               fields=toy_fields(32, ragged(16, 3, 4, 8), obs_shape=(64, 64, 3), act_dim=5, obs_dtype=np.uint8),
+               cfg=dict(atc, p_aug=0.999), B=3, seed=132, k=2)
     yield dict(name='gc_pixel_odd_shape_aug', kind='gc',
                fields=toy_fields(23, Lp, obs_shape=(10, 12, 2), act_dim=2, obs_dtype=np.uint8),
                cfg=cfg(frame_stack=3, p_aug=1.0), B=6, seed=123)
@@ -124,10 +144,10 @@ def cases():
 def run_reference(case):
     ref = refshim.load_reference_datasets_module()
     fields = {k: v.copy() for k, v in case['fields'].items()}
-    cls = ref.GCDataset if case['kind'] == 'gc' else ref.HGCDataset
+    cls = {'gc': ref.GCDataset, 'hgc': ref.HGCDataset, 'atc': ref.ATCDataset}[case['kind']]
     outs = []
     logs = []
-    for preprocess in (True, False):
+    for preprocess in case.get('preprocess', (True, False)):
         ds = ref.Dataset.create(**{k: v.copy() for k, v in fields.items()})
         sampler = cls(ds, dict(case['cfg']), preprocess_frame_stack=preprocess)
         idxs = None
@@ -135,14 +155,19 @@ def run_reference(case):
             idxs = ds.valid_idxs[np.random.default_rng(case['seed']).integers(0, len(ds.valid_idxs), case['B'])]
         np.random.seed(case['seed'])
         with refshim.DrawRecorder() as rec:
-            out = sampler.sample(case['B'], idxs=idxs, evaluation=case.get('evaluation', False))
+            if case['kind'] == 'atc':
+                out = sampler.sample(case['B'], case['k'], evaluation=case.get('evaluation', False))
+            else:
+                out = sampler.sample(case['B'], idxs=idxs, evaluation=case.get('evaluation', False))
         outs.append(out)
         logs.append(rec.log)
-    # the pre-stacked and on-the-fly paths of the reference must agree (they do; asserted so it stays true)
-    assert outs[0].keys() == outs[1].keys()
-    for k in outs[0]:
-        assert np.array_equal(outs[0][k], outs[1][k]) and outs[0][k].dtype == outs[1][k].dtype, k
-    return outs[1], logs[1], idxs
+    # the pre-stacked and on-the-fly paths of the reference must agree (they do, except for TRL where the valid_idxs
+    # override is lost by pre-stacking; those cases pin one mode each); asserted so it stays true
+    assert all(o.keys() == outs[0].keys() for o in outs)
+    for o in outs[1:]:
+        for k in outs[0]:
+            assert np.array_equal(outs[0][k], o[k]) and outs[0][k].dtype == o[k].dtype, k
+    return outs[-1], logs[-1], idxs
 
 
 def main():
@@ -153,6 +178,7 @@ def main():
             'meta': np.array(json.dumps(dict(
                 name=case['name'], kind=case['kind'], cfg=case['cfg'], B=case['B'], seed=case['seed'],
                 evaluation=case.get('evaluation', False), n_draws=len(log), draw_kinds=[k for k, _ in log],
+                k=case.get('k'), preprocess=list(case.get('preprocess', (True, False))),
                 numpy=np.__version__,
             ))),
         }

@@ -21,7 +21,7 @@ def load_case(name):
     log = [(kind, z[f'draw/{i}']) for i, kind in enumerate(meta['draw_kinds'])]
     idxs = z['idxs'] if 'idxs' in z.files else None
     return dict(meta=meta, fields=fields, out=out, log=log, idxs=idxs, cfg=meta['cfg'], kind=meta['kind'],
-                B=meta['B'], evaluation=meta['evaluation'])
+                B=meta['B'], evaluation=meta['evaluation'], k=meta.get('k'))
 
 
 def assert_batches_identical(got, want, label=''):

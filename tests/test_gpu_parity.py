@@ -5,7 +5,7 @@ import pytest
 
 from tests.golden.make_golden import cfg, ragged, toy_fields
 from tests.golden_util import assert_batches_identical, case_names, load_case
-from tests.gpu_util import device_sampler, draws_from_log, oracle_with_draws, to_host
+from tests.gpu_util import device_sample, device_sampler, draws_from_log, oracle_with_draws, to_host
 
 pytestmark = pytest.mark.gpu
 CASES = case_names()
@@ -16,17 +16,18 @@ def test_validation_mode_matches_golden(name):
     """The device consumes the reference's recorded draws and must return the reference's batch, every key."""
     case = load_case(name)
     sampler = device_sampler(case['fields'], case['cfg'], case['kind'])
-    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'], draws=draws_from_log(case))
+    got = device_sample(sampler, case, draws=draws_from_log(case))
     assert_batches_identical(to_host(got), case['out'], label=name + ':')
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', [n for n in CASES if not n.startswith('trl_')])
 def test_numpy_rng_mode_matches_golden(name):
-    """rng='numpy': same np.random.seed as the reference run -> same batch, with no recording in between."""
+    """rng='numpy': same np.random.seed as the reference run -> same batch, with no recording in between.
+    (TRL draws a midpoint between idx and the goal row, which only exists on the device: recorded draws only.)"""
     case = load_case(name)
     sampler = device_sampler(case['fields'], case['cfg'], case['kind'], rng='numpy', output='numpy')
     np.random.seed(case['meta']['seed'])
-    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'])
+    got = device_sample(sampler, case)
     assert_batches_identical(got, case['out'], label=name + ':')
 
 
@@ -135,3 +136,48 @@ def test_plain_dataset_sample_and_subset():
     for k, v in case['fields'].items():
         assert np.array_equal(got[k], v[idxs])
     assert np.array_equal(got['next_observations'], case['fields']['observations'][np.minimum(idxs + 1, ds.size - 1)])
+
+
+def test_get_observations_helpers():
+    """get_observations / get_goal_observations / get_stacked_observations (datasets.py:341-366) for explicit rows."""
+    from oracle.replay_oracle import OracleSampler
+
+    for name in ('gc_pixel_fs3_aug', 'gc_state_oracle_reps', 'hgc_state_hiql'):
+        case = load_case(name)
+        sampler = device_sampler(case['fields'], case['cfg'], case['kind'])
+        oracle = OracleSampler(case['fields'], case['cfg'], case['kind'])
+        n = len(case['fields']['terminals'])
+        idxs = np.array([0, 1, 2, n - 1, n // 2, 3, 3])
+        assert np.array_equal(np.asarray(sampler.get_observations(idxs)), oracle._obs(idxs)), name
+        assert np.array_equal(np.asarray(sampler.get_goal_observations(idxs)), oracle._goal(idxs)), name
+        if case['cfg']['frame_stack'] is not None:
+            assert np.array_equal(np.asarray(sampler.get_stacked_observations(idxs)), oracle._obs(idxs)), name
+
+
+def test_atc_anchor_sets_match_oracle():
+    from oracle.replay_oracle import OracleATCSampler
+
+    case = load_case('atc_state_noaug')
+    sampler = device_sampler(case['fields'], case['cfg'], 'atc')
+    oracle = OracleATCSampler(case['fields'], case['cfg'])
+    for k in (0, 1, 7, 30):
+        assert np.array_equal(sampler.get_valid_atc_idxs(k), oracle.valid_anchors(k)), k
+    with pytest.raises(ValueError):
+        sampler.get_valid_atc_idxs(10_000)
+
+
+def test_trl_philox_mode_properties():
+    """TRL in the on-device RNG mode: midpoints lie in [idx, goal), offsets are consistent, rows are never terminal."""
+    case = load_case('trl_state')
+    fields = {k: v.copy() for k, v in case['fields'].items()}
+    fields['observations'][:, 0] = np.arange(len(fields['terminals']))
+    sampler = device_sampler(fields, case['cfg'], 'gc', seed=4)
+    out = to_host(sampler.sample(4096))
+    i = out['observations'][:, 0].astype(np.int64)
+    g = out['value_goal_observations'][:, 0].astype(np.int64)
+    m = out['value_midpoint_observations'][:, 0].astype(np.int64)
+    assert (fields['terminals'][i] == 0).all() and (g > i).all() and (m >= i).all() and (m < g).all()
+    assert np.array_equal(out['value_offsets'], g - i) and np.array_equal(out['value_midpoint_offsets'], m - i)
+    assert np.array_equal(out['next_actions'], fields['actions'][i + 1])
+    assert np.array_equal(out['value_midpoint_actions'], fields['actions'][m])
+    assert np.array_equal(out['value_next_goals'][:, 0].astype(np.int64), i + 1)

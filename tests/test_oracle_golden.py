@@ -4,10 +4,17 @@ import numpy as np
 import pytest
 
 from oracle import refshim
-from oracle.replay_oracle import OracleSampler, ReplaySource
+from oracle.replay_oracle import OracleATCSampler, OracleSampler, ReplaySource
 from tests.golden_util import assert_batches_identical, case_names, load_case
 
 CASES = case_names()
+
+
+def oracle_sample(case, source):
+    if case['kind'] == 'atc':
+        return OracleATCSampler(case['fields'], case['cfg']).sample(case['B'], case['k'], evaluation=case['evaluation'], source=source)
+    sampler = OracleSampler(case['fields'], case['cfg'], case['kind'])
+    return sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'], source=source)
 
 
 def test_fixtures_present():
@@ -17,9 +24,8 @@ def test_fixtures_present():
 @pytest.mark.parametrize('name', CASES)
 def test_oracle_matches_golden(name):
     case = load_case(name)
-    sampler = OracleSampler(case['fields'], case['cfg'], case['kind'])
     src = ReplaySource(case['log'])
-    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'], source=src)
+    got = oracle_sample(case, src)
     assert src.exhausted(), 'oracle consumed fewer draws than the reference'
     assert_batches_identical(got, case['out'], label=name + ':')
 
@@ -28,9 +34,8 @@ def test_oracle_matches_golden(name):
 def test_oracle_global_stream_matches_golden(name):
     """Same check through the global np.random stream: seed -> identical batch, no recording involved."""
     case = load_case(name)
-    sampler = OracleSampler(case['fields'], case['cfg'], case['kind'])
     np.random.seed(case['meta']['seed'])
-    got = sampler.sample(case['B'], idxs=case['idxs'], evaluation=case['evaluation'])
+    got = oracle_sample(case, None)
     assert_batches_identical(got, case['out'], label=name + ':')
 
 
