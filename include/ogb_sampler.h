@@ -46,11 +46,11 @@ typedef enum {
 /* One dataset field as handed to Dataset.create(**fields) (datasets.py:45-57): C-contiguous, rows on axis 0. */
 typedef struct {
   const char* name;
-  const void* data;              /* host pointer, or a device pointer on the target device when on_device != 0 */
+  const void* data;              /* host pointer (on_device 0), device pointer on the target device (1), or NULL (2) */
   int32_t dtype;                 /* ogb_dtype */
   int32_t ndim;                  /* including the leading row axis */
   int64_t shape[OGB_MAX_NDIM];
-  int32_t on_device;
+  int32_t on_device;             /* 2: allocate a zero-filled buffer (ReplayBuffer.create, datasets.py:101-103) */
 } ogb_field;
 
 /* The sampler hyper-parameters GCDataset/HGCDataset read from `config` (datasets.py:157-169,473-475,515-517,543,
@@ -120,6 +120,7 @@ int ogb_device_count(int* out);
 int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out);
 int ogb_dataset_size(const ogb_dataset* ds, int64_t* out);
 int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out);   /* -1 when the dataset has no 'valids' */
+int ogb_dataset_set_active_rows(ogb_dataset* ds, int64_t n);      /* ReplayBuffer.size (datasets.py:131,142): rows to draw from */
 int ogb_dataset_resident_bytes(const ogb_dataset* ds, size_t* out);
 int ogb_dataset_destroy(ogb_dataset* ds);
 
@@ -131,6 +132,9 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream);    /* launch on t
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep_index_vectors);
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out);   /* len(dataset.valid_idxs) as this sampler sees it (TRL overrides it) */
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out);
+/* ReplayBuffer.add_transition (datasets.py:134-142): write one row of every field (host pointers in field order,
+ * NULL = leave untouched), stream-ordered between the sampler's sample() calls. */
+int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_rows, int32_t n_fields);
 int ogb_sampler_copy_bounds(const ogb_sampler* s, int64_t* terminal_locs, int64_t* initial_locs); /* host out */
 int ogb_sampler_get_counter(const ogb_sampler* s, uint64_t* out); /* checkpointable RNG position */
 int ogb_sampler_set_counter(ogb_sampler* s, uint64_t counter);

@@ -4,7 +4,7 @@ Drop-in for `impls/utils/datasets.py` of hliuson/ogbench: same classes and call 
 HBM, hand-written sm_100a CUDA kernels behind a C-ABI (include/ogb_sampler.h).  No CPU fallback.
 """
 
-from .datasets import ATCDataset, Dataset, GCDataset, HGCDataset, get_size  # noqa: F401
+from .datasets import ATCDataset, Dataset, GCDataset, HGCDataset, ReplayBuffer, get_size  # noqa: F401
 from .device_array import DeviceArray  # noqa: F401
 
-__all__ = ['Dataset', 'GCDataset', 'HGCDataset', 'ATCDataset', 'DeviceArray', 'get_size']
+__all__ = ['Dataset', 'GCDataset', 'HGCDataset', 'ATCDataset', 'ReplayBuffer', 'DeviceArray', 'get_size']

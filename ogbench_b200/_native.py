@@ -77,6 +77,7 @@ SIGNATURES = [
     ('ogb_dataset_create', C.c_int, [C.POINTER(Field), C.c_int32, C.c_int32, C.POINTER(_P)]),
     ('ogb_dataset_size', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_dataset_num_valid', C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ('ogb_dataset_set_active_rows', C.c_int, [_P, C.c_int64]),
     ('ogb_dataset_resident_bytes', C.c_int, [_P, C.POINTER(C.c_size_t)]),
     ('ogb_dataset_destroy', C.c_int, [_P]),
     ('ogb_sampler_create', C.c_int, [_P, C.POINTER(Config), C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
@@ -84,6 +85,7 @@ SIGNATURES = [
     ('ogb_sampler_set_debug', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_num_choices', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_num_terminals', C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ('ogb_sampler_write_row', C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.c_int32]),
     ('ogb_sampler_copy_bounds', C.c_int, [_P, _P, _P]),
     ('ogb_sampler_get_counter', C.c_int, [_P, C.POINTER(C.c_uint64)]),
     ('ogb_sampler_set_counter', C.c_int, [_P, C.c_uint64]),

@@ -193,7 +193,8 @@ struct DLManagedTensor_ {
 struct ogb_dataset {
   std::atomic<int> refs{1};
   int device = 0;
-  int64_t size = 0;
+  int64_t size = 0;         // rows allocated
+  int64_t active_rows = 0;  // rows that hold data (== size except for a ReplayBuffer that is still filling up)
   std::vector<Field> fields;
   int obs_field = -1, terminals_field = -1, valids_field = -1, next_obs_field = -1, oracle_field = -1;
   // valid rows
@@ -653,7 +654,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   int64_t size = 0;
   for (int i = 0; i < n_fields; ++i) {
     const ogb_field& in = fields[i];
-    if (!in.name || !in.data || in.ndim < 1 || in.ndim > OGB_MAX_NDIM || dtype_size(in.dtype) == 0)
+    if (!in.name || (!in.data && in.on_device != 2) || in.ndim < 1 || in.ndim > OGB_MAX_NDIM || dtype_size(in.dtype) == 0)
       return bail(fail(OGB_ERR_INVALID, "field %d: bad descriptor", i));
     size = std::max<int64_t>(size, in.shape[0]);  // get_size: the longest leaf (datasets.py:11-14)
   }
@@ -663,6 +664,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
                        (long long)fields[i].shape[0], (long long)size));
   if (size < 1 || size > (int64_t)2147483000) return bail(fail(OGB_ERR_UNSUPPORTED, "dataset size %lld out of range", (long long)size));
   ds->size = size;
+  ds->active_rows = size;
 
   for (int i = 0; i < n_fields; ++i) {
     const ogb_field& in = fields[i];
@@ -688,7 +690,10 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
     ds->fields.push_back(f);
     ds->resident_bytes += padded_bytes;
     const cudaMemcpyKind kind = in.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (f.stride == row) {
+    if (in.on_device == 2) {  // zero-filled buffer (ReplayBuffer.create, datasets.py:101-103)
+      e = cudaMemset(f.dptr, 0, padded_bytes);
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "memset of field '%s': %s", in.name, cudaGetErrorString(e)));
+    } else if (f.stride == row) {
       e = cudaMemcpy(f.dptr, in.data, dense_bytes, kind);
       if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "upload of field '%s': %s", in.name, cudaGetErrorString(e)));
     } else {
@@ -762,6 +767,12 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
 int ogb_dataset_size(const ogb_dataset* ds, int64_t* out) {
   if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = ds->size;
+  return 0;
+}
+int ogb_dataset_set_active_rows(ogb_dataset* ds, int64_t n) {
+  if (!ds) return fail(OGB_ERR_INVALID, "null dataset");
+  if (n < 0 || n > ds->size) return fail(OGB_ERR_INVALID, "active rows must be in [0, %lld]", (long long)ds->size);
+  ds->active_rows = n;
   return 0;
 }
 int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out) {
@@ -872,7 +883,30 @@ int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   if (s->trl_rows.dev) *out = (int64_t)s->trl_rows.host.size();
-  else *out = s->ds->valid_mode == 0 ? s->ds->size : s->ds->n_valid;
+  else *out = s->ds->valid_mode == 0 ? s->ds->active_rows : s->ds->n_valid;
+  return 0;
+}
+
+// ReplayBuffer.add_transition (datasets.py:134-142): overwrite row `row` of every field, ordered on the sampler's
+// stream after the sample() calls already issued and before the ones that follow.
+int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_rows, int32_t n_fields) {
+  if (!s || !field_rows) return fail(OGB_ERR_INVALID, "null argument");
+  ogb_dataset* ds = s->ds;
+  if (row < 0 || row >= ds->size) return fail(OGB_ERR_INDEX, "row %lld out of range", (long long)row);
+  if (n_fields != (int32_t)ds->fields.size()) return fail(OGB_ERR_INVALID, "expected %zu field pointers", ds->fields.size());
+  OGB_CUDA(cudaSetDevice(ds->device));
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (s->aux_stream) {  // index kernels of big launches read tiny fields on the auxiliary stream
+    cudaEvent_t ev = s->chunk_events[s->next_event];
+    s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
+    OGB_CUDA(cudaEventRecord(ev, s->aux_stream));
+    OGB_CUDA(cudaStreamWaitEvent(s->stream, ev, 0));
+  }
+  for (size_t i = 0; i < ds->fields.size(); ++i) {
+    if (!field_rows[i]) continue;
+    const Field& f = ds->fields[i];
+    OGB_CUDA(cudaMemcpyAsync(f.dptr + (size_t)row * f.stride, field_rows[i], f.row_bytes, cudaMemcpyHostToDevice, s->stream));
+  }
   return 0;
 }
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out) {
@@ -935,7 +969,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + spec.next_offset >= ds->size))
         return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
   }
-  const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->size : ds->n_valid);
+  const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->active_rows : ds->n_valid);
+  if (n_choices < 1) return fail(OGB_ERR_INVALID, "nothing to sample from: the dataset holds no rows yet");
   const bool aug_mode = cfg.has_p_aug && !evaluation && spec.kind != OGB_KIND_PLAIN;
   const int n_goal_sets = (spec.kind == OGB_KIND_GC || spec.kind == OGB_KIND_HGC) ? 3 : 0;
   const bool geom[3] = {cfg.value_geom_sample != 0, true, cfg.actor_geom_sample != 0};

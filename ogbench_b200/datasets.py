@@ -36,10 +36,23 @@ def _is_device_array(x) -> bool:
     return not isinstance(x, np.ndarray) and (hasattr(x, '__cuda_array_interface__') or hasattr(x, 'data_ptr'))
 
 
+class _ZeroField:
+    """Placeholder for a field that is allocated zero-filled on the device (ReplayBuffer.create)."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+
 def _describe_field(name: str, arr, keepalive: list) -> _native.Field:
     f = _native.Field()
     f.name = name.encode()
-    if _is_device_array(arr):
+    if isinstance(arr, _ZeroField):
+        np_dtype, shape, ptr = arr.dtype, arr.shape, None
+        f.on_device = 2
+    elif _is_device_array(arr):
         if hasattr(arr, 'data_ptr'):  # torch tensor
             if not arr.is_cuda or not arr.is_contiguous():
                 raise ValueError(f'field {name!r}: device tensors must be contiguous CUDA tensors')
@@ -157,17 +170,106 @@ class Dataset(Mapping):
 
     def _plain_sampler(self, device=0) -> '_Sampler':
         if device not in self._plain:
-            self._plain[device] = _Sampler(self, None, _native.KIND_PLAIN, device=device)
+            self._plain[device] = _Sampler(self, None, _native.KIND_PLAIN, device=device, output=self.output)
         return self._plain[device]
+
+    rng = 'philox'     # 'numpy': draw the indices on the host from np.random, exactly like the reference
+    output = 'device'  # 'numpy': return host arrays like the reference
 
     def sample(self, batch_size, idxs=None):
         """Sample a batch of transitions (datasets.py:72-76)."""
+        if idxs is None and self.rng == 'numpy':
+            idxs = self.get_random_idxs(batch_size)
         return self._plain_sampler().sample(batch_size, idxs)
 
     def get_subset(self, idxs):
         """Return the rows `idxs` of every field plus next_observations (datasets.py:78-83)."""
         idxs = np.asarray(idxs, dtype=np.int64)
         return self._plain_sampler().sample(len(idxs), idxs)
+
+
+class ReplayBuffer(Dataset):
+    """Replay buffer class, device-resident (reference: datasets.py:86-146).
+
+    The buffers live in HBM; `add_transition` writes one row per field, stream-ordered with `sample`.  Indexing the
+    buffer (`rb['observations']`) is not supported: there is no host mirror.
+    """
+
+    @classmethod
+    def create(cls, transition, size, **kwargs):
+        """Create a replay buffer from the example transition (datasets.py:92-106)."""
+        fields = {k: _ZeroField((size, *np.array(v).shape), np.array(v).dtype) for k, v in transition.items()}
+        return cls(fields, **kwargs)
+
+    @classmethod
+    def create_from_initial_dataset(cls, init_dataset, size, **kwargs):
+        """Create a replay buffer from the initial dataset (datasets.py:108-125)."""
+        init = dict(init_dataset)
+        n = get_size(init)
+        fields = {k: _ZeroField((size, *np.asarray(v).shape[1:]), np.asarray(v).dtype) for k, v in init.items()}
+        rb = cls(fields, **kwargs)
+        rb._fill(init, n)
+        rb.size = rb.pointer = n
+        rb._sync_size()
+        return rb
+
+    def __init__(self, fields, rng='philox', output='device', device=0):
+        self._dict = dict(fields)
+        self.rng, self.output, self._device = rng, output, device
+        self.max_size = get_size(self._dict)
+        self.size = 0
+        self.pointer = 0
+        self._native = {}
+        self._plain = {}
+        self._names = list(self._dict)
+
+    def __getitem__(self, key):
+        raise NotImplementedError('the device ReplayBuffer keeps no host mirror of its buffers')
+
+    def native(self, device: int = 0) -> _NativeDataset:
+        fresh = device not in self._native
+        nds = super().native(device)
+        if fresh:  # a new buffer holds no rows yet (datasets.py:131)
+            _native.check(_native.lib().ogb_dataset_set_active_rows(nds.ptr, int(self.size)))
+        return nds
+
+    def _sync_size(self):
+        _native.check(_native.lib().ogb_dataset_set_active_rows(self.native(self._device).ptr, int(self.size)))
+
+    def _write(self, row, transition):
+        sampler = self._plain_sampler(self._device)
+        ptrs = (C.c_void_p * len(self._names))()
+        keep = []
+        for i, name in enumerate(self._names):
+            zf = self._dict[name]
+            arr = np.ascontiguousarray(np.asarray(transition[name]), dtype=zf.dtype).reshape(zf.shape[1:])
+            keep.append(arr)
+            ptrs[i] = arr.ctypes.data
+        _native.check(_native.lib().ogb_sampler_write_row(sampler.ptr, int(row), ptrs, len(self._names)))
+
+    def _fill(self, init, n):
+        for r in range(n):
+            self._write(r, {k: np.asarray(v)[r] for k, v in init.items()})
+
+    def add_transition(self, transition):
+        """Add a transition to the replay buffer (datasets.py:134-142)."""
+        self._write(self.pointer, transition)
+        self.pointer = (self.pointer + 1) % self.max_size
+        self.size = max(self.pointer, self.size)
+        self._sync_size()
+
+    def clear(self):
+        """Clear the replay buffer (datasets.py:144-146)."""
+        self.size = self.pointer = 0
+        self._sync_size()
+
+    def get_random_idxs(self, num_idxs):
+        return np.random.randint(self.size, size=num_idxs)  # no 'valids' in a replay buffer: datasets.py:70
+
+    def sample(self, batch_size, idxs=None):
+        if idxs is None and self.rng == 'numpy':
+            idxs = self.get_random_idxs(batch_size)
+        return self._plain_sampler(self._device).sample(batch_size, idxs)
 
 
 class _PinnedPool:

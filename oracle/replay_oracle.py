@@ -548,3 +548,39 @@ class OracleATCSampler:
                     if batch[key].ndim == 4:
                         batch[key] = shifted_edge_crop(batch[key], crop, padding)
         return batch
+
+
+class OracleReplayBuffer:
+    """numpy restatement of ReplayBuffer (datasets.py:86-146): a ring of rows plus Dataset.sample (:65-83)."""
+
+    def __init__(self, transition, size):
+        self.buffers = {k: np.zeros((size, *np.array(v).shape), dtype=np.array(v).dtype) for k, v in transition.items()}
+        self.max_size = size
+        self.size = 0
+        self.pointer = 0
+
+    @classmethod
+    def from_initial_dataset(cls, init, size):
+        rb = cls({k: np.asarray(v)[0] for k, v in init.items()}, size)
+        n = dataset_size(init)
+        for k, v in init.items():
+            rb.buffers[k][:n] = v
+        rb.size = rb.pointer = n  # :124
+        return rb
+
+    def add_transition(self, transition):
+        for k, v in transition.items():
+            self.buffers[k][self.pointer] = v
+        self.pointer = (self.pointer + 1) % self.max_size  # :141
+        self.size = max(self.pointer, self.size)  # :142
+
+    def clear(self):
+        self.size = self.pointer = 0
+
+    def sample(self, batch_size, idxs=None):
+        if idxs is None:
+            idxs = np.random.randint(self.size, size=batch_size)  # :70 (a replay buffer has no 'valids')
+        batch = {k: v[idxs] for k, v in self.buffers.items()}
+        if 'next_observations' not in batch:
+            batch['next_observations'] = self.buffers['observations'][np.minimum(idxs + 1, self.size - 1)]  # :82
+        return batch
