@@ -1,0 +1,141 @@
+"""The step before the hot path: OGBench `.npz` files -> HBM-resident datasets, with shard cycling.
+
+`load_dataset` has the signature and the result of `ogbench.load_dataset` (ogbench/utils.py:14-96): a dict of host
+arrays in the regular or the compact layout.  It is I/O (np.load, decompression) plus an O(N) pass over the
+1-D `terminals` array, so it stays on the host like the reference's; what changes is what happens next --
+`load_gc_dataset` uploads the fields once and returns a device sampler, and `ShardCycler` reproduces the
+directory-of-shards mode of impls/main.py:81-93,185-199 with the *next* shard loaded and uploaded by a background
+thread while the current one is being sampled, so the swap every `dataset_replace_interval` steps costs nothing.
+"""
+
+from __future__ import annotations
+
+import glob
+import os
+import threading
+from typing import Any, Callable, List, Optional
+
+import numpy as np
+
+from .datasets import Dataset, GCDataset
+
+
+def load_dataset(dataset_path, ob_dtype=np.float32, action_dtype=np.float32, compact_dataset=False, add_info=False):
+    """Load an OGBench dataset file (same contract as ogbench/utils.py:14-96).
+
+    Returns a dict with 'observations', 'actions', 'terminals' and 'next_observations' (regular layout) or 'valids'
+    (compact layout); with add_info also 'qpos', 'qvel', 'button_states' when the file has them.
+    """
+    file = np.load(dataset_path)
+    dataset = {}
+    for k, dtype in (('observations', ob_dtype), ('actions', action_dtype), ('terminals', np.float32)):
+        dataset[k] = file[k][...].astype(dtype, copy=False)
+    info_keys = []
+    if add_info:
+        for k in ('qpos', 'qvel', 'button_states'):
+            if k in file:
+                dataset[k] = file[k][...]
+                info_keys.append(k)
+
+    terminals = dataset['terminals']
+    follows_terminal = np.concatenate([terminals[1:], [1.0]])       # terminals shifted left, the file ends a trajectory
+    if compact_dataset:
+        # keep every row; the last row of a trajectory is only ever a next-observation, so it is marked invalid and
+        # its predecessor becomes terminal as well (ogbench/utils.py:60-73)
+        dataset['valids'] = 1.0 - terminals
+        dataset['terminals'] = np.minimum(terminals + follows_terminal, 1.0).astype(np.float32)
+    else:
+        # regular layout: drop each trajectory's last row, next_observations are the rows shifted by one
+        # (ogbench/utils.py:74-94)
+        ob_mask = (1.0 - terminals).astype(bool)
+        next_ob_mask = np.concatenate([[False], ob_mask[:-1]])
+        dataset['next_observations'] = dataset['observations'][next_ob_mask]
+        dataset['observations'] = dataset['observations'][ob_mask]
+        dataset['actions'] = dataset['actions'][ob_mask]
+        dataset['terminals'] = follows_terminal[ob_mask].astype(np.float32)
+        for k in info_keys:
+            dataset[k] = dataset[k][ob_mask]
+    return dataset
+
+
+def load_gc_dataset(dataset_path, config, dataset_class=GCDataset, ob_dtype=np.float32, action_dtype=np.float32,
+                    device: int = 0, **sampler_kwargs):
+    """`.npz` -> compact layout (what impls/utils/env_utils.py:89-95 asks for) -> HBM -> device sampler."""
+    fields = load_dataset(dataset_path, ob_dtype=ob_dtype, action_dtype=action_dtype, compact_dataset=True)
+    dataset = Dataset.create(**fields)
+    return dataset_class(dataset, config, device=device, **sampler_kwargs)
+
+
+def list_shards(dataset_dir: str) -> List[str]:
+    """Training shards of a dataset directory (impls/main.py:84-88): sorted *.npz without the validation files."""
+    shards = [f for f in sorted(glob.glob(f'{dataset_dir}/*.npz')) if '-val.npz' not in f]
+    if not shards:
+        raise FileNotFoundError(f'No .npz files found in {dataset_dir}')
+    return shards
+
+
+class ShardCycler:
+    """Cycle through dataset shards like impls/main.py:185-199, without the reload stall.
+
+        cycler = ShardCycler(list_shards(path), make_sampler=lambda p: load_gc_dataset(p, config), replace_interval=1000)
+        for i in range(1, train_steps + 1):
+            train_dataset = cycler.at_step(i)          # swaps to the next shard when i % replace_interval == 0
+            batch = train_dataset.sample(batch_size)
+
+    Random goals stay shard-local, exactly as in the reference (only the loaded shard is sampled).
+    """
+
+    def __init__(self, shard_paths: List[str], make_sampler: Callable[[str], Any], replace_interval: int, prefetch: bool = True):
+        assert len(shard_paths) >= 1
+        self.paths = list(shard_paths)
+        self.make_sampler = make_sampler
+        self.replace_interval = int(replace_interval)
+        self.prefetch = prefetch
+        self.index = 0
+        self.current = make_sampler(self.paths[0])
+        self.swaps = 0
+        self.prefetched_swaps = 0
+        self._next: Optional[Any] = None
+        self._next_index: Optional[int] = None
+        self._thread: Optional[threading.Thread] = None
+        self._error: Optional[BaseException] = None
+        self._start_prefetch()
+
+    def _start_prefetch(self):
+        if not self.prefetch or len(self.paths) < 2 or self.replace_interval <= 0:
+            return
+        nxt = (self.index + 1) % len(self.paths)
+
+        def work():
+            try:
+                self._next = self.make_sampler(self.paths[nxt])   # np.load + upload; ctypes releases the GIL
+            except BaseException as exc:  # surfaced at the swap
+                self._error = exc
+
+        self._next, self._next_index, self._error = None, nxt, None
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def at_step(self, step: int):
+        """Sampler to use at training step `step` (1-based, like the loop in impls/main.py:183)."""
+        if self.replace_interval > 0 and len(self.paths) > 1 and step % self.replace_interval == 0:
+            self.index = (self.index + 1) % len(self.paths)
+            if self._thread is not None:
+                ready_early = not self._thread.is_alive()
+                self._thread.join()
+                self._thread = None
+                if self._error is not None:
+                    raise self._error
+                assert self._next_index == self.index
+                self.current, self._next = self._next, None
+                self.prefetched_swaps += int(ready_early)
+            else:
+                self.current = self.make_sampler(self.paths[self.index])
+            self.swaps += 1
+            self._start_prefetch()
+        return self.current
+
+    def close(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None

@@ -1,0 +1,78 @@
+"""Loader (ogbench/utils.py:14-96) against golden vectors from the reference; shard cycling (impls/main.py:185-199)."""
+
+import os
+
+import numpy as np
+import pytest
+
+from ogbench_b200 import loader
+from tests.golden.make_golden_loader import CASES
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('name,raw_kw,load_kw', CASES, ids=[c[0] for c in CASES])
+def test_load_dataset_matches_reference(name, raw_kw, load_kw):
+    want = np.load(os.path.join(HERE, name + '.npz'))
+    raw = os.path.join(HERE, name + '_raw.npz')
+    for compact in (False, True):
+        for add_info in (False, True):
+            got = loader.load_dataset(raw, compact_dataset=compact, add_info=add_info, **load_kw)
+            prefix = f'c{int(compact)}i{int(add_info)}/'
+            keys = {k[len(prefix):] for k in want.files if k.startswith(prefix)}
+            assert set(got) == keys
+            for k in keys:
+                w = want[prefix + k]
+                assert got[k].dtype == w.dtype and got[k].shape == w.shape and np.array_equal(got[k], w), (compact, add_info, k)
+
+
+def test_list_shards(tmp_path):
+    for n in ('b.npz', 'a.npz', 'a-val.npz', 'c.txt'):
+        (tmp_path / n).write_bytes(b'')
+    assert [os.path.basename(p) for p in loader.list_shards(str(tmp_path))] == ['a.npz', 'b.npz']
+    with pytest.raises(FileNotFoundError):
+        loader.list_shards(str(tmp_path / 'missing'))
+
+
+def test_shard_cycler_schedule_without_device():
+    """Swap schedule of impls/main.py:185-199: at every step i with i % interval == 0 the next shard becomes current."""
+    loads = []
+
+    def make(path):
+        loads.append(path)
+        return path
+
+    cyc = loader.ShardCycler(['s0', 's1', 's2'], make, replace_interval=4)
+    seen = [cyc.at_step(i) for i in range(1, 14)]
+    cyc.close()
+    assert seen == ['s0'] * 3 + ['s1'] * 4 + ['s2'] * 4 + ['s0'] * 2
+    assert cyc.swaps == 3 and loads[:4] == ['s0', 's1', 's2', 's0']
+    single = loader.ShardCycler(['only'], make, replace_interval=2)
+    assert [single.at_step(i) for i in range(1, 6)] == ['only'] * 5
+
+
+@pytest.mark.gpu
+def test_shard_cycler_on_device(tmp_path):
+    from tests.golden.make_golden import cfg
+
+    paths = []
+    for s in range(3):
+        rng = np.random.default_rng(s)
+        n_ep, T = 6, 30
+        obs = rng.standard_normal((n_ep * T, 4)).astype(np.float32)
+        obs[:, 0] = 1000 * s + np.arange(n_ep * T)                     # shard id readable from the batch
+        term = np.zeros(n_ep * T, dtype=bool)
+        term[T - 1::T] = True
+        p = str(tmp_path / f'shard{s}.npz')
+        np.savez(p, observations=obs, actions=rng.uniform(-1, 1, (n_ep * T, 2)).astype(np.float32), terminals=term)
+        paths.append(p)
+    config = cfg()
+    cyc = loader.ShardCycler(loader.list_shards(str(tmp_path)), lambda p: loader.load_gc_dataset(p, config, seed=1), replace_interval=5)
+    for i in range(1, 16):
+        batch = cyc.at_step(i).sample(64)
+        shard = (i // 5) % 3
+        for key in ('observations', 'next_observations', 'value_goals', 'actor_goals'):   # goals are shard-local
+            ids = np.asarray(batch[key])[:, 0]
+            assert ((ids >= 1000 * shard) & (ids < 1000 * shard + 180)).all(), (i, key)
+    cyc.close()
+    assert cyc.swaps == 3
