@@ -186,6 +186,13 @@ int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* 
 int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t purpose, int64_t n, int32_t device,
                     uint32_t* out_host);                           /* [n,4] raw Philox4x32-10 words, for RNG tests */
 
+int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out);
+                                                                   /* debug (env OGB_TIMELINE=1): device times, in ms since the
+                                                                      first, of index begin/end and gather begin/end per call */
+int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t device, int64_t* mismatches);
+                                                                   /* 2n geometric draws: float32 fast path vs the float64
+                                                                      expression ceil(log(1-U)/log(discount)); counts differences */
+
 #ifdef __cplusplus
 }
 #endif

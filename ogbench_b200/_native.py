@@ -113,6 +113,8 @@ SIGNATURES = [
     ('ogb_host_free', C.c_int, [_P]),
     ('ogb_searchsorted_warp', C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     ('ogb_philox_fill', C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64, C.c_int32, _P]),
+    ('ogb_debug_timeline', C.c_int, [_P, C.c_int32, _P]),
+    ('ogb_geometric_check', C.c_int, [C.c_double, C.c_uint64, C.c_int64, C.c_int32, _P]),
 ]
 
 

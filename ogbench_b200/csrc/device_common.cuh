@@ -13,12 +13,14 @@ namespace ogb {
 // oracle/philox_np.py restates exactly this for the tests.
 // ---------------------------------------------------------------------------------------------------------
 enum Purpose : uint32_t {
-  PURPOSE_IDX = 0,      // .x,.y -> transition index position; .z -> crop shift (cy, cx jointly)
-  PURPOSE_GOAL = 1,     // + goal_set (0 value, 1 low-value, 2 actor): .x,.y -> random-goal position; .z,.w -> geometric / distance U
-  PURPOSE_MIX = 4,      // 32-bit uniforms of the goal mix: .x value u_traj, .y value u_cur, .z actor u_traj, .w actor u_cur
-  PURPOSE_MIX_LOW = 5,  // .x low-value u_traj, .y low-value u_cur
-  PURPOSE_TRL_MID = 6,  // .x,.y -> TRL midpoint position in [idx, value goal)
-  PURPOSE_COIN = 7      // row = 0xFFFFFFFF: .x,.y -> the per-batch augmentation coin
+  PURPOSE_IDX = 0,       // .x,.y -> transition index position; .z,.w -> value-goal mix coins (u_traj, u_cur)
+  PURPOSE_GOAL = 1,      // .x,.y -> the value goal's 64 bits; .z,.w -> the actor goal's 64 bits (a goal spends its bits
+                         //          either on the random-goal position or on the geometric / distance uniform)
+  PURPOSE_GOAL_LOW = 2,  // .x,.y -> the low-value goal's 64 bits; .z,.w -> its mix coins (HGC + low_discount)
+  PURPOSE_CROP = 3,      // .x -> crop shift (cy, cx jointly); only drawn for augmented batches
+  PURPOSE_MIX = 4,       // .x,.y -> actor-goal mix coins (u_traj, u_cur); only drawn when that mix is a real choice
+  PURPOSE_TRL_MID = 6,   // .x,.y -> TRL midpoint position in [idx, value goal)
+  PURPOSE_COIN = 7       // row = 0xFFFFFFFF: .x,.y -> the per-batch augmentation coin
 };
 
 // The ten round keys (key + i * Weyl constant) are the same for every thread: the host computes them once and the
@@ -59,12 +61,11 @@ __device__ __forceinline__ uint4 draw4(const RngKey& key, uint64_t batch, uint32
   return philox4x32_10(ctr, key);
 }
 
-// 32-bit uniform in [0, 1) as a double (exact), for the goal-mix coins
-__device__ __forceinline__ double unit_from_word(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
-
-// uniform integer in [0, n): 64-bit multiply-shift, bias < n / 2^64
-__device__ __forceinline__ int64_t bounded_u64(uint32_t hi, uint32_t lo, uint64_t n) {
-  return (int64_t)__umul64hi(((uint64_t)hi << 32) | lo, n);
+// uniform integer in [0, n), n < 2^32, from 64 random bits: floor(((hi << 32) | lo) * n / 2^64), bias < n / 2^64
+__device__ __forceinline__ uint32_t bounded_u32n(uint32_t hi, uint32_t lo, uint32_t n) {
+  const uint64_t t = (uint64_t)lo * n;
+  const uint64_t u = (uint64_t)hi * n + (t >> 32);
+  return (uint32_t)(u >> 32);
 }
 
 // uniform double in [0, 1) with 53 random bits, the same construction numpy's legacy rand() uses on two words
@@ -72,17 +73,24 @@ __device__ __forceinline__ double unit_double(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-// geometric(p) by inversion, support [1, inf): ceil(log(1-U) / log(1-p)); log_1mp = log(1-p) comes from the host.
-// The float32 estimate decides unless the quotient lies close enough to an integer that float error could change
-// the ceiling; only then (a few rows in a thousand) is the float64 expression evaluated.  Both branches return
-// the value of the float64 expression.
-__device__ __forceinline__ int64_t geometric_from_unit(double u, double log_1mp) {
-  const float qf = __fdividef(log1pf(-(float)u), (float)log_1mp);
+// geometric(p) by inversion on U = unit_double(a, b), support [1, inf): ceil(log(1-U) / log(1-p)); log_1mp = log(1-p)
+// comes from the host.  A float32 estimate decides unless the quotient q lies so close to an integer that the
+// estimate's error could change the ceiling; only then (about one row in 2,500) is the float64 expression
+// evaluated.  Both branches return the value of the float64 expression.  Error budget of the estimate, with
+// uf = float(a) * 2^-32:  |uf - U| <= 2^-27 + 2^-24 U  ->  |dq| <= q * 6e-8 / (1-U) + 7.5e-9 / ((1-U) |log_1mp|);
+// log1pf 1 ulp, __fdividef 2 ulp, float(log_1mp) 0.5 ulp -> 4.2e-7 * q.  The margin below is twice that bound.
+__device__ __forceinline__ int64_t geometric_from_words(uint32_t a, uint32_t b, double log_1mp, float abs_margin) {
+  const float uf = __uint2float_rn(a) * 2.3283064365386962891e-10f;
+  const float qf = __fdividef(log1pf(-uf), (float)log_1mp);
   const float cf = ceilf(qf);
-  const float margin = 1e-4f * (1.0f + qf);        // relative float error of the quotient is < 1e-5 for u < 0.99
+  const float inv = __fdividef(1.0f, 1.0f - uf);
+  const float margin = inv * fmaf(1.0f + qf, 1.2e-7f, abs_margin) + (1.0f + qf) * 8.4e-7f;   // abs_margin = 1.5e-8 / |log_1mp|
   double x;
-  if (u < 0.99 && cf - qf > margin && qf - (cf - 1.0f) > margin) x = (double)cf;
-  else x = ceil(log(1.0 - u) / log_1mp);
+  if (uf < 0.9999f && cf - qf > margin && qf - (cf - 1.0f) > margin) {
+    x = (double)cf;
+  } else {
+    x = ceil(log(1.0 - unit_double(a, b)) / log_1mp);
+  }
   return x < 1.0 ? 1 : (int64_t)x;
 }
 

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,6 +27,7 @@
 namespace {
 
 thread_local std::string g_error;
+std::vector<cudaEvent_t> g_timeline;   // OGB_TIMELINE=1: four events per sample() call (index begin/end, gather begin/end)
 
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -157,6 +159,23 @@ __global__ void philox_fill_kernel(const __grid_constant__ ogb::RngKey key, uint
     out[r] = ogb::draw4(key, batch, (uint32_t)r, purpose);
 }
 
+// test helper: the float32 fast path of the geometric inversion against the float64 expression it stands for
+__global__ void geometric_check_kernel(const __grid_constant__ ogb::RngKey key, double log_1mp, float abs_margin, int64_t n,
+                                       unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 w = ogb::draw4(key, (uint64_t)(r >> 32), (uint32_t)r, 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t a = h ? w.z : w.x, b = h ? w.w : w.y;
+      const double x = ceil(log(1.0 - ogb::unit_double(a, b)) / log_1mp);
+      const int64_t want = x < 1.0 ? 1 : (int64_t)x;
+      if (ogb::geometric_from_words(a, b, log_1mp, abs_margin) != want) ++bad;
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 enum Route { ROUTE_ROW = 0, ROUTE_FRAMES = 1, ROUTE_SCALAR = 2 };
 enum ScalarKind {
   SC_MASKS = 0, SC_REWARDS, SC_HV_OFFSETS, SC_HV_STEPS, SC_HV_MASKS, SC_HV_REWARDS, SC_LV_STEPS, SC_LV_MASKS, SC_LV_REWARDS,
@@ -204,6 +223,7 @@ struct ogb_dataset {
   int32_t* d_gap_c = nullptr;
   int32_t* d_gap_bucket = nullptr;
   int gap_shift = 0;
+  std::vector<int32_t> gaps_host;       // c[m] of valid_mode 2, kept for the sampler's segment table
   std::vector<uint8_t> terminals_host;  // terminals > 0, one byte per row (tiny next to the data)
   std::vector<uint8_t> valid_host;      // valids > 0 (empty when the dataset has no 'valids')
   size_t resident_bytes = 0;
@@ -234,6 +254,10 @@ struct ogb_sampler {
   int term_shift = 0;
   double* d_neg_lut = nullptr;
   double* d_pow_lut = nullptr;
+  // one-probe segment table (valid_mode 3): valid row AND final state from the same lookup
+  int4* d_seg_table = nullptr;
+  int32_t* d_seg_bucket = nullptr;
+  int seg_shift = -1;                    // < 0: not available for this dataset
   int n_slots = 0;
   std::vector<KeyPlan> plan[2];  // [evaluation]
   std::map<std::pair<int, int>, CUtensorMap> tmaps;  // (field, band_rows) -> descriptor
@@ -381,6 +405,8 @@ void sampler_unref(ogb_sampler* s) {
   if (s->trl_rows.dev) cudaFree(s->trl_rows.dev);
   if (s->d_term) cudaFree(s->d_term);
   if (s->d_term_bucket) cudaFree(s->d_term_bucket);
+  if (s->d_seg_table) cudaFree(s->d_seg_table);
+  if (s->d_seg_bucket) cudaFree(s->d_seg_bucket);
   if (s->d_neg_lut) cudaFree(s->d_neg_lut);
   if (s->d_pow_lut) cudaFree(s->d_pow_lut);
   dataset_unref(s->ds);
@@ -413,6 +439,42 @@ void batch_unref(ogb_batch* b) {
   else for (cudaEvent_t ev : free_after) cudaEventDestroy(ev);
   delete b;
   sampler_unref(s);
+}
+
+// Segment table of valid_mode 3 (relabel_rows.cuh, valid_row_fast).  Segment m = the valid rows that have exactly m
+// invalid rows before them.  Usable when (a) two boundaries c[m] are never closer than 16 positions, so that buckets
+// of 2^shift <= min gap positions hold at most one of them, and (b) no trajectory ends inside a segment before its
+// last valid row, so that final_state_idxs (datasets.py:306) is one value per segment.  Anything else keeps the
+// general searches.
+int build_segment_table(ogb_sampler* s) {
+  const ogb_dataset* ds = s->ds;
+  if (ds->valid_mode != 2 || ds->gaps_host.empty() || static_cast<const char*>(getenv("OGB_NO_SEGMENTS")) != nullptr) return 0;
+  const std::vector<int32_t>& c = ds->gaps_host;
+  const size_t n_gaps = c.size();
+  int64_t min_gap = ds->n_valid;
+  for (size_t m = 0; m + 1 < n_gaps; ++m) min_gap = std::min<int64_t>(min_gap, (int64_t)c[m + 1] - c[m]);
+  if (min_gap < 16) return 0;
+  int shift = 4;
+  while (((int64_t)1 << (shift + 1)) <= min_gap) ++shift;
+  if ((ds->n_valid >> shift) > ((int64_t)1 << 22)) return 0;
+  std::vector<int32_t> fin(n_gaps + 2);
+  for (size_t m = 0; m <= n_gaps; ++m) {
+    const int64_t first_row = m == 0 ? 0 : (int64_t)c[m - 1] + (int64_t)(m - 1) + 1;          // invalid row m-1 is c[m-1] + (m-1)
+    const int64_t last_valid = m < n_gaps ? (int64_t)c[m] + (int64_t)m - 1 : ds->size - 1;
+    if (first_row > last_valid) { fin[m] = (int32_t)std::min<int64_t>(first_row, ds->size - 1); continue; }  // empty: never looked up
+    auto it = std::lower_bound(s->term_host.begin(), s->term_host.end(), (int32_t)first_row);
+    if (it == s->term_host.end() || (int64_t)*it < last_valid) return 0;                        // (b) fails
+    fin[m] = *it;
+  }
+  fin[n_gaps + 1] = fin[n_gaps];
+  std::vector<int4> table(n_gaps + 1);
+  for (size_t m = 0; m <= n_gaps; ++m)
+    table[m] = make_int4(m < n_gaps ? c[m] : 0x7fffffff, fin[m], fin[m + 1], 0);
+  std::vector<int32_t> bucket = build_buckets(c, ds->n_valid + 1, shift);
+  OGB_TRY(upload_vector(table, &s->d_seg_table));
+  OGB_TRY(upload_vector(bucket, &s->d_seg_bucket));
+  s->seg_shift = shift;
+  return 0;
 }
 
 // ------------------------------------------------ key plan ------------------------------------------------
@@ -752,6 +814,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
       std::vector<int32_t> bucket = build_buckets(gaps, ds->n_valid + 1, ds->gap_shift);
       rc = upload_vector(gaps, &ds->d_gap_c);
       if (!rc) rc = upload_vector(bucket, &ds->d_gap_bucket);
+      ds->gaps_host = gaps;
       ds->resident_bytes += (gaps.size() + bucket.size()) * 4;
     } else {
       ds->valid_mode = 1;
@@ -844,6 +907,10 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
     int rc = upload_vector(s->term_host, &s->d_term);
     if (!rc) rc = upload_vector(bucket, &s->d_term_bucket);
     if (rc) return bail(rc);
+    {
+      int rc2 = build_segment_table(s);
+      if (rc2) return bail(rc2);
+    }
     if (kind == OGB_KIND_GC && cfg->trl == 1) {  // datasets.py:198-204: arange(cur, terminal) for every terminal row
       for (int64_t r = 0; r < ds->size; ++r)
         if (!ds->terminals_host[(size_t)r]) s->trl_rows.host.push_back((int32_t)r);
@@ -1043,7 +1110,19 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   // auxiliary stream, so that the index kernel of this call overlaps the gathers of the previous call, which are
   // still running on the main stream.  The recycled block only has to wait for its own previous owner.
   static const char* no_overlap = getenv("OGB_NO_OVERLAP");
-  const bool use_aux = !no_overlap && total >= kOverlapMinRows;
+  static const char* no_fuse = getenv("OGB_NO_FUSE");
+  static const char* force_gather = getenv("OGB_GATHER");  // "lsu" forces the register-staged kernel (A/B measurements)
+  auto takes_async_path = [&](const Field& f) {
+    return f.row_bytes > 16 && f.stride <= (size_t)ogb::kAsyncMaxStride && (size_t)ds->size * f.stride < ((size_t)1 << 36) &&
+           !(force_gather && strcmp(force_gather, "lsu") == 0);
+  };
+  // When some key goes through the cp.async row gather, the index algebra is fused into that launch (one kernel per
+  // sample() for vector observations); otherwise the index kernel runs on its own.
+  bool fuse = false;
+  if (!no_fuse)
+    for (const KeyPlan& k : plan)
+      if (k.route == ROUTE_ROW && k.alias_of < 0 && takes_async_path(ds->fields[(size_t)k.field])) fuse = true;
+  const bool use_aux = !fuse && !no_overlap && total >= kOverlapMinRows;
   if (use_aux) {
     int rc = ensure_aux(s);
     if (rc) return bail(rc);
@@ -1075,6 +1154,12 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   p.gap_bucket = ds->d_gap_bucket;
   p.gap_shift = ds->gap_shift;
   p.valid_mode = spec.choice_table ? 1 : ds->valid_mode;
+  if (!spec.choice_table && s->seg_shift >= 0) {
+    p.valid_mode = 3;
+    p.seg_table = s->d_seg_table;
+    p.seg_bucket = s->d_seg_bucket;
+    p.seg_shift = s->seg_shift;
+  }
   p.next_offset = (int32_t)spec.next_offset;
   p.trl = spec.trl ? 1 : 0;
   p.n_choices = n_choices;
@@ -1082,12 +1167,28 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   const double p_cur[3] = {cfg.value_p_curgoal, cfg.value_p_curgoal, cfg.actor_p_curgoal};
   const double p_traj[3] = {cfg.value_p_trajgoal, cfg.value_p_trajgoal, cfg.actor_p_trajgoal};
   const double disc[3] = {cfg.discount, cfg.has_low_discount ? cfg.low_discount : cfg.discount, cfg.discount};
+  auto word_threshold = [](double prob, uint32_t* thr, uint8_t* always) {
+    // (w * 2^-32 < prob) <=> (w < ceil(prob * 2^32)) for 32-bit words w; the scaling by 2^32 is exact in float64
+    const double t = std::ceil(prob * 4294967296.0);
+    *always = t >= 4294967296.0 ? 1 : 0;
+    *thr = t <= 0.0 ? 0u : (t >= 4294967296.0 ? 0xFFFFFFFFu : (uint32_t)t);
+  };
   for (int gs = 0; gs < 3; ++gs) {
-    p.goal[gs].geom = geom[gs];
-    p.goal[gs].cur_only = cur_only[gs];
-    p.goal[gs].p_cur = p_cur[gs];
-    p.goal[gs].thr_traj = cur_only[gs] ? 0.0 : p_traj[gs] / (1.0 - p_cur[gs]);
-    p.goal[gs].log_1mp = std::log(1.0 - (1.0 - disc[gs]));
+    GoalSpec& spec = p.goal[gs];
+    spec.geom = geom[gs];
+    spec.cur_only = cur_only[gs];
+    spec.p_cur = p_cur[gs];
+    spec.thr_traj = cur_only[gs] ? 0.0 : p_traj[gs] / (1.0 - p_cur[gs]);
+    spec.log_1mp = std::log(1.0 - (1.0 - disc[gs]));
+    spec.geo_abs_margin = (float)(1.5e-8 / std::fabs(spec.log_1mp));
+    word_threshold(spec.thr_traj, &spec.thr_traj32, &spec.traj_always);
+    word_threshold(spec.p_cur, &spec.thr_cur32, &spec.cur_always);
+  }
+  {  // the actor coins are only drawn when they can change the outcome
+    const GoalSpec& a = p.goal[2];
+    const bool cur_fixed = a.cur_only || a.cur_always || a.thr_cur32 == 0;
+    const bool traj_fixed = a.traj_always || a.thr_traj32 == 0;
+    p.actor_mix = (a.cur_only || (cur_fixed && traj_fixed)) ? 0 : 1;
   }
   p.neg_lut = s->d_neg_lut;
   p.pow_lut = s->d_pow_lut;
@@ -1102,9 +1203,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   p.crop_pad = cfg.crop_padding;
   p.p_aug = cfg.p_aug;
   p.key = make_rng_key(s->seed, s->stream_id);
-  p.need_mix = (!cur_only[0] || !cur_only[2]) ? 1 : 0;
   p.batch0 = s->counter;
   p.batch = batch_size;
+  p.batch_magic = batch_size > 1 && batch_size < ((int64_t)1 << 32) ? (uint64_t)(~(uint64_t)0 / (uint64_t)batch_size) + 1 : 0;
   p.total_rows = total;
   p.n_slots = spec.n_slots;
   p.vec_rows = b->vec_rows;
@@ -1163,7 +1264,6 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   std::vector<size_t> async_keys, lsu_keys;
   p.n_tiny = 0;
   {
-    static const char* force = getenv("OGB_GATHER");  // "lsu" forces the register-staged kernel (A/B measurements)
     for (size_t i = 0; i < plan.size(); ++i) {
       if (plan[i].route != ROUTE_ROW || plan[i].alias_of >= 0) continue;
       const Field& f = ds->fields[(size_t)plan[i].field];
@@ -1175,25 +1275,37 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         t.slot = (uint8_t)plan[i].slot;
         t.size_log2 = (uint8_t)v;
         t.n_elem = (uint8_t)(f.row_bytes >> v);
-      } else if (f.row_bytes > 16 && f.stride <= (size_t)kAsyncMaxStride && !(force && strcmp(force, "lsu") == 0)) {
+        t.row_bytes = (uint8_t)f.row_bytes;
+      } else if (takes_async_path(f)) {
         async_keys.push_back(i);
       } else {
         lsu_keys.push_back(i);
       }
     }
   }
-  p.write_vecs = (!async_keys.empty() || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
+  fuse = fuse && !async_keys.empty();
+  // the index vectors only go to memory when a later launch (or the debug interface) reads them
+  p.write_vecs = ((!fuse && !async_keys.empty()) || async_keys.size() > (size_t)kMaxRowJobs || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
 
   // ---- prepare every launch once; each is then issued per row chunk ----
   typedef std::function<int(int64_t, int64_t, cudaStream_t)> LaunchFn;
   std::vector<LaunchFn> gather_launches;
+  LaunchFn fused_launch;
 
   LaunchFn index_launch = [&, p](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
     p.row_begin = begin;
     p.row_end = end;
     const unsigned grid = (unsigned)std::min<int64_t>((end - begin + kRelabelThreads - 1) / kRelabelThreads, (int64_t)ds->sm_count * 16);
-    if (draws) relabel_index_kernel<true><<<grid, kRelabelThreads, 0, st>>>(p);
-    else relabel_index_kernel<false><<<grid, kRelabelThreads, 0, st>>>(p);
+    const int flavour = p.kind == OGB_KIND_GC ? FLAVOUR_GC : (p.kind == OGB_KIND_HGC ? FLAVOUR_HGC : FLAVOUR_PLAIN);
+    if (draws) {
+      if (flavour == FLAVOUR_GC) relabel_index_kernel<true, FLAVOUR_GC><<<grid, kRelabelThreads, 0, st>>>(p);
+      else if (flavour == FLAVOUR_HGC) relabel_index_kernel<true, FLAVOUR_HGC><<<grid, kRelabelThreads, 0, st>>>(p);
+      else relabel_index_kernel<true, FLAVOUR_PLAIN><<<grid, kRelabelThreads, 0, st>>>(p);
+    } else {
+      if (flavour == FLAVOUR_GC) relabel_index_kernel<false, FLAVOUR_GC><<<grid, kRelabelThreads, 0, st>>>(p);
+      else if (flavour == FLAVOUR_HGC) relabel_index_kernel<false, FLAVOUR_HGC><<<grid, kRelabelThreads, 0, st>>>(p);
+      else relabel_index_kernel<false, FLAVOUR_PLAIN><<<grid, kRelabelThreads, 0, st>>>(p);
+    }
     if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "relabel_index_kernel launch failed");
     b->launches++;
     return 0;
@@ -1210,32 +1322,73 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     for (size_t t = q0; t < async_keys.size() && t < q0 + kMaxRowJobs; ++t)
       max_stride = std::max(max_stride, ds->fields[(size_t)plan[async_keys[t]].field].stride);
     static const int env_stage = getenv("OGB_STAGE_BYTES") ? atoi(getenv("OGB_STAGE_BYTES")) : 0;
-    static const int env_flat = getenv("OGB_DRAIN_FLAT") ? atoi(getenv("OGB_DRAIN_FLAT")) : 1;
-    ap.stage_bytes = env_stage ? std::max<int>(env_stage, (int)max_stride) : 4096;
-    ap.flat_drain = env_flat;
+    ap.stage_bytes = env_stage ? std::max<int>((env_stage + 127) / 128 * 128, (int)max_stride) : 4096;
     auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
     for (; q < async_keys.size() && ap.n_jobs < kMaxRowJobs; ++q) {
       const KeyPlan& k = plan[async_keys[q]];
       const Field& f = ds->fields[(size_t)k.field];
       AsyncJob& job = ap.jobs[ap.n_jobs++];
-      const int v = largest_vec_log2(f.row_bytes, 16);
       job.src = f.dptr;
       job.dst = base + b->offsets[async_keys[q]];
       job.stride = (uint32_t)f.stride;
       job.row_bytes = (uint32_t)f.row_bytes;
       job.cpr = (uint32_t)((f.row_bytes + 15) / 16);
       job.cpr_magic = magic(job.cpr);
-      job.epr = (uint32_t)(f.row_bytes >> v);
+      job.chunk_dr = (uint8_t)(32 / job.cpr);
+      job.chunk_dch = (uint8_t)(32 % job.cpr);
+      job.chunk_step = (uint32_t)job.chunk_dr * job.stride + (uint32_t)job.chunk_dch * 16u;
+      job.chunk_wrap = job.stride - job.cpr * 16u;
+      job.gap = (uint32_t)(f.stride - f.row_bytes);
+      if (f.row_bytes % 16 == 0 && job.gap == 0) {
+        job.drain = DRAIN_DENSE16;
+      } else if (f.row_bytes % 4 == 0) {
+        job.drain = DRAIN_WORDS;
+        job.epr = (uint32_t)(f.row_bytes / 4);
+      } else {
+        job.drain = DRAIN_ELEMS;
+        job.vec_log2 = (uint8_t)(f.row_bytes % 2 == 0 ? 1 : 0);
+        job.epr = (uint32_t)(f.row_bytes >> job.vec_log2);
+      }
       job.epr_magic = magic(job.epr);
       size_t rpi = std::min<size_t>(32, (size_t)ap.stage_bytes / f.stride);
       if (rpi > 4) rpi &= ~(size_t)3;   // items start on 16-byte boundaries of the dense output (16-byte drain stores)
       job.rows_per_item = (uint16_t)rpi;
-      job.vec_log2 = (uint8_t)v;
       job.slot = (uint8_t)k.slot;
     }
     const size_t smem = (size_t)kAsyncWarps * kAsyncStages * ap.stage_bytes;
-    OGB_CUDA(cudaFuncSetAttribute(gather_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    if (fuse && q0 == 0) {
+      // index algebra + the first (normally the only) group of row jobs in ONE launch
+      FusedParams* fp = new FusedParams();
+      fp->relabel = p;
+      fp->gather = ap;
+      std::shared_ptr<FusedParams> keep(fp);
+      const int flavour = p.kind == OGB_KIND_GC ? FLAVOUR_GC : (p.kind == OGB_KIND_HGC ? FLAVOUR_HGC : FLAVOUR_PLAIN);
+      const bool inject = draws != nullptr;
+      fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
+        FusedParams& f = *keep;
+        f.relabel.row_begin = f.gather.row_begin = begin;
+        f.relabel.row_end = f.gather.row_end = end;
+        const int64_t n_warp_tiles = (end - begin + 31) / 32;
+        const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * ctas_per_sm);
+        const void* fn = nullptr;
+        if (inject) fn = flavour == FLAVOUR_GC ? (const void*)relabel_gather_kernel<true, FLAVOUR_GC>
+                       : flavour == FLAVOUR_HGC ? (const void*)relabel_gather_kernel<true, FLAVOUR_HGC>
+                                                : (const void*)relabel_gather_kernel<true, FLAVOUR_PLAIN>;
+        else fn = flavour == FLAVOUR_GC ? (const void*)relabel_gather_kernel<false, FLAVOUR_GC>
+                : flavour == FLAVOUR_HGC ? (const void*)relabel_gather_kernel<false, FLAVOUR_HGC>
+                                         : (const void*)relabel_gather_kernel<false, FLAVOUR_PLAIN>;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+          return fail(OGB_ERR_CUDA, "cudaFuncSetAttribute(relabel_gather_kernel) failed");
+        void* args[] = {(void*)&f};
+        if (cudaLaunchKernel(fn, dim3(grid), dim3(kAsyncWarps * 32), args, smem, st) != cudaSuccess)
+          return fail(OGB_ERR_CUDA, "relabel_gather_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        b->launches++;
+        return 0;
+      };
+      continue;
+    }
+    OGB_CUDA(cudaFuncSetAttribute(gather_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
       ap.row_begin = begin;
       ap.row_end = end;
@@ -1381,16 +1534,28 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
 
   // ---- issue: index kernel on `first`, gathers on the main stream behind it ----
   {
-    int rc = index_launch(0, total, first);
+    static const bool timeline = getenv("OGB_TIMELINE") != nullptr;   // debug: when did each phase run on the device
+    auto stamp = [&](cudaStream_t st) {
+      if (!timeline) return;
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      cudaEventRecord(ev, st);
+      g_timeline.push_back(ev);
+    };
+    stamp(first);
+    int rc = fused_launch ? fused_launch(0, total, first) : index_launch(0, total, first);
     if (rc) return bail(rc);
+    stamp(first);
     if (first != s->stream) {
       cudaEvent_t ev = s->chunk_events[s->next_event];
       s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
       if (cudaEventRecord(ev, first) != cudaSuccess || cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess)
         return bail(fail(OGB_ERR_CUDA, "stream join failed"));
     }
+    stamp(s->stream);
     for (size_t q = 0; q < gather_launches.size() && !rc; ++q) rc = gather_launches[q](0, total, s->stream);
     if (rc) return bail(rc);
+    stamp(s->stream);
   }
   if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
     return bail(fail(OGB_ERR_CUDA, "ready event failed"));
@@ -1670,6 +1835,38 @@ int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* 
   OGB_CUDA(cudaGetLastError());
   OGB_CUDA(cudaMemcpy(out_host, d_o, (size_t)m * 8, cudaMemcpyDeviceToHost));
   cudaFree(d_t); cudaFree(d_k); cudaFree(d_o);
+  return 0;
+}
+
+int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out) {
+  if (!out_ms || !n_out) return fail(OGB_ERR_INVALID, "null argument");
+  OGB_CUDA(cudaDeviceSynchronize());
+  const int n = (int)std::min<size_t>(g_timeline.size(), (size_t)std::max(capacity, 0));
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.0f;
+    OGB_CUDA(cudaEventElapsedTime(&ms, g_timeline[0], g_timeline[(size_t)i]));
+    out_ms[i] = ms;
+  }
+  for (cudaEvent_t ev : g_timeline) cudaEventDestroy(ev);
+  g_timeline.clear();
+  *n_out = n;
+  return 0;
+}
+
+int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t device, int64_t* mismatches) {
+  if (!mismatches || n < 0 || !(discount > 0.0 && discount < 1.0)) return fail(OGB_ERR_INVALID, "bad arguments");
+  OGB_CUDA(cudaSetDevice(device));
+  unsigned long long* d = nullptr;
+  OGB_CUDA(cudaMalloc((void**)&d, 8));
+  OGB_CUDA(cudaMemset(d, 0, 8));
+  const double log_1mp = std::log(1.0 - (1.0 - discount));
+  const ogb::RngKey key = ogb::make_rng_key(seed, 0);
+  if (n > 0) geometric_check_kernel<<<148 * 8, 256>>>(key, log_1mp, (float)(1.5e-8 / std::fabs(log_1mp)), n, d);
+  OGB_CUDA(cudaGetLastError());
+  unsigned long long host = 0;
+  OGB_CUDA(cudaMemcpy(&host, d, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *mismatches = (int64_t)host;
   return 0;
 }
 

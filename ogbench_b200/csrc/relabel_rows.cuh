@@ -29,11 +29,16 @@ enum : int {
 };
 
 struct GoalSpec {
+  // Philox mode: the goal-mix coins are 32-bit words w, and (w * 2^-32 < p) <=> (w < ceil(p * 2^32)) exactly, so the
+  // kernel compares integers; *_always covers thresholds >= 2^32 (p >= 1)
+  uint32_t thr_traj32, thr_cur32;
+  uint8_t traj_always, cur_always;
+  uint8_t geom;      // geometric (1) or uniform-in-remainder (0) future goals
+  uint8_t cur_only;  // p_curgoal == 1.0 short-circuit (datasets.py:317-318)
+  float geo_abs_margin;  // absolute slack of the float32 geometric estimate, 2^-26 / |log(1-p)|
   double thr_traj;   // p_trajgoal / (1.0 - p_curgoal), float64 as the reference evaluates it (datasets.py:321)
   double p_cur;
   double log_1mp;    // log(1 - (1 - discount)) for the geometric inversion
-  int32_t geom;      // geometric (1) or uniform-in-remainder (0) future goals
-  int32_t cur_only;  // p_curgoal == 1.0 short-circuit (datasets.py:317-318)
 };
 
 struct GoalInject {
@@ -66,7 +71,7 @@ struct TinyJob {
   uint8_t slot;
   uint8_t size_log2;   // element size
   uint8_t n_elem;      // row = n_elem elements (<= 16 bytes in total)
-  uint8_t pad_;
+  uint8_t row_bytes;
   uint32_t pad2_;
 };
 
@@ -81,7 +86,11 @@ struct RelabelParams {
   int32_t n_rows_ds;
   int32_t term_shift;
   int32_t gap_shift;
-  int32_t valid_mode;          // 0: no 'valids'; 1: table; 2: gap ranks
+  int32_t valid_mode;          // 0: no 'valids'; 1: table; 2: gap ranks; 3: segment table (one probe, see valid_row_fast)
+  const int4* seg_table;       // valid_mode 3: {c[m], final_state(segment m), final_state(segment m+1), 0}
+  const int32_t* seg_bucket;   //               lower_bound(c, b << seg_shift); a bucket holds at most one c[m]
+  int32_t seg_shift;
+  int32_t pad_seg_;
   // ---- sampler config ----
   GoalSpec goal[3];            // value, low-value, actor
   const double* neg_lut;       // -(1 - discount**s)/(1 - discount)
@@ -96,7 +105,7 @@ struct RelabelParams {
   int32_t k_val, k_act, k_lo;
   int32_t gc_negative;
   int32_t stacked_next;        // frame_stack set: next_observations uses un-clamped idx+1 (datasets.py:231)
-  int32_t need_mix;            // some goal set has 0 < p_cur < 1 or a real traj/random choice: draw the mix uniforms
+  int32_t actor_mix;           // the actor goal mix is a real random choice: draw its two coins (PURPOSE_MIX)
   int32_t aug_mode;            // draw the per-batch coin (p_aug is not None and not evaluation)
   int32_t crop_pad;
   double p_aug;
@@ -110,8 +119,9 @@ struct RelabelParams {
   const int64_t* given_idxs;
   // ---- launch shape ----
   int64_t batch;               // rows per sample() call
+  uint64_t batch_magic;        // ceil(2^64 / batch), 0 when batch == 1: g / batch == umul64hi(g, magic) for g < 2^32
   int64_t total_rows;          // batch * n_batches (also the stride of the [slot][row] index vectors)
-  int64_t row_begin, row_end;  // rows this launch handles (a big launch is split into chunks, see ogb_sampler.cu)
+  int64_t row_begin, row_end;  // rows this launch handles
   int32_t n_slots;
   int32_t pad0_;
   // ---- scalar outputs (float64 / int64 like the reference) ----
@@ -134,41 +144,61 @@ struct RelabelParams {
   TinyJob tiny[kMaxTinyJobs];
 };
 
+// valid_mode 3 -- datasets whose invalid rows are far apart (every compact OGBench dataset: one per trajectory) and
+// whose trajectories end where their valid rows end.  Position pos among the valid rows falls into segment
+// m = #{invalid rows before it} = upper_bound(c, pos); buckets are narrower than the smallest gap between two c[m],
+// so a bucket holds at most one boundary and the search is ONE probe: two dependent loads give the row AND the
+// trajectory's final state (datasets.py:306 needs a second search in the reference).
+__device__ __forceinline__ int32_t valid_row_fast(const RelabelParams& p, const uint32_t pos, int32_t& fin) {
+  const int lo = __ldg(p.seg_bucket + (pos >> p.seg_shift));
+  const int4 e = __ldg(p.seg_table + lo);
+  const bool past = e.x <= (int32_t)pos;
+  fin = past ? e.z : e.y;
+  return (int32_t)pos + lo + (past ? 1 : 0);
+}
+
 __device__ __forceinline__ int32_t valid_row(const RelabelParams& p, int64_t pos) {
+  if (p.valid_mode == 3) { int32_t unused; return valid_row_fast(p, (uint32_t)pos, unused); }
   if (p.valid_mode == 0) return (int32_t)pos;
   if (p.valid_mode == 1) return __ldg(p.valid_table + pos);
   const int j = (int)pos;
   return j + lower_bound_bucketed(p.gap_c, p.gap_bucket, p.gap_shift, j + 1);  // upper_bound(c, j)
 }
 
-// `mix` carries the two 32-bit goal-mix uniforms of this goal set (Philox mode; ignored when draws are injected).
-template <bool kInject>
-__device__ __forceinline__ int32_t pick_goal(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
-                                             const uint64_t batch_id, const uint32_t r, const int64_t g, const uint2 mix) {
+// datasets.py:313-316 -- float64, separate multiply/add (no FMA contraction), round half to even
+__device__ __forceinline__ int32_t uniform_future_goal(int32_t i, int32_t fin, double d) {
+  const int32_t lo = (i + 1 < fin) ? i + 1 : fin;
+  return (int32_t)rint(__dadd_rn(__dmul_rn((double)lo, d), __dmul_rn((double)fin, __dsub_rn(1.0, d))));
+}
+
+// Validation mode: the reference's own draws (float64 uniforms, int64 offsets) decide.
+__device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
+                                                      const int64_t g) {
   const GoalSpec& s = p.goal[gs];
   if (s.cur_only) return i;                                  // p_curgoal == 1.0  (datasets.py:317-318)
-  if (kInject) {
-    const GoalInject& in = p.in_goal[gs];
-    if (in.u_cur[g] < s.p_cur) return i;                     // np.where(rand < p_cur, idxs, ...)  :325
-    if (!(in.u_traj[g] < s.thr_traj)) return valid_row(p, in.rand_pos[g]);   // random goal  :303,:320-322
-    if (s.geom) {                                            // :309-310
-      const int64_t t = (int64_t)i + in.offset[g];
-      return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
-    }
-    const int32_t lo = (i + 1 < fin) ? i + 1 : fin;          // :313-316 -- float64, no FMA contraction, half-even
-    const double d = in.dist[g];
-    return (int32_t)rint(__dadd_rn(__dmul_rn((double)lo, d), __dmul_rn((double)fin, __dsub_rn(1.0, d))));
-  }
-  if (unit_from_word(mix.y) < s.p_cur) return i;
-  const uint4 a = draw4(p.key, batch_id, r, PURPOSE_GOAL + (uint32_t)gs);
-  if (!(unit_from_word(mix.x) < s.thr_traj)) return valid_row(p, bounded_u64(a.x, a.y, (uint64_t)p.n_choices));
-  const double u = unit_double(a.z, a.w);
-  if (s.geom) {
-    const int64_t t = (int64_t)i + geometric_from_unit(u, s.log_1mp);
+  const GoalInject& in = p.in_goal[gs];
+  if (in.u_cur[g] < s.p_cur) return i;                       // np.where(rand < p_cur, idxs, ...)  :325
+  if (!(in.u_traj[g] < s.thr_traj)) return valid_row(p, in.rand_pos[g]);   // random goal  :303,:320-322
+  if (s.geom) {                                              // :309-310
+    const int64_t t = (int64_t)i + in.offset[g];
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
   }
-  const int32_t lo = (i + 1 < fin) ? i + 1 : fin;
-  return (int32_t)rint(__dadd_rn(__dmul_rn((double)lo, u), __dmul_rn((double)fin, __dsub_rn(1.0, u))));
+  return uniform_future_goal(i, fin, in.dist[g]);
+}
+
+// Philox mode: `mix` = (u_traj, u_cur) as 32-bit words, `bits` = the 64 random bits of this goal set, spent either
+// on the random-goal position or on the geometric / distance uniform -- never both, since the mix decides first.
+__device__ __forceinline__ int32_t pick_goal_philox(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
+                                                    const uint2 mix, const uint2 bits) {
+  const GoalSpec& s = p.goal[gs];
+  if (s.cur_only) return i;
+  if (s.cur_always || mix.y < s.thr_cur32) return i;
+  if (!(s.traj_always || mix.x < s.thr_traj32)) return valid_row(p, bounded_u32n(bits.x, bits.y, (uint32_t)p.n_choices));
+  if (s.geom) {
+    const int64_t t = (int64_t)i + geometric_from_words(bits.x, bits.y, s.log_1mp, s.geo_abs_margin);
+    return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
+  }
+  return uniform_future_goal(i, fin, unit_double(bits.x, bits.y));
 }
 
 // datasets.py:478-491
@@ -193,154 +223,215 @@ __device__ __forceinline__ void put_slot(const RelabelParams& p, int32_t* sr, co
   if (p.vec_init != nullptr) p.vec_init[(int64_t)slot * p.total_rows + g] = trajectory_first_row(p, x);
 }
 
+template <int kSlots>
 __device__ __forceinline__ int32_t pick_slot(const int32_t* sr, const int slot) {
   int32_t x = sr[0];
 #pragma unroll
-  for (int v = 1; v < kMaxSlots; ++v) x = (slot == v) ? sr[v] : x;
+  for (int v = 1; v < kSlots; ++v) x = (slot == v) ? sr[v] : x;
   return x;
 }
 
-template <bool kInject>
+// kernel flavours: which index algebra is compiled in
+enum : int { FLAVOUR_GC = 0, FLAVOUR_HGC = 1, FLAVOUR_PLAIN = 2 };  // PLAIN also serves ATC (index + offset, crop)
+template <int kFlavour> struct FlavourSlots { static constexpr int value = kFlavour == FLAVOUR_GC ? GC_TRL_NUM_SLOTS : (kFlavour == FLAVOUR_HGC ? HGC_NUM_SLOTS : 2); };
+
+__device__ __forceinline__ void split_row(const RelabelParams& p, const int64_t g, uint64_t& batch_id, uint32_t& r) {
+  // g / batch with the host's magic number; g < 2^32 (a launch holds at most 2^31 rows)
+  const uint32_t g32 = (uint32_t)g;
+  uint32_t kb = g32;
+  if (p.batch_magic != 0) {
+    const uint64_t lo = (uint64_t)g32 * (uint32_t)p.batch_magic;
+    const uint64_t hi = (uint64_t)g32 * (uint32_t)(p.batch_magic >> 32) + (lo >> 32);
+    kb = (uint32_t)(hi >> 32);
+  } else if (p.batch != 1) {
+    kb = (uint32_t)(g / p.batch);   // batch >= 2^32: never on the fast path
+  }
+  r = g32 - kb * (uint32_t)p.batch;
+  batch_id = p.batch0 + (uint64_t)kb;
+}
+
+// All per-row work of sample(): index draws, goal relabelling, rewards/masks, the rows of <= 16 bytes, crop shifts.
+// On return sr[] holds the dataset row of every slot for batch row g.
+template <bool kInject, int kFlavour>
+__device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_t g, int32_t* sr) {
+  constexpr int kSlots = FlavourSlots<kFlavour>::value;
+  uint64_t batch_id;
+  uint32_t r;
+  split_row(p, g, batch_id, r);
+
+  uint4 w0 = make_uint4(0, 0, 0, 0);
+  if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
+  int32_t i, fin = -1;
+  if (p.given_idxs != nullptr) {
+    i = (int32_t)p.given_idxs[g];
+  } else {
+    const int64_t pos = kInject ? p.in_idx_pos[g] : (int64_t)bounded_u32n(w0.x, w0.y, (uint32_t)p.n_choices);
+    if (p.valid_mode == 3) i = valid_row_fast(p, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe
+    else i = valid_row(p, pos);
+  }
+  put_slot(p, sr, SLOT_IDX, g, i);
+  const int32_t nxt = p.stacked_next ? i + p.next_offset                                           // :231 / :408
+                                     : (i + p.next_offset < p.n_rows_ds ? i + p.next_offset : p.n_rows_ds - 1);  // :82
+  put_slot(p, sr, SLOT_NEXT, g, nxt);
+
+  if (kFlavour != FLAVOUR_PLAIN) {
+    uint4 gb = make_uint4(0, 0, 0, 0), amix = make_uint4(0, 0, 0, 0);
+    if (!kInject) {
+      gb = draw4(p.key, batch_id, r, PURPOSE_GOAL);
+      if (p.actor_mix) amix = draw4(p.key, batch_id, r, PURPOSE_MIX);
+    }
+    if (fin < 0) {                                                      // final_state_idxs  :306,:505
+      const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
+      fin = __ldg(p.term + tl);
+    }
+    const double neg = p.gc_negative ? 1.0 : 0.0;
+    const int32_t vg = kInject ? pick_goal_injected(p, 0, i, fin, g)                   // :233-239 / :508-514
+                               : pick_goal_philox(p, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
+    const int32_t ag = kInject ? pick_goal_injected(p, 2, i, fin, g)                   // :240-246 / :585-591
+                               : pick_goal_philox(p, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
+    const double succ = (i == vg) ? 1.0 : 0.0;                         // :250-252 / :579-582
+    p.masks[g] = 1.0 - succ;
+    p.rewards[g] = succ - neg;
+    if (kFlavour == FLAVOUR_GC) {
+      put_slot(p, sr, GC_VALUE_GOAL, g, vg);
+      put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
+      if (p.trl) {                                                     // :259-267
+        const int64_t span = vg > i ? (int64_t)vg - i : 1;             // the reference asserts idxs != value_goal_idxs
+        int32_t mid;
+        if (kInject) {
+          mid = (int32_t)p.in_trl_mid[g];
+        } else {
+          const uint4 t = draw4(p.key, batch_id, r, PURPOSE_TRL_MID);
+          mid = i + (int32_t)bounded_u32n(t.x, t.y, (uint32_t)span);   // randint(idxs, value_goal_idxs): [i, vg)
+        }
+        put_slot(p, sr, GC_TRL_MID, g, mid);
+        put_slot(p, sr, GC_TRL_PLUS1, g, i + 1);
+        p.trl_offsets[g] = (int64_t)vg - i;
+        p.trl_mid_offsets[g] = (int64_t)mid - i;
+      }
+    } else {
+      const int32_t hv = vg;
+      int32_t hv_next, hv_s, lv_next, lv_s;
+      subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
+      subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
+      put_slot(p, sr, HGC_HV_GOAL, g, hv);
+      put_slot(p, sr, HGC_HV_NEXT, g, hv_next);
+      put_slot(p, sr, HGC_LV_NEXT, g, lv_next);
+      p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
+      p.hv_steps[g] = hv_s;
+      p.lv_steps[g] = lv_s;
+      const double hv_succ = hv_s < p.k_val ? 1.0 : 0.0;                            // :533
+      const double lv_succ = lv_s < p.k_lo ? 1.0 : 0.0;                             // :552
+      p.hv_masks[g] = 1.0 - hv_succ;
+      p.hv_rewards[g] = p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ);
+      double lv_mask = 1.0 - lv_succ;
+      double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
+      if (p.has_low_goal) {                                                         // :563-576
+        int32_t lvg;
+        if (kInject) {
+          lvg = pick_goal_injected(p, 1, i, fin, g);
+        } else {
+          const uint4 lb = draw4(p.key, batch_id, r, PURPOSE_GOAL_LOW);
+          lvg = pick_goal_philox(p, 1, i, fin, make_uint2(lb.z, lb.w), make_uint2(lb.x, lb.y));
+        }
+        put_slot(p, sr, HGC_LV_GOAL, g, lvg);
+        const double s = (i == lvg) ? 1.0 : 0.0;
+        lv_mask = 1.0 - s;
+        lv_rew = s - neg;
+      }
+      p.lv_masks[g] = lv_mask;
+      p.lv_rewards[g] = lv_rew;
+      const int32_t ha = ag;
+      int32_t ha_next, la_next, unused;
+      subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
+      subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
+      const int64_t la = (int64_t)i + p.k_act;                                      // :610
+      put_slot(p, sr, HGC_HA_GOAL, g, ha);
+      put_slot(p, sr, HGC_HA_NEXT, g, ha_next);
+      put_slot(p, sr, HGC_LA_GOAL, g, (int32_t)(la < (int64_t)fin ? la : (int64_t)fin));
+      put_slot(p, sr, HGC_LA_NEXT, g, la_next);
+    }
+  }
+
+  // rows of <= 16 bytes: this thread copies them now (datasets.py:78-83 for the per-transition fields).  Rows of 4, 8,
+  // 12 or 16 bytes are loaded four jobs at a time before any is stored, so their L2 latencies overlap.
+#pragma unroll 1
+  for (int j0 = 0; j0 < p.n_tiny; j0 += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u < p.n_tiny) {
+        const TinyJob& job = p.tiny[j0 + u];
+        const uint32_t row_bytes = job.row_bytes;
+        const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * row_bytes;
+        if (row_bytes == 4) v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp));
+        else if (row_bytes == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp)); v[u].x = t.x; v[u].y = t.y; }
+        else if (row_bytes == 16) v[u] = __ldg(reinterpret_cast<const uint4*>(sp));
+        else if (row_bytes == 12) {
+          v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp)); v[u].y = __ldg(reinterpret_cast<const uint32_t*>(sp) + 1);
+          v[u].z = __ldg(reinterpret_cast<const uint32_t*>(sp) + 2);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u < p.n_tiny) {
+        const TinyJob& job = p.tiny[j0 + u];
+        const uint32_t row_bytes = job.row_bytes;
+        uint8_t* dp = job.dst + (size_t)g * row_bytes;
+        if (row_bytes == 4) *reinterpret_cast<uint32_t*>(dp) = v[u].x;
+        else if (row_bytes == 8) *reinterpret_cast<uint2*>(dp) = make_uint2(v[u].x, v[u].y);
+        else if (row_bytes == 16) *reinterpret_cast<uint4*>(dp) = v[u];
+        else if (row_bytes == 12) {
+          reinterpret_cast<uint32_t*>(dp)[0] = v[u].x; reinterpret_cast<uint32_t*>(dp)[1] = v[u].y; reinterpret_cast<uint32_t*>(dp)[2] = v[u].z;
+        } else {                                      // odd sizes: element by element
+          const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * row_bytes;
+          if (job.size_log2 == 1) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
+          else if (job.size_log2 == 2) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
+          else for (uint32_t e = 0; e < row_bytes; ++e) dp[e] = __ldg(sp + e);
+        }
+      }
+    }
+  }
+
+  if (p.crop_out != nullptr) {
+    int dy = -128, dx = -128;
+    if (p.aug_mode) {                                                               // :278-279, :621-622
+      double coin;
+      if (kInject) {
+        coin = p.in_coin;
+      } else {
+        const uint4 c = draw4(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
+        coin = unit_double(c.x, c.y);
+      }
+      if (coin < p.p_aug) {                                                         // :333
+        int cy, cx;
+        if (kInject) {
+          cy = (int)p.in_crop[2 * g];
+          cx = (int)p.in_crop[2 * g + 1];
+        } else {
+          const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
+          const uint4 cw = draw4(p.key, batch_id, r, PURPOSE_CROP);
+          const uint32_t joint = __umulhi(cw.x, span * span);          // (cy, cx) jointly uniform on span x span
+          cy = (int)(joint / span);
+          cx = (int)(joint % span);
+        }
+        dy = cy - p.crop_pad;
+        dx = cx - p.crop_pad;
+      }
+    }
+    p.crop_out[2 * g] = (int8_t)dy;
+    p.crop_out[2 * g + 1] = (int8_t)dx;
+  }
+}
+
+template <bool kInject, int kFlavour>
 __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
   for (int64_t g = p.row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.row_end; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t kb = g / p.batch;
-    const uint32_t r = (uint32_t)(g - kb * p.batch);
-    const uint64_t batch_id = p.batch0 + (uint64_t)kb;
     int32_t sr[kMaxSlots];
 #pragma unroll
     for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
-
-    uint4 w0 = make_uint4(0, 0, 0, 0);
-    if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
-    int32_t i;
-    if (p.given_idxs != nullptr) {
-      i = (int32_t)p.given_idxs[g];
-    } else {
-      const int64_t pos = kInject ? p.in_idx_pos[g] : bounded_u64(w0.x, w0.y, (uint64_t)p.n_choices);
-      i = valid_row(p, pos);                                            // datasets.py:65-70
-    }
-    put_slot(p, sr, SLOT_IDX, g, i);
-    const int32_t nxt = p.stacked_next ? i + p.next_offset                                           // :231 / :408
-                                       : (i + p.next_offset < p.n_rows_ds ? i + p.next_offset : p.n_rows_ds - 1);  // :82
-    put_slot(p, sr, SLOT_NEXT, g, nxt);
-
-    if (p.kind == 0 || p.kind == 1) {
-      uint4 mix = make_uint4(0, 0, 0, 0);
-      if (!kInject && p.need_mix) mix = draw4(p.key, batch_id, r, PURPOSE_MIX);
-      const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
-      const int32_t fin = __ldg(p.term + tl);                            // final_state_idxs  :306,:505
-      const double neg = p.gc_negative ? 1.0 : 0.0;
-      if (p.kind == 0) {
-        const int32_t vg = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g, make_uint2(mix.x, mix.y));
-        const int32_t ag = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g, make_uint2(mix.z, mix.w));
-        put_slot(p, sr, GC_VALUE_GOAL, g, vg);
-        put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
-        const double succ = (i == vg) ? 1.0 : 0.0;                       // :250-252
-        p.masks[g] = 1.0 - succ;
-        p.rewards[g] = succ - neg;
-        if (p.trl) {                                                     // :259-267
-          const int64_t span = vg > i ? (int64_t)vg - i : 1;             // the reference asserts idxs != value_goal_idxs
-          int32_t mid;
-          if (kInject) {
-            mid = (int32_t)p.in_trl_mid[g];
-          } else {
-            const uint4 t = draw4(p.key, batch_id, r, PURPOSE_TRL_MID);
-            mid = i + (int32_t)bounded_u64(t.x, t.y, (uint64_t)span);    // randint(idxs, value_goal_idxs): [i, vg)
-          }
-          put_slot(p, sr, GC_TRL_MID, g, mid);
-          put_slot(p, sr, GC_TRL_PLUS1, g, i + 1);
-          p.trl_offsets[g] = (int64_t)vg - i;
-          p.trl_mid_offsets[g] = (int64_t)mid - i;
-        }
-      } else {
-        const int32_t hv = pick_goal<kInject>(p, 0, i, fin, batch_id, r, g, make_uint2(mix.x, mix.y));   // :508-514
-        int32_t hv_next, hv_s, lv_next, lv_s;
-        subgoal_step(i, fin, hv, p.k_val, hv_next, hv_s);                             // :519-524
-        subgoal_step(i, fin, hv, p.k_lo, lv_next, lv_s);                              // :544-549
-        put_slot(p, sr, HGC_HV_GOAL, g, hv);
-        put_slot(p, sr, HGC_HV_NEXT, g, hv_next);
-        put_slot(p, sr, HGC_LV_NEXT, g, lv_next);
-        p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
-        p.hv_steps[g] = hv_s;
-        p.lv_steps[g] = lv_s;
-        const double hv_succ = hv_s < p.k_val ? 1.0 : 0.0;                            // :533
-        const double lv_succ = lv_s < p.k_lo ? 1.0 : 0.0;                             // :552
-        p.hv_masks[g] = 1.0 - hv_succ;
-        p.hv_rewards[g] = p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ);
-        double lv_mask = 1.0 - lv_succ;
-        double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
-        if (p.has_low_goal) {                                                         // :563-576
-          uint4 mix_low = make_uint4(0, 0, 0, 0);
-          if (!kInject) mix_low = draw4(p.key, batch_id, r, PURPOSE_MIX_LOW);
-          const int32_t lvg = pick_goal<kInject>(p, 1, i, fin, batch_id, r, g, make_uint2(mix_low.x, mix_low.y));
-          put_slot(p, sr, HGC_LV_GOAL, g, lvg);
-          const double s = (i == lvg) ? 1.0 : 0.0;
-          lv_mask = 1.0 - s;
-          lv_rew = s - neg;
-        }
-        p.lv_masks[g] = lv_mask;
-        p.lv_rewards[g] = lv_rew;
-        const double succ = (i == hv) ? 1.0 : 0.0;                                    // :579-582
-        p.masks[g] = 1.0 - succ;
-        p.rewards[g] = succ - neg;
-        const int32_t ha = pick_goal<kInject>(p, 2, i, fin, batch_id, r, g, make_uint2(mix.z, mix.w));   // :585-591
-        int32_t ha_next, la_next, unused;
-        subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600
-        subgoal_step(i, fin, ha, p.k_lo, la_next, unused);                            // :613-618
-        const int64_t la = (int64_t)i + p.k_act;                                      // :610
-        put_slot(p, sr, HGC_HA_GOAL, g, ha);
-        put_slot(p, sr, HGC_HA_NEXT, g, ha_next);
-        put_slot(p, sr, HGC_LA_GOAL, g, (int32_t)(la < (int64_t)fin ? la : (int64_t)fin));
-        put_slot(p, sr, HGC_LA_NEXT, g, la_next);
-      }
-    }
-
-    // rows of <= 16 bytes: this thread copies them now (datasets.py:78-83 for the per-transition fields)
-#pragma unroll 1
-    for (int j = 0; j < p.n_tiny; ++j) {
-      const TinyJob& job = p.tiny[j];
-      const int row_bytes = (int)job.n_elem << job.size_log2;
-      const uint8_t* sp = job.src + (size_t)pick_slot(sr, job.slot) * row_bytes;
-      uint8_t* dp = job.dst + (size_t)g * row_bytes;
-      switch (job.size_log2) {
-        case 4: *reinterpret_cast<uint4*>(dp) = __ldg(reinterpret_cast<const uint4*>(sp)); break;
-        case 3:
-          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint2*>(dp)[e] = __ldg(reinterpret_cast<const uint2*>(sp) + e);
-          break;
-        case 2:
-          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
-          break;
-        case 1:
-          for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
-          break;
-        default:
-          for (int e = 0; e < job.n_elem; ++e) dp[e] = __ldg(sp + e);
-          break;
-      }
-    }
-
-    if (p.crop_out != nullptr) {
-      int dy = -128, dx = -128;
-      if (p.aug_mode) {                                                               // :278-279, :621-622
-        double coin;
-        if (kInject) {
-          coin = p.in_coin;
-        } else {
-          const uint4 c = draw4(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
-          coin = unit_double(c.x, c.y);
-        }
-        if (coin < p.p_aug) {                                                         // :333
-          const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
-          const uint32_t joint = __umulhi(w0.z, span * span);            // (cy, cx) jointly uniform on span x span
-          const int cy = kInject ? (int)p.in_crop[2 * g] : (int)(joint / span);
-          const int cx = kInject ? (int)p.in_crop[2 * g + 1] : (int)(joint % span);
-          dy = cy - p.crop_pad;
-          dx = cx - p.crop_pad;
-        }
-      }
-      p.crop_out[2 * g] = (int8_t)dy;
-      p.crop_out[2 * g + 1] = (int8_t)dx;
-    }
+    relabel_row<kInject, kFlavour>(p, g, sr);
   }
 }
 
@@ -468,12 +559,18 @@ __global__ void __launch_bounds__(kRelabelThreads, kGatherMinBlocks) gather_rows
 // in flight.  Here the source rows go HBM -> shared memory with cp.async (LDGSTS, 16 bytes per lane, L1
 // bypassed) into a per-warp ring of kAsyncStages stages, so several KB per warp are in flight without holding
 // registers, and the drain is shared-memory loads + *flat* coalesced stores: the dense output tile of a job is
-// one contiguous span, so lanes store consecutive elements no matter how long a row is.
+// one contiguous span, so lanes store consecutive 16-byte pieces no matter how long a row is.
 // Work item = (warp tile of 32 batch rows, job, sub-range of rows that fits one stage).
+//
+// Both inner loops are written for instruction count (the first version spent 17 integer instructions per memory
+// instruction): the (row, chunk) position of a lane advances incrementally in the issue loop, and the drain turns
+// a dense word index into a stage offset with one multiply-high per word (row = word / words_per_row).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAsyncStages = 3;
 constexpr int kAsyncWarps = 8;
 constexpr int kAsyncMaxStride = 4096;
+
+enum : int { DRAIN_WORDS = 0, DRAIN_DENSE16 = 1, DRAIN_ELEMS = 2 };
 
 struct AsyncJob {
   const uint8_t* src;
@@ -482,11 +579,18 @@ struct AsyncJob {
   uint32_t row_bytes;
   uint32_t cpr;           // 16-byte chunks copied per row = ceil(row_bytes / 16)
   uint32_t cpr_magic;     // ceil(2^32 / cpr), or 0 when cpr == 1: e / cpr == umulhi(e, magic) for e * cpr < 2^32
-  uint32_t epr;           // output elements per row (row_bytes >> vec_log2)
+  uint32_t chunk_step;    // advance of a lane's stage offset per issue iteration: (32 / cpr) * stride + (32 % cpr) * 16
+  uint32_t chunk_wrap;    // extra advance when the chunk index wraps into the next row: stride - cpr * 16
+  uint32_t epr;           // output elements per row: 4-byte words (DRAIN_WORDS) or 1 << vec_log2 bytes (DRAIN_ELEMS)
   uint32_t epr_magic;
+  uint32_t gap;           // stride - row_bytes: padding between two rows in a stage
   uint16_t rows_per_item; // rows of one stage
-  uint8_t vec_log2;
+  uint8_t drain;          // DRAIN_*
+  uint8_t vec_log2;       // DRAIN_ELEMS only
   uint8_t slot;
+  uint8_t chunk_dr;       // 32 / cpr
+  uint8_t chunk_dch;      // 32 % cpr
+  uint8_t pad_;
 };
 
 struct AsyncGatherParams {
@@ -495,8 +599,6 @@ struct AsyncGatherParams {
   int64_t row_begin, row_end;  // row_begin is a multiple of 32
   int32_t n_jobs;
   int32_t stage_bytes;
-  int32_t flat_drain;          // 1: flat element index (coalesced 128-byte stores), 0: row by row
-  int32_t pad_;
   AsyncJob jobs[kMaxRowJobs];
 };
 
@@ -509,7 +611,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __device__ __forceinline__ uint32_t fast_div(uint32_t e, uint32_t magic) { return magic ? __umulhi(e, magic) : e; }
 
-// flat drain: the item's dense output is one contiguous span, lanes store consecutive elements (full 128-byte lines)
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
+}
+
+// generic element drain (rows whose size is not a multiple of 4 bytes): flat element index, coalesced stores
 template <typename V>
 __device__ __forceinline__ void drain_flat(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const uint32_t n_elem,
                                            const uint32_t stride, const uint32_t epr, const uint32_t epr_magic, const int lane) {
@@ -519,178 +628,189 @@ __device__ __forceinline__ void drain_flat(const uint8_t* __restrict__ sbase, ui
   }
 }
 
-// 4-byte elements, the common case (float32 rows whose size is not a multiple of 16): each lane assembles 16
-// consecutive output bytes from four shared-memory words (they straddle at most one row boundary) and issues one
-// 16-byte store, so a warp-wide store covers 512 contiguous bytes of the dense output.
-__device__ __forceinline__ void drain_flat_quads(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const uint32_t n_words,
-                                                 const uint32_t stride, const uint32_t epr, const uint32_t epr_magic, const int lane) {
+// Word rows (float32 observations, actions ...): output word w of the item lives at stage offset 4*w + gap*(w / epr).
+// Each lane assembles 16 consecutive output bytes from four shared words and issues one 16-byte store, so a
+// warp-wide store covers 512 contiguous bytes of the dense output.  `dbase` must be 16-byte aligned.
+__device__ __forceinline__ void drain_words(const uint32_t sbase, uint8_t* __restrict__ dbase, const uint32_t n_words,
+                                            const uint32_t epr_magic, const uint32_t gap, const int lane) {
   const uint32_t n_quads = n_words >> 2;
-  const uint32_t row_gap = stride - epr * 4u;             // padding bytes between two rows in the stage
+#pragma unroll 2
   for (uint32_t q = lane; q < n_quads; q += 32) {
-    const uint32_t w0 = q << 2;
-    const uint32_t r = fast_div(w0, epr_magic);
-    uint32_t col = w0 - r * epr;
-    uint32_t off = r * stride + col * 4u;
-    uint32_t v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = *reinterpret_cast<const uint32_t*>(sbase + off);
-      off += 4u;
-      if (++col == epr) { col = 0; off += row_gap; }
-    }
-    reinterpret_cast<uint4*>(dbase)[q] = make_uint4(v[0], v[1], v[2], v[3]);
+    const uint32_t w = q << 2;
+    const uint32_t a0 = sbase + 4u * w + gap * fast_div(w, epr_magic);
+    const uint32_t a1 = sbase + 4u * w + 4u + gap * fast_div(w + 1u, epr_magic);
+    const uint32_t a2 = sbase + 4u * w + 8u + gap * fast_div(w + 2u, epr_magic);
+    const uint32_t a3 = sbase + 4u * w + 12u + gap * fast_div(w + 3u, epr_magic);
+    const uint32_t v0 = lds32(a0), v1 = lds32(a1), v2 = lds32(a2), v3 = lds32(a3);
+    reinterpret_cast<uint4*>(dbase)[q] = make_uint4(v0, v1, v2, v3);
   }
-  for (uint32_t e = (n_quads << 2) + lane; e < n_words; e += 32) {   // ragged last tile only
-    const uint32_t r = fast_div(e, epr_magic), col = e - r * epr;
-    reinterpret_cast<uint32_t*>(dbase)[e] = *reinterpret_cast<const uint32_t*>(sbase + r * stride + col * 4u);
-  }
+  for (uint32_t w = (n_quads << 2) + lane; w < n_words; w += 32)    // ragged last tile only
+    reinterpret_cast<uint32_t*>(dbase)[w] = lds32(sbase + 4u * w + gap * fast_div(w, epr_magic));
 }
 
-template <typename V>
-__device__ __forceinline__ void drain_rows(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const int rows,
-                                           const uint32_t stride, const uint32_t row_bytes, const uint32_t epr, const int lane) {
-  if (epr <= 32) {
-    const bool ok = (uint32_t)lane < epr;
-    const uint32_t off = (uint32_t)lane * (uint32_t)sizeof(V);
-    int r = 0;
-    for (; r + 4 <= rows; r += 4) {
-      V v[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (ok) v[q] = *reinterpret_cast<const V*>(sbase + (uint32_t)(r + q) * stride + off);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (ok) *reinterpret_cast<V*>(dbase + (uint32_t)(r + q) * row_bytes + off) = v[q];
-    }
-    for (; r < rows; ++r)
-      if (ok) *reinterpret_cast<V*>(dbase + (uint32_t)r * row_bytes + off) = *reinterpret_cast<const V*>(sbase + (uint32_t)r * stride + off);
-  } else {
-    for (int r = 0; r < rows; ++r)
-      for (uint32_t c = lane; c < epr; c += 32)
-        reinterpret_cast<V*>(dbase + (uint32_t)r * row_bytes)[c] = reinterpret_cast<const V*>(sbase + (uint32_t)r * stride)[c];
-  }
+// same layout, 4-byte stores: used when the item's output span does not start on a 16-byte boundary
+__device__ __forceinline__ void drain_words_unaligned(const uint32_t sbase, uint8_t* __restrict__ dbase, const uint32_t n_words,
+                                                      const uint32_t epr_magic, const uint32_t gap, const int lane) {
+  for (uint32_t w = lane; w < n_words; w += 32)
+    reinterpret_cast<uint32_t*>(dbase)[w] = lds32(sbase + 4u * w + gap * fast_div(w, epr_magic));
+}
+
+// rows without padding whose size is a multiple of 16: the stage already holds the dense output span
+__device__ __forceinline__ void drain_dense16(const uint32_t sbase, uint8_t* __restrict__ dbase, const uint32_t n_bytes, const int lane) {
+  const uint32_t n16 = n_bytes >> 4;
+#pragma unroll 2
+  for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dbase)[i] = lds128(sbase + (i << 4));
 }
 
 struct ItemCursor {
-  int64_t wt;   // warp tile
+  int32_t wt;   // warp tile (32 batch rows); a launch holds < 2^31 rows, so tiles fit 32 bits comfortably
   int32_t j;    // job
   int32_t sub;  // first row of the sub-range within the warp tile
+  int32_t n;    // rows of this tile (32 except for the ragged last tile)
 };
 
-__global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
-  extern __shared__ __align__(128) uint8_t smem_ring[];
+// One body, two kernels.  kFused == false: the source rows come from the index vectors an earlier
+// relabel_index_kernel wrote.  kFused == true: the warp computes the index algebra of its 32 batch rows itself
+// (relabel_row, one lane per row) when it enters a tile and keeps the rows of every slot in registers -- sample() is
+// then a single launch.
+// (A TMA variant -- one cp.async.bulk per source row instead of 16-byte LDGSTS chunks -- was measured and dropped:
+// equal on 224/288-byte rows, 17 % slower on 128-byte rows.)
+template <bool kFused, bool kInject, int kFlavour>
+__device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& p, const RelabelParams& rp, uint8_t* smem_ring) {
+  constexpr int kSlots = FlavourSlots<kFlavour>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_global = (int64_t)blockIdx.x * kAsyncWarps + warp;
-  const int64_t n_warps_global = (int64_t)gridDim.x * kAsyncWarps;
-  const int64_t n_warp_tiles = (p.row_end + 31) >> 5;
-  const int64_t first_tile = (p.row_begin >> 5) + warp_global;
-  uint8_t* ring = smem_ring + (size_t)warp * kAsyncStages * p.stage_bytes;
-  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int32_t n_warps_global = (int32_t)gridDim.x * kAsyncWarps;
+  const int32_t n_warp_tiles = (int32_t)((p.row_end + 31) >> 5);
+  const int32_t last_n = (int32_t)(p.row_end - ((int64_t)(n_warp_tiles - 1) << 5));      // rows of the last tile
+  const int32_t first_tile = (int32_t)(p.row_begin >> 5) + (int32_t)blockIdx.x * kAsyncWarps + warp;
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(smem_ring) + (uint32_t)warp * (uint32_t)kAsyncStages * stage_bytes;
+  const int32_t n_jobs = p.n_jobs;
 
+  auto tile_rows = [&](int32_t wt) -> int32_t { return wt == n_warp_tiles - 1 ? last_n : 32; };
   auto advance = [&](ItemCursor& c) {
     c.sub += p.jobs[c.j].rows_per_item;
-    if (c.sub >= 32) {
+    if (c.sub >= c.n) {
       c.sub = 0;
-      if (++c.j == p.n_jobs) { c.j = 0; c.wt += n_warps_global; }
+      if (++c.j == n_jobs) { c.j = 0; c.wt += n_warps_global; c.n = tile_rows(c.wt); }
     }
   };
-  // lane l keeps the source row of batch row (wt*32 + l) for the (tile, job) pair being issued; the vector of the
-  // pair after it is fetched one pair ahead, so its L2/HBM latency is hidden behind a whole job of work
-  auto load_rows = [&](int64_t wt, int j) -> int32_t {
+  // lane l keeps the source row of batch row (wt*32 + l) for the (tile, job) pair being issued
+  int32_t sr[kMaxSlots];                 // kFused: rows of every slot for the tile being issued
+#pragma unroll
+  for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
+  int32_t issue_rows = 0;
+  // !kFused: the vector of the pair after the current one is fetched one pair ahead, so its latency hides behind a job
+  auto load_rows = [&](int32_t wt, int j) -> int32_t {
     if (wt >= n_warp_tiles) return 0;
-    const int64_t g0 = wt << 5;
-    const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
-    return __ldg(p.vec_rows + (int64_t)p.jobs[j].slot * p.total_rows + g0 + min(lane, n - 1));
+    const int n = tile_rows(wt);
+    return __ldg(p.vec_rows + (int64_t)p.jobs[j].slot * p.total_rows + ((int64_t)wt << 5) + min(lane, n - 1));
   };
-  int32_t issue_rows = load_rows(first_tile, 0);
-  int64_t pref_wt = p.n_jobs > 1 ? first_tile : first_tile + n_warps_global;
-  int32_t pref_job = p.n_jobs > 1 ? 1 : 0;
-  int32_t pref_rows = load_rows(pref_wt, pref_job);
-  int64_t issue_rows_wt = first_tile;
-  int32_t issue_rows_job = 0;
+  int32_t pref_rows = 0;
+  if (!kFused) pref_rows = load_rows(first_tile, 0);
 
-  auto issue = [&](const ItemCursor& c, int stage) {
+  auto issue = [&](const ItemCursor& c, const uint32_t stage_u32) {
     if (c.wt < n_warp_tiles) {
       const AsyncJob& job = p.jobs[c.j];
-      const int64_t g0 = c.wt << 5;
-      const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
-      if (issue_rows_wt != c.wt || issue_rows_job != c.j) {   // entering the next pair: rotate the prefetched vector in
-        issue_rows = pref_rows;
-        issue_rows_wt = c.wt;
-        issue_rows_job = c.j;
-        pref_job = c.j + 1 < p.n_jobs ? c.j + 1 : 0;
-        pref_wt = pref_job ? c.wt : c.wt + n_warps_global;
-        pref_rows = load_rows(pref_wt, pref_job);
+      if (c.sub == 0) {                                        // entering the next (tile, job) pair
+        if (kFused) {
+          if (c.j == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, ((int64_t)c.wt << 5) + lane, sr);
+          issue_rows = pick_slot<kSlots>(sr, job.slot);
+        } else {
+          issue_rows = pref_rows;
+          const int nj = c.j + 1 < n_jobs ? c.j + 1 : 0;
+          pref_rows = load_rows(nj ? c.wt : c.wt + n_warps_global, nj);
+        }
       }
-      const int rows = min((int)job.rows_per_item, n - c.sub);     // may be <= 0 for the ragged last tile
-      const uint32_t n_chunks = rows > 0 ? (uint32_t)rows * job.cpr : 0u;
-      const uint32_t base = ring_u32 + (uint32_t)stage * (uint32_t)p.stage_bytes;
-      for (uint32_t e0 = 0; e0 < n_chunks; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        const uint32_t r = min(fast_div(e, job.cpr_magic), (uint32_t)rows - 1);
-        const int32_t src_row = __shfl_sync(0xffffffffu, issue_rows, c.sub + (int)r);
-        if (e < n_chunks) {
-          const uint32_t ch = e - r * job.cpr;
-          cp_async16(base + r * job.stride + (ch << 4), job.src + (size_t)(uint32_t)src_row * job.stride + (ch << 4));
+      const int rows = min((int)job.rows_per_item, c.n - c.sub);
+      const uint32_t cpr = job.cpr, stride = job.stride;
+      const int n_chunks = rows * (int)cpr;
+      // lane -> (row r, chunk ch) of the item; both advance incrementally, no division inside the loop.
+      // Source addresses are formed in 16-byte units (32-bit), so a field must stay below 64 GB (host-checked).
+      uint32_t r = fast_div((uint32_t)lane, job.cpr_magic);
+      uint32_t ch = (uint32_t)lane - r * cpr;
+      uint32_t soff = stage_u32 + r * stride + (ch << 4);
+      const uint32_t stride16 = stride >> 4;
+      const uint32_t dr = job.chunk_dr, dch = job.chunk_dch, step = job.chunk_step;
+      const uint4* __restrict__ src16 = reinterpret_cast<const uint4*>(job.src);
+      r += (uint32_t)c.sub;
+      if (dch == 0) {                                          // chunks per row divide 32: a lane stays on its chunk column
+        src16 += ch;
+#pragma unroll 2
+        for (int e = lane; e - lane < n_chunks; e += 32) {
+          const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, issue_rows, (int)r);
+          if (e < n_chunks) cp_async16(soff, src16 + src_row * stride16);
+          r += dr; soff += step;
+        }
+      } else {
+        const uint32_t wrap = job.chunk_wrap;
+#pragma unroll 2
+        for (int e = lane; e - lane < n_chunks; e += 32) {
+          const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, issue_rows, (int)r);
+          if (e < n_chunks) cp_async16(soff, src16 + (src_row * stride16 + ch));
+          r += dr; ch += dch; soff += step;
+          if (ch >= cpr) { ch -= cpr; ++r; soff += wrap; }
         }
       }
     }
     cp_async_commit();
   };
 
-  auto drain = [&](const ItemCursor& c, int stage) {
+  auto drain = [&](const ItemCursor& c, const uint32_t sbase) {
     const AsyncJob& job = p.jobs[c.j];
-    const int64_t g0 = c.wt << 5;
-    const int n = (int)(p.row_end - g0 < 32 ? p.row_end - g0 : 32);
-    const int rows = min((int)job.rows_per_item, n - c.sub);
-    if (rows <= 0) return;
-    const uint8_t* sbase = ring + (size_t)stage * p.stage_bytes;
-    uint8_t* dbase = job.dst + (size_t)(g0 + c.sub) * job.row_bytes;
-    if (p.flat_drain) {
+    const int rows = min((int)job.rows_per_item, c.n - c.sub);
+    uint8_t* dbase = job.dst + (size_t)(uint32_t)((c.wt << 5) + c.sub) * job.row_bytes;
+    if (job.drain == DRAIN_WORDS) {
+      if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_words(sbase, dbase, (uint32_t)rows * job.epr, job.epr_magic, job.gap, lane);
+      else drain_words_unaligned(sbase, dbase, (uint32_t)rows * job.epr, job.epr_magic, job.gap, lane);
+    } else if (job.drain == DRAIN_DENSE16) {
+      drain_dense16(sbase, dbase, (uint32_t)rows * job.row_bytes, lane);
+    } else {
+      const uint8_t* sgen = smem_ring + (size_t)(sbase - (uint32_t)__cvta_generic_to_shared(smem_ring));
       const uint32_t n_elem = (uint32_t)rows * job.epr;
-      switch (job.vec_log2) {
-        case 4: drain_flat<uint4>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
-        case 3: drain_flat<uint2>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
-        case 2:
-          if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_flat_quads(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
-          else drain_flat<uint32_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
-          break;
-        case 1: drain_flat<uint16_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
-        default: drain_flat<uint8_t>(sbase, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane); break;
-      }
-      return;
-    }
-    // one warp-wide shared load + global store per 32 elements of a row; rows are unrolled by 4 for ILP
-    switch (job.vec_log2) {
-      case 4: drain_rows<uint4>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
-      case 3: drain_rows<uint2>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
-      case 2: drain_rows<uint32_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
-      case 1: drain_rows<uint16_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
-      default: drain_rows<uint8_t>(sbase, dbase, rows, job.stride, job.row_bytes, job.epr, lane); break;
+      if (job.vec_log2 == 1) drain_flat<uint16_t>(sgen, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
+      else drain_flat<uint8_t>(sgen, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
     }
   };
 
-  ItemCursor head{first_tile, 0, 0};  // next item to issue
-  ItemCursor tail{first_tile, 0, 0};  // next item to drain
-  int head_stage = 0, tail_stage = 0;
+  ItemCursor head{first_tile, 0, 0, 32};  // next item to issue
+  if (first_tile < n_warp_tiles) head.n = tile_rows(first_tile);
+  ItemCursor tail = head;                  // next item to drain
+  const uint32_t ring_end = ring_u32 + (uint32_t)kAsyncStages * stage_bytes;
+  uint32_t head_stage = ring_u32, tail_stage = ring_u32;   // shared-memory addresses of the stages
 #pragma unroll 1
-  for (int s = 0; s < kAsyncStages - 1; ++s) {
-    issue(head, head_stage);
+  for (int t = 0; tail.wt < n_warp_tiles; ++t) {
+    issue(head, head_stage);             // one cp.async group per iteration (empty once the head has run off the end)
     if (head.wt < n_warp_tiles) advance(head);
-    head_stage = head_stage + 1 == kAsyncStages ? 0 : head_stage + 1;
+    head_stage += stage_bytes;
+    if (head_stage == ring_end) head_stage = ring_u32;
+    if (t >= kAsyncStages - 1) {
+      cp_async_wait<kAsyncStages - 1>();   // everything but the newest kAsyncStages-1 groups has landed
+      __syncwarp();                        // ... for every lane of this warp
+      drain(tail, tail_stage);
+      __syncwarp();                        // the stage may be overwritten by the next issue
+      advance(tail);
+      tail_stage += stage_bytes;
+      if (tail_stage == ring_end) tail_stage = ring_u32;
+    }
   }
-#pragma unroll 1
-  while (tail.wt < n_warp_tiles) {
-    issue(head, head_stage);
-    if (head.wt < n_warp_tiles) advance(head);
-    head_stage = head_stage + 1 == kAsyncStages ? 0 : head_stage + 1;
-    cp_async_wait<kAsyncStages - 1>();   // everything but the newest kAsyncStages-1 groups has landed
-    __syncwarp();                        // ... for every lane of this warp
-    drain(tail, tail_stage);
-    __syncwarp();                        // the stage may be overwritten by the next issue
-    advance(tail);
-    tail_stage = tail_stage + 1 == kAsyncStages ? 0 : tail_stage + 1;
-  }
+}
+
+__global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
+  extern __shared__ __align__(128) uint8_t smem_ring[];
+  gather_rows_async_body<false, false, FLAVOUR_PLAIN>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_ring);
+}
+
+struct FusedParams {
+  RelabelParams relabel;
+  AsyncGatherParams gather;
+};
+
+// sample() in one launch: index algebra + row gathers (datasets.py:213-294 / :496-643 for vector observations)
+template <bool kInject, int kFlavour>
+__global__ void __launch_bounds__(kAsyncWarps * 32) relabel_gather_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(128) uint8_t smem_ring[];
+  gather_rows_async_body<true, kInject, kFlavour>(p.gather, p.relabel, smem_ring);
 }
 
 }  // namespace ogb

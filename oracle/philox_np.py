@@ -18,7 +18,7 @@ M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
 MASK32 = np.uint64(0xFFFFFFFF)
 
-PURPOSE_IDX, PURPOSE_GOAL, PURPOSE_MIX, PURPOSE_MIX_LOW, PURPOSE_COIN = 0, 1, 4, 5, 7
+PURPOSE_IDX, PURPOSE_GOAL, PURPOSE_GOAL_LOW, PURPOSE_CROP, PURPOSE_MIX, PURPOSE_TRL_MID, PURPOSE_COIN = 0, 1, 2, 3, 4, 6, 7
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -71,37 +71,45 @@ def geometric_is_knife_edge(u, discount, tol=1e-9):
 def philox_draws(seed, stream, batch_index, batch_size, n_choices, goal_sets, aug, p_aug, padding=3, idxs_given=False):
     """Draws of one device sample() call.
 
-    goal_sets: list of (slot, geom, discount, cur_only) with slot 0 = value, 1 = low-value, 2 = actor -- the same
-    slots the kernel uses for the purpose ids.  aug: whether the per-batch coin is drawn at all.
+    goal_sets: list of (slot, geom, discount, cur_only) with slot 0 = value, 1 = low-value, 2 = actor.  aug: whether
+    the per-batch coin is drawn at all.  Word layout (device_common.cuh, enum Purpose): a goal set owns 64 random bits
+    that serve either as its random-goal position or as its geometric / distance uniform -- the mix coins decide
+    which one the sampler looks at, so building both from the same bits here is equivalent.
     """
     rows = np.arange(batch_size, dtype=np.uint64)
     d = Draws()
-    w = draw4(seed, stream, batch_index, rows, PURPOSE_IDX)
+    w = draw4(seed, stream, batch_index, rows, PURPOSE_IDX)            # x,y: index position; z,w: value mix coins
     if not idxs_given:
         d.idx_pos = bounded_u64(w[0], w[1], n_choices)
     knife = np.zeros(batch_size, dtype=bool)
-    mix = draw4(seed, stream, batch_index, rows, PURPOSE_MIX)          # value (x, y) and actor (z, w) mix uniforms
-    mix_low = draw4(seed, stream, batch_index, rows, PURPOSE_MIX_LOW)
+    gb = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL)          # x,y: value goal bits; z,w: actor goal bits
+    low = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL_LOW)     # x,y: low-value goal bits; z,w: its mix coins
+    amix = draw4(seed, stream, batch_index, rows, PURPOSE_MIX)         # x,y: actor mix coins
     two32 = 4294967296.0
+    bits_of = {0: (gb[0], gb[1]), 1: (low[0], low[1]), 2: (gb[2], gb[3])}
+    coins_of = {0: (w[2], w[3]), 1: (low[2], low[3]), 2: (amix[0], amix[1])}
     for slot, geom, discount, cur_only in goal_sets:
-        a = draw4(seed, stream, batch_index, rows, PURPOSE_GOAL + slot)
-        g = GoalDraws(rand_pos=bounded_u64(a[0], a[1], n_choices))
-        u = unit_double(a[2], a[3])
+        a0, a1 = bits_of[slot]
+        g = GoalDraws(rand_pos=bounded_u64(a0, a1, n_choices))
+        u = unit_double(a0, a1)
         if geom:
             g.offset = geometric_from_unit(u, discount)
             knife |= geometric_is_knife_edge(u, discount)
         else:
             g.dist = u
         if not cur_only:
-            words = {0: (mix[0], mix[1]), 1: (mix_low[0], mix_low[1]), 2: (mix[2], mix[3])}[slot]
-            g.u_traj = words[0].astype(np.float64) / two32
-            g.u_cur = words[1].astype(np.float64) / two32
+            # when the actor mix is not a real choice the device skips PURPOSE_MIX; the coins then cannot change the
+            # outcome, so the values used here are immaterial
+            c0, c1 = coins_of[slot]
+            g.u_traj = c0.astype(np.float64) / two32
+            g.u_cur = c1.astype(np.float64) / two32
         d.goals.append(g)
     if aug:
         c = draw4(seed, stream, batch_index, np.array([0xFFFFFFFF], dtype=np.uint64), PURPOSE_COIN)
         d.aug_coin = float(unit_double(c[0], c[1])[0])
         if d.aug_coin < p_aug:
             span = np.uint64(2 * padding + 1)
-            joint = (w[2] * span * span) >> np.uint64(32)                 # (cy, cx) jointly uniform on span x span
+            cw = draw4(seed, stream, batch_index, rows, PURPOSE_CROP)
+            joint = (cw[0] * span * span) >> np.uint64(32)                # (cy, cx) jointly uniform on span x span
             d.crop = np.stack([joint // span, joint % span], axis=1).astype(np.int64)
     return d, knife

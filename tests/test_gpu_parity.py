@@ -77,6 +77,56 @@ def test_oracle_sweep(spec):
         assert_batches_identical(got, want, label=f'{spec}/{it}:')
 
 
+LONG = [
+    ('gc', (29,), None, {}),
+    ('gc', (2,), None, dict(value_geom_sample=False, actor_geom_sample=True, actor_p_curgoal=0.2, actor_p_trajgoal=0.3, actor_p_randomgoal=0.5)),
+    ('hgc', (11,), None, dict(subgoal_steps=7, discount=0.995)),
+    ('hgc', (6,), None, dict(subgoal_steps=9, low_discount=0.95, low_subgoal_steps=2)),
+    ('gc', (7,), 3, {}),
+]
+
+
+@pytest.mark.parametrize('spec', LONG, ids=[f"{s[0]}-{s[1][0]}-fs{s[2]}-{i}" for i, s in enumerate(LONG)])
+@pytest.mark.parametrize('layout', ['compact', 'early_terminals', 'extra_invalid'])
+def test_oracle_sweep_long_trajectories(spec, layout):
+    """Trajectories of 18+ rows take the one-probe segment table (valid row and final state from one lookup,
+    relabel_rows.cuh valid_row_fast); 'early_terminals' puts extra terminals inside trajectories, so the table has to
+    be refused and the general searches used; 'extra_invalid' adds invalid rows in the middle of trajectories."""
+    kind, obs_shape, fs, over = spec
+    seed = abs(hash(str(spec) + layout)) % 1000
+    lengths = ragged(seed, 150, 18, 90)
+    fields = toy_fields(seed, lengths, obs_shape, 5, np.float32)
+    rng = np.random.default_rng(seed)
+    if layout == 'early_terminals':
+        extra = rng.choice(len(fields['terminals']), size=40, replace=False)
+        fields['terminals'] = fields['terminals'].copy()
+        fields['terminals'][extra] = 1.0
+    elif layout == 'extra_invalid':
+        starts = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+        fields['valids'] = fields['valids'].copy()
+        fields['valids'][starts[::3] + 8] = 0.0          # far from every other invalid row: the table stays usable
+    config = cfg(frame_stack=fs, **over)
+    sampler = device_sampler(fields, config, kind, rng='numpy', output='numpy')
+    for it, evaluation in enumerate([False, True, False]):
+        np.random.seed(seed * 10 + it)
+        _, want = oracle_with_draws(fields, config, kind, 1024, evaluation=evaluation)
+        np.random.seed(seed * 10 + it)
+        got = sampler.sample(1024, evaluation=evaluation)
+        assert_batches_identical(got, want, label=f'{spec}/{layout}/{it}:')
+    # the on-device RNG mode must agree with the oracle fed the restated Philox draws on these layouts too
+    from oracle import philox_np
+    from oracle.replay_oracle import DrawsSource, OracleSampler
+    from tests.test_gpu_philox import goal_sets_for
+
+    dev = device_sampler(fields, config, kind, seed=77, stream_id=3)
+    oracle = OracleSampler(fields, config, kind)
+    got = to_host(dev.sample(512))
+    draws, knife = philox_np.philox_draws(77, 3, 0, 512, len(oracle.valid_table), goal_sets_for(config, kind), True, 0.0)
+    want = oracle.sample(512, source=DrawsSource(draws))
+    for k in want:
+        assert np.array_equal(got[k][~knife], want[k][~knife]), (k, layout)
+
+
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')
     sampler = device_sampler(case['fields'], case['cfg'], 'hgc')

@@ -34,6 +34,17 @@ def test_philox_words_match_numpy():
             assert np.array_equal(out[:, k].astype(np.uint64), want[k]), (seed, k)
 
 
+@pytest.mark.parametrize('discount', [0.9, 0.99, 0.995, 0.999, 0.9999])
+def test_geometric_fast_path_equals_float64_expression(discount):
+    """The float32 estimate of ceil(log(1-U)/log(discount)) must never decide differently from the float64
+    expression it replaces (it falls back to float64 whenever its error bound reaches an integer boundary)."""
+    from ogbench_b200 import _native
+
+    bad = C.c_int64(-1)
+    _native.check(_native.lib().ogb_geometric_check(discount, 2024, 1 << 27, 0, C.byref(bad)))
+    assert bad.value == 0
+
+
 CASES = [
     ('gc', (29,), None, {}, np.float32),
     ('gc', (3,), None, dict(value_geom_sample=False, actor_geom_sample=True, actor_p_curgoal=0.2, actor_p_trajgoal=0.3,
