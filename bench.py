@@ -203,8 +203,9 @@ class ClockSampler(threading.Thread):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 def default_batches_per_launch(w):
-    # ~1M transitions per launch for vector workloads (output >> L2), 8 batches for the pixel workload (~0.55 GB)
-    return 8 if w.obs_dtype == 'uint8' else max(1, (1 << 20) // w.batch)
+    # ~1M transitions per launch for vector workloads, 16 batches for the pixel workload: ~1.1 GB of output per launch
+    # in both cases (>> 126 MB L2)
+    return 16 if w.obs_dtype == 'uint8' else max(1, (1 << 20) // w.batch)
 
 
 def run_gpu_arm(args):
@@ -231,6 +232,7 @@ def run_gpu_arm(args):
     stream = torch.cuda.Stream(device=local)
     sampler._sampler.set_stream(stream.cuda_stream)
     lib = _native.lib()
+    _native.check(lib.ogb_sampler_set_profile(sampler._sampler.ptr, 1))   # CUDA events around the dominant kernel of each launch
 
     def barrier():
         dist_util.barrier()
@@ -243,32 +245,50 @@ def run_gpu_arm(args):
         return handle, n.value
 
     # ---- device-resident throughput ----
-    prev = None
-    for _ in range(max(args.warmup, 3)):
-        h, _ = launch()
-        prev = h  # same hand-over pattern as the timed loop, so both recycled output blocks exist before timing
+    launches = 0
+    dominant_ms = []
+    dominant_name = C.c_char_p()
+
+    def harvest(handle, keep):
+        # device time of the launch's dominant kernel, from the events the library recorded on its own streams
+        ms = C.c_float()
+        _native.check(lib.ogb_batch_dominant_kernel(handle.ptr, C.byref(dominant_name), C.byref(ms)))
+        if keep and ms.value >= 0:
+            dominant_ms.append(ms.value)
+
+    def run(n_steps, keep):
+        # Up to three batches are alive at any time (the consumer holds two while the next is produced); a handle is
+        # harvested two launches after its own, when its kernels have long finished, and dropping it recycles its block.
+        nonlocal launches
+        pending = []
+        for _ in range(n_steps):
+            h, n = launch()
+            launches += n if keep else 0
+            pending.append(h)
+            if len(pending) > 2:
+                harvest(pending.pop(0), keep)
+        return pending
+
+    tail = run(max(args.warmup, 3) + 2, False)   # same hand-over pattern as the timed loop: every recycled block exists
+    del tail
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
-    per_launch = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches = 0
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for a, b in per_launch:
-            a.record(stream)
-            h, n = launch()
-            b.record(stream)
-            launches += n
-            prev = h  # dropping the previous handle returns its block to the stream-ordered pool
+        tail = run(args.steps, True)
         ev1.record(stream)
     barrier()
     clocks.stop_flag.set()
     clocks.join()
-    del prev
+    for h in tail:
+        harvest(h, True)
+    del tail
     elapsed_ms = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in per_launch]))
+    kernel_ms = float(np.mean(dominant_ms)) if dominant_ms else elapsed_ms / args.steps
+    kernel_name = (dominant_name.value or b'').decode()
     elapsed_ms = dist_util.reduce_scalar(elapsed_ms, 'max', device=f'cuda:{local}')   # slowest rank
     per_step = w.batch * L
     value = dist_util.reduce_scalar(args.steps * per_step, 'sum', device=f'cuda:{local}') / (elapsed_ms * 1e-3)
@@ -311,11 +331,15 @@ def run_gpu_arm(args):
 
     peak, peak_src = hbm_peak()
     achieved = w.bytes_per_transition * per_step / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json),
+    # scaled to this run's launch size when the capture used another batches_per_launch
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(args.config, {}).get(str(L))
+            entry = json.load(open(tpath)).get(args.config)
+            if entry and entry.get('kernel', '').find(kernel_name) >= 0:
+                traffic = float(entry['dram_bytes_per_launch']) * per_step / float(entry.get('transitions_per_launch', per_step))
         except Exception:
             traffic = None
     line = {
@@ -330,8 +354,11 @@ def run_gpu_arm(args):
                   f'and gathers from a {dataset.native(local).resident_bytes() / 1e6:.0f} MB resident dataset',
         },
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'kernel': 'relabel_rows_kernel' if w.obs_dtype != 'uint8' else 'gather_frames_tma_kernel',
-                     'kernel_ms': kernel_ms, 'bytes_per_transition': w.bytes_per_transition, 'peak_source': peak_src},
+                     'kernel': kernel_name, 'kernel_ms': kernel_ms, 'bytes_per_transition': w.bytes_per_transition,
+                     'bytes_per_launch': w.bytes_per_transition * per_step, 'peak_source': peak_src,
+                     'step_frac': w.bytes_per_transition * per_step / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
+                     'note': 'achieved = algorithmic bytes of one launch / device time of the dominant kernel (CUDA events on its '
+                             'stream); step_frac = the same bytes / whole step time (index kernel and launch gaps included)'},
         'clocks': clocks.summary(),
         'gpu_launches': launches,
     }

@@ -130,6 +130,7 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
                        ogb_sampler** out);
 int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream);    /* launch on the caller's stream instead */
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep_index_vectors);
+int ogb_sampler_set_profile(ogb_sampler* s, int32_t on);          /* record CUDA events around the dominant kernel of each call */
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out);   /* len(dataset.valid_idxs) as this sampler sees it (TRL overrides it) */
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out);
 /* ReplayBuffer.add_transition (datasets.py:134-142): write one row of every field (host pointers in field order,
@@ -163,6 +164,8 @@ int ogb_batch_num_keys(const ogb_batch* b, int32_t* out);
 int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out);
 int ogb_batch_nbytes(const ogb_batch* b, size_t* out);            /* size of the single device block */
 int ogb_batch_launches(const ogb_batch* b, int32_t* out);         /* kernels launched to produce it */
+int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms); /* the kernel that moved the batch's bytes and, in
+                                                                     profile mode, its device time (host-waits for it); else -1 */
 int ogb_batch_sync(ogb_batch* b);                                 /* host-wait for the batch to be ready */
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream);/* make a consumer stream wait (DLPack protocol) */
 int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return */

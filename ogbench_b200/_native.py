@@ -83,6 +83,7 @@ SIGNATURES = [
     ('ogb_sampler_create', C.c_int, [_P, C.POINTER(Config), C.c_int32, C.c_uint64, C.c_uint32, C.POINTER(_P)]),
     ('ogb_sampler_set_stream', C.c_int, [_P, _P]),
     ('ogb_sampler_set_debug', C.c_int, [_P, C.c_int32]),
+    ('ogb_sampler_set_profile', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_num_choices', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_num_terminals', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_write_row', C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.c_int32]),
@@ -99,6 +100,7 @@ SIGNATURES = [
     ('ogb_batch_key_info', C.c_int, [_P, C.c_int32, C.POINTER(KeyInfo)]),
     ('ogb_batch_nbytes', C.c_int, [_P, C.POINTER(C.c_size_t)]),
     ('ogb_batch_launches', C.c_int, [_P, C.POINTER(C.c_int32)]),
+    ('ogb_batch_dominant_kernel', C.c_int, [_P, _P, _P]),
     ('ogb_batch_sync', C.c_int, [_P]),
     ('ogb_batch_wait_on_stream', C.c_int, [_P, _P]),
     ('ogb_batch_copy_to_host', C.c_int, [_P, _P, C.c_size_t]),

@@ -247,6 +247,7 @@ struct ogb_sampler {
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
   bool debug = false;
+  bool profile = false;                  // record timing events around the dominant kernel of every call
   // trajectory tables
   std::vector<int32_t> term_host;
   int32_t* d_term = nullptr;
@@ -298,6 +299,8 @@ struct ogb_batch {
   int8_t* crop = nullptr;
   int n_slots = 0;
   int launches = 0;
+  cudaEvent_t prof_begin = nullptr, prof_end = nullptr;   // profile mode: brackets of the dominant kernel
+  const char* dominant = "";                               // its name
   cudaEvent_t ready = nullptr;
   std::vector<cudaStream_t> consumers;
   bool main_stream_consumer = false;  // somebody took the batch on the sampler's own stream
@@ -426,6 +429,8 @@ void batch_unref(ogb_batch* b) {
     cudaStreamSynchronize(s->stream);
     if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
   }
+  if (b->prof_begin) cudaEventDestroy(b->prof_begin);
+  if (b->prof_end) cudaEventDestroy(b->prof_end);
   if (b->escaped) cudaDeviceSynchronize();
   if (b->main_stream_consumer) b->consumers.push_back(s->stream);
   for (cudaStream_t c : b->consumers) {
@@ -942,6 +947,11 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
   s->owns_stream = false;
   return 0;
 }
+int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  s->profile = on != 0;
+  return 0;
+}
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->debug = keep != 0;
@@ -1032,9 +1042,14 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   if (total > (int64_t)1 << 31) return fail(OGB_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
   const bool stacked_next = (cfg.frame_stack > 0 && spec.kind != OGB_KIND_PLAIN) || spec.kind == OGB_KIND_ATC;
   if (idxs) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
-    for (int64_t r = 0; r < total; ++r)
-      if (idxs[r] < 0 || idxs[r] >= ds->size || (stacked_next && idxs[r] + spec.next_offset >= ds->size))
-        return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
+    // branch-free scan (vectorises): idx < 0 or idx > last sets the sign bit of idx | (last - idx)
+    const int64_t last = (stacked_next ? ds->size - spec.next_offset : ds->size) - 1;
+    int64_t bad = 0;
+    for (int64_t r = 0; r < total; ++r) bad |= idxs[r] | (last - idxs[r]);
+    if (bad < 0)
+      for (int64_t r = 0; r < total; ++r)
+        if (idxs[r] < 0 || idxs[r] > last)
+          return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
   }
   const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->active_rows : ds->n_valid);
   if (n_choices < 1) return fail(OGB_ERR_INVALID, "nothing to sample from: the dataset holds no rows yet");
@@ -1118,11 +1133,16 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   };
   // When some key goes through the cp.async row gather, the index algebra is fused into that launch (one kernel per
   // sample() for vector observations); otherwise the index kernel runs on its own.
+  // Measured on B200 (c2/c3/c5 shapes): for launches of ~1M rows the split form is as fast or faster (the fused warps
+  // serialise their own index latency), for small launches the saved kernel launch wins.  OGB_FUSE=0/1 forces either.
+  static const char* fuse_env = getenv("OGB_FUSE");
   bool fuse = false;
-  if (!no_fuse)
+  if (!no_fuse && (fuse_env ? atoi(fuse_env) != 0 : (total < kOverlapMinRows && !any_frames)))
     for (const KeyPlan& k : plan)
       if (k.route == ROUTE_ROW && k.alias_of < 0 && takes_async_path(ds->fields[(size_t)k.field])) fuse = true;
-  const bool use_aux = !fuse && !no_overlap && total >= kOverlapMinRows;
+  // Image batches are few rows with long gathers: their (latency-bound) index kernel always goes to the auxiliary
+  // stream, where it runs under the frame gathers of the previous call.
+  const bool use_aux = !fuse && !no_overlap && (total >= kOverlapMinRows || any_frames);
   if (use_aux) {
     int rc = ensure_aux(s);
     if (rc) return bail(rc);
@@ -1543,8 +1563,15 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       g_timeline.push_back(ev);
     };
     stamp(first);
+    const bool prof_first = s->profile && (fused_launch || gather_launches.empty());
+    if (prof_first) {
+      cudaEventCreate(&b->prof_begin);
+      cudaEventCreate(&b->prof_end);
+      cudaEventRecord(b->prof_begin, first);
+    }
     int rc = fused_launch ? fused_launch(0, total, first) : index_launch(0, total, first);
     if (rc) return bail(rc);
+    if (prof_first) cudaEventRecord(b->prof_end, first);
     stamp(first);
     if (first != s->stream) {
       cudaEvent_t ev = s->chunk_events[s->next_event];
@@ -1553,8 +1580,19 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         return bail(fail(OGB_ERR_CUDA, "stream join failed"));
     }
     stamp(s->stream);
+    // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
+    // else the index kernel itself (datasets whose rows are all <= 16 bytes)
+    b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather_kernel"
+                : !async_keys.empty() ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
+    const bool prof_gathers = s->profile && !gather_launches.empty() && !fused_launch;
+    if (prof_gathers) {
+      cudaEventCreate(&b->prof_begin);
+      cudaEventCreate(&b->prof_end);
+      cudaEventRecord(b->prof_begin, s->stream);
+    }
     for (size_t q = 0; q < gather_launches.size() && !rc; ++q) rc = gather_launches[q](0, total, s->stream);
     if (rc) return bail(rc);
+    if (prof_gathers) cudaEventRecord(b->prof_end, s->stream);
     stamp(s->stream);
   }
   if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
@@ -1702,6 +1740,16 @@ int ogb_batch_nbytes(const ogb_batch* b, size_t* out) {
 int ogb_batch_launches(const ogb_batch* b, int32_t* out) {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->launches;
+  return 0;
+}
+int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) {
+  if (!b || !name || !ms) return fail(OGB_ERR_INVALID, "null argument");
+  *name = b->dominant;
+  *ms = -1.0f;
+  if (b->prof_begin && b->prof_end) {
+    OGB_CUDA(cudaEventSynchronize(b->prof_end));
+    OGB_CUDA(cudaEventElapsedTime(ms, b->prof_begin, b->prof_end));
+  }
   return 0;
 }
 int ogb_batch_sync(ogb_batch* b) {

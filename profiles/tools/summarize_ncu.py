@@ -59,7 +59,14 @@ def main():
             if dominant is None or us > dominant[1]:
                 dominant = (r[ik], us, rd + wr)
         open(os.path.join(ROOT, 'profiles', f'{tag}_{cfg}_ncu_summary.txt'), 'w').write('\n'.join(lines) + '\n')
-        traffic[cfg] = {'kernel': dominant[0], 'dram_bytes_per_launch': dominant[2], 'duration_us_under_ncu': dominant[1], 'source': os.path.basename(rep)}
+        sys.path.insert(0, ROOT)
+        import bench
+        from ogbench_b200 import synthetic
+        w = synthetic.WORKLOADS[cfg]
+        traffic[cfg] = {'kernel': dominant[0], 'dram_bytes_per_launch': dominant[2], 'duration_us_under_ncu': dominant[1],
+                        'transitions_per_launch': w.batch * bench.default_batches_per_launch(w),
+                        'algorithmic_bytes_per_launch': w.bytes_per_transition * w.batch * bench.default_batches_per_launch(w),
+                        'source': os.path.basename(rep)}
         print(cfg, dominant)
     json.dump(traffic, open(tpath, 'w'), indent=1)
 
