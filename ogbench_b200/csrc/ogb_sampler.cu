@@ -95,6 +95,8 @@ struct Field {
   size_t row_bytes = 0;
   size_t stride = 0;
   uint8_t* dptr = nullptr;
+  bool in_record = false;  // dptr points into the dataset's packed record table (stride = record stride)
+  size_t rec_off = 0;      // byte offset of this field inside a record
 };
 
 int shift_for(int64_t key_range, int64_t table_len) {
@@ -224,6 +226,8 @@ struct ogb_dataset {
   int32_t* d_gap_bucket = nullptr;
   int gap_shift = 0;
   std::vector<int32_t> gaps_host;       // c[m] of valid_mode 2, kept for the sampler's segment table
+  uint8_t* record_base = nullptr;       // packed record table: one record per row holding every small field
+  size_t record_stride = 0;
   std::vector<uint8_t> terminals_host;  // terminals > 0, one byte per row (tiny next to the data)
   std::vector<uint8_t> valid_host;      // valids > 0 (empty when the dataset has no 'valids')
   size_t resident_bytes = 0;
@@ -386,7 +390,8 @@ void block_give(ogb_sampler* s, uint8_t* block, size_t bytes, std::vector<cudaEv
 void dataset_unref(ogb_dataset* ds) {
   if (ds->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(ds->device);
-  for (auto& f : ds->fields) if (f.dptr) cudaFree(f.dptr);
+  for (auto& f : ds->fields) if (f.dptr && !f.in_record) cudaFree(f.dptr);
+  if (ds->record_base) cudaFree(ds->record_base);
   if (ds->d_valid_table) cudaFree(ds->d_valid_table);
   if (ds->d_gap_c) cudaFree(ds->d_gap_c);
   if (ds->d_gap_bucket) cudaFree(ds->d_gap_bucket);
@@ -733,6 +738,16 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   ds->size = size;
   ds->active_rows = size;
 
+  // ---- resident layout ----
+  // Every field whose row is at most kRecordMaxRow bytes lives in ONE packed record per dataset row:
+  //   [observations | other fields ...], sub-fields of more than 16 bytes on 16-byte offsets (cp.async sources), smaller
+  //   ones on their natural alignment, the record padded to 32, 64 or a multiple of 128 bytes.
+  // DRAM moves 64-byte granules, so a transition's own fields (observation, action, terminal, valid: datasets.py:78-83
+  // gathers them all at the same row) then cost one aligned span instead of one granule each, and a goal row costs
+  // ceil(obs_bytes / 64) granules.  Larger rows (image frames) keep an array of their own.
+  constexpr size_t kRecordMaxRow = 2048, kRecordMaxBytes = 4096;
+  static const bool no_records = getenv("OGB_NO_RECORDS") != nullptr;
+  std::vector<int> order;
   for (int i = 0; i < n_fields; ++i) {
     const ogb_field& in = fields[i];
     Field f;
@@ -747,19 +762,73 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
     }
     f.row_bytes = row;
     if (row == 0) return bail(fail(OGB_ERR_INVALID, "field '%s' has empty rows", in.name));
-    // resident row stride: rows <= 16 B stay dense (they are copied by the index kernel, one thread per row);
-    // longer rows start on a 32-byte sector boundary, which also makes them 16-byte cp.async sources
+    if (row > 0xFFFFFFF0ull) return bail(fail(OGB_ERR_UNSUPPORTED, "field '%s': row too large", in.name));
+    // a field outside the record: rows <= 16 B stay dense, longer rows start on a 32-byte sector boundary
     f.stride = row <= 16 ? row : round_up(row, 32);
-    if (f.stride > 0xFFFFFFFFull) return bail(fail(OGB_ERR_UNSUPPORTED, "field '%s': row too large", in.name));
-    const size_t dense_bytes = (size_t)size * row, padded_bytes = (size_t)size * f.stride;
-    cudaError_t e = cudaMalloc((void**)&f.dptr, padded_bytes);
-    if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for field '%s': %s", padded_bytes, in.name, cudaGetErrorString(e)));
     ds->fields.push_back(f);
-    ds->resident_bytes += padded_bytes;
+    if (!no_records && row <= kRecordMaxRow) order.push_back(i);
+  }
+  {
+    auto align_of = [](const Field& f) -> size_t {
+      if (f.row_bytes > 16) return 16;
+      size_t a = 16;
+      while (f.row_bytes % a != 0) a >>= 1;
+      return a;
+    };
+    // observations first (goal gathers read a prefix of the record), then by decreasing alignment
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      const bool oa = ds->fields[(size_t)a].name == "observations", ob = ds->fields[(size_t)b].name == "observations";
+      if (oa != ob) return oa;
+      return align_of(ds->fields[(size_t)a]) > align_of(ds->fields[(size_t)b]);
+    });
+    size_t cursor = 0;
+    std::vector<int> packed;
+    for (int i : order) {
+      Field& f = ds->fields[(size_t)i];
+      const size_t off = round_up(cursor, align_of(f));
+      if (off + f.row_bytes > kRecordMaxBytes) continue;      // does not fit any more: keeps its own array
+      f.rec_off = off;
+      f.in_record = true;
+      cursor = off + f.row_bytes;
+      packed.push_back(i);
+    }
+    if (packed.size() < 2) {                                   // nothing to share a record with
+      for (int i : packed) ds->fields[(size_t)i].in_record = false;
+    } else {
+      // 32- and 64-byte records stay sector / granule sized; longer ones are padded to whole 128-byte L2 lines, so that a
+      // goal row (a prefix of the record) never straddles a line (measured on the 156-byte C2 record: stride 256 is
+      // 8 % faster than 160 or 192 and 3 % faster than separate arrays)
+      static const int env_align = getenv("OGB_RECORD_ALIGN") ? atoi(getenv("OGB_RECORD_ALIGN")) : 0;
+      ds->record_stride = cursor <= 32 ? 32 : cursor <= 64 ? 64 : round_up(cursor, env_align >= 32 ? (size_t)env_align : 128);
+      const size_t bytes = (size_t)size * ds->record_stride;
+      cudaError_t e = cudaMalloc((void**)&ds->record_base, bytes);
+      if (e == cudaSuccess) e = cudaMemset(ds->record_base, 0, bytes);
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for the record table: %s", bytes, cudaGetErrorString(e)));
+      ds->resident_bytes += bytes;
+      for (int i : packed) {
+        Field& f = ds->fields[(size_t)i];
+        f.dptr = ds->record_base + f.rec_off;
+        f.stride = ds->record_stride;
+      }
+    }
+  }
+  for (int i = 0; i < n_fields; ++i) {
+    const ogb_field& in = fields[i];
+    Field& f = ds->fields[(size_t)i];
+    const size_t row = f.row_bytes;
+    const size_t dense_bytes = (size_t)size * row, padded_bytes = (size_t)size * f.stride;
+    cudaError_t e = cudaSuccess;
+    if (!f.in_record) {
+      e = cudaMalloc((void**)&f.dptr, padded_bytes);
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "cudaMalloc(%zu) for field '%s': %s", padded_bytes, in.name, cudaGetErrorString(e)));
+      ds->resident_bytes += padded_bytes;
+    }
     const cudaMemcpyKind kind = in.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (in.on_device == 2) {  // zero-filled buffer (ReplayBuffer.create, datasets.py:101-103)
-      e = cudaMemset(f.dptr, 0, padded_bytes);
-      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "memset of field '%s': %s", in.name, cudaGetErrorString(e)));
+      if (!f.in_record) {     // (the record table is zero-filled as a whole)
+        e = cudaMemset(f.dptr, 0, padded_bytes);
+        if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "memset of field '%s': %s", in.name, cudaGetErrorString(e)));
+      }
     } else if (f.stride == row) {
       e = cudaMemcpy(f.dptr, in.data, dense_bytes, kind);
       if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "upload of field '%s': %s", in.name, cudaGetErrorString(e)));
@@ -772,7 +841,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
         if (e != cudaSuccess) { if (staging) cudaFree(staging); return bail(fail(OGB_ERR_CUDA, "staging of field '%s': %s", in.name, cudaGetErrorString(e))); }
         dense = staging;
       }
-      cudaMemset(f.dptr, 0, padded_bytes);
+      if (!f.in_record) cudaMemset(f.dptr, 0, padded_bytes);
       const int v = std::min(2, largest_vec_log2(row, 16));
       repad_rows_kernel<<<ds->sm_count * 8, 256>>>(dense, f.dptr, size, (uint32_t)row, (uint32_t)f.stride, v);
       e = cudaDeviceSynchronize();
@@ -789,10 +858,9 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
 
   auto host_copy_1d = [&](int fi, std::vector<uint8_t>* flags) -> int {
     const Field& f = ds->fields[fi];
-    std::vector<uint8_t> raw((size_t)size * f.row_bytes);
-    if (f.stride != f.row_bytes) return fail(OGB_ERR_UNSUPPORTED, "field '%s' must be one value per row", f.name.c_str());
-    OGB_CUDA(cudaMemcpy(raw.data(), f.dptr, raw.size(), cudaMemcpyDeviceToHost));
     if (f.row_bytes != f.itemsize) return fail(OGB_ERR_UNSUPPORTED, "field '%s' must be one value per row", f.name.c_str());
+    std::vector<uint8_t> raw((size_t)size * f.row_bytes);
+    OGB_CUDA(cudaMemcpy2D(raw.data(), f.row_bytes, f.dptr, f.stride, f.row_bytes, (size_t)size, cudaMemcpyDeviceToHost));
     flags->resize((size_t)size);
     for (int64_t r = 0; r < size; ++r) (*flags)[(size_t)r] = positive_at(raw.data(), f.dtype, r) ? 1 : 0;
     return 0;
@@ -1281,31 +1349,85 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     }
   }
   // ---- classify the vector-valued keys: tiny rows ride along in the index kernel, the rest go to a gather launch ----
-  std::vector<size_t> async_keys, lsu_keys;
+  // A span job loads one contiguous piece of the source rows named by one index vector and feeds one output per key.
+  // Fields of the packed record table that are gathered through the same index vector and lie next to each other
+  // (observations, actions, terminals, valids of the sampled transition) share ONE span.
+  struct SpanJob {
+    int slot;
+    const uint8_t* src;            // 16-byte aligned start of the span in row 0
+    size_t stride, bytes;          // source row stride, span length (multiple of 16)
+    std::vector<std::pair<size_t, size_t>> outs;   // (plan index, offset of the field inside the span)
+  };
+  std::vector<SpanJob> span_jobs;
+  std::vector<size_t> lsu_keys;
   p.n_tiny = 0;
   {
+    auto add_tiny = [&](size_t i) -> bool {
+      const Field& f = ds->fields[(size_t)plan[i].field];
+      if (f.row_bytes > 16 || p.n_tiny >= kMaxTinyJobs) return false;
+      TinyJob& t = p.tiny[p.n_tiny++];
+      const int v = largest_vec_log2(f.row_bytes, f.row_bytes);
+      t.src = f.dptr;
+      t.dst = base + b->offsets[i];
+      t.slot = (uint8_t)plan[i].slot;
+      t.size_log2 = (uint8_t)v;
+      t.n_elem = (uint8_t)(f.row_bytes >> v);
+      t.row_bytes = (uint8_t)f.row_bytes;
+      t.stride = (uint16_t)f.stride;
+      return true;
+    };
+    std::map<int, std::vector<size_t>> record_keys;   // slot -> keys whose field lives in the record table
     for (size_t i = 0; i < plan.size(); ++i) {
       if (plan[i].route != ROUTE_ROW || plan[i].alias_of >= 0) continue;
       const Field& f = ds->fields[(size_t)plan[i].field];
-      if (f.row_bytes <= 16 && p.n_tiny < kMaxTinyJobs) {
-        TinyJob& t = p.tiny[p.n_tiny++];
-        const int v = largest_vec_log2(f.row_bytes, f.row_bytes);
-        t.src = f.dptr;
-        t.dst = base + b->offsets[i];
-        t.slot = (uint8_t)plan[i].slot;
-        t.size_log2 = (uint8_t)v;
-        t.n_elem = (uint8_t)(f.row_bytes >> v);
-        t.row_bytes = (uint8_t)f.row_bytes;
+      if (f.in_record && f.stride <= (size_t)kAsyncMaxStride && !(force_gather && strcmp(force_gather, "lsu") == 0) &&
+          (size_t)ds->size * f.stride < ((size_t)1 << 36)) {
+        record_keys[plan[i].slot].push_back(i);
+      } else if (add_tiny(i)) {
       } else if (takes_async_path(f)) {
-        async_keys.push_back(i);
+        span_jobs.push_back({plan[i].slot, f.dptr, f.stride, round_up(f.row_bytes, 16), {{i, 0}}});
       } else {
         lsu_keys.push_back(i);
       }
     }
+    for (auto& kv : record_keys) {
+      std::vector<size_t>& keys = kv.second;
+      std::sort(keys.begin(), keys.end(), [&](size_t a, size_t c) {
+        return ds->fields[(size_t)plan[a].field].rec_off < ds->fields[(size_t)plan[c].field].rec_off;
+      });
+      for (size_t k0 = 0; k0 < keys.size();) {
+        // extend the span while the next field starts within 32 bytes of the end of the current one
+        const Field& f0 = ds->fields[(size_t)plan[keys[k0]].field];
+        size_t lo = f0.rec_off & ~(size_t)15, hi = f0.rec_off + f0.row_bytes, k1 = k0 + 1;
+        bool has_long = f0.row_bytes > 16;
+        while (k1 < keys.size()) {
+          const Field& fn = ds->fields[(size_t)plan[keys[k1]].field];
+          if (fn.rec_off > hi + 32) break;
+          hi = std::max(hi, fn.rec_off + fn.row_bytes);
+          has_long |= fn.row_bytes > 16;
+          ++k1;
+        }
+        if (has_long) {
+          SpanJob job{kv.first, ds->record_base + lo, ds->record_stride, round_up(hi - lo, 16), {}};
+          for (size_t k = k0; k < k1; ++k) job.outs.push_back({keys[k], ds->fields[(size_t)plan[keys[k]].field].rec_off - lo});
+          span_jobs.push_back(std::move(job));
+        } else {
+          for (size_t k = k0; k < k1; ++k)
+            if (!add_tiny(keys[k])) {   // more tiny rows than the index kernel takes: a span of their own
+              const Field& fk = ds->fields[(size_t)plan[keys[k]].field];
+              const size_t l2 = fk.rec_off & ~(size_t)15;
+              span_jobs.push_back({kv.first, ds->record_base + l2, ds->record_stride, round_up(fk.rec_off + fk.row_bytes - l2, 16),
+                                   {{keys[k], fk.rec_off - l2}}});
+            }
+        }
+        k0 = k1;
+      }
+    }
   }
-  fuse = fuse && !async_keys.empty();
+  const bool any_async = !span_jobs.empty();
+  fuse = fuse && any_async;
   // the index vectors only go to memory when a later launch (or the debug interface) reads them
-  p.write_vecs = ((!fuse && !async_keys.empty()) || async_keys.size() > (size_t)kMaxRowJobs || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
+  p.write_vecs = ((!fuse && any_async) || span_jobs.size() > (size_t)kMaxRowJobs || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
 
   // ---- prepare every launch once; each is then issued per row chunk ----
   typedef std::function<int(int64_t, int64_t, cudaStream_t)> LaunchFn;
@@ -1332,48 +1454,54 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   };
 
   // asynchronous row gather (cp.async ring per warp), all element widths in one launch
-  for (size_t q = 0; q < async_keys.size();) {
+  for (size_t q = 0; q < span_jobs.size();) {
     AsyncGatherParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.vec_rows = b->vec_rows;
     ap.total_rows = total;
-    size_t max_stride = 0;
+    size_t max_pitch = 0;
     const size_t q0 = q;
-    for (size_t t = q0; t < async_keys.size() && t < q0 + kMaxRowJobs; ++t)
-      max_stride = std::max(max_stride, ds->fields[(size_t)plan[async_keys[t]].field].stride);
+    for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) max_pitch = std::max(max_pitch, span_jobs[t].bytes);
     static const int env_stage = getenv("OGB_STAGE_BYTES") ? atoi(getenv("OGB_STAGE_BYTES")) : 0;
-    ap.stage_bytes = env_stage ? std::max<int>((env_stage + 127) / 128 * 128, (int)max_stride) : 4096;
+    ap.stage_bytes = env_stage ? std::max<int>((env_stage + 127) / 128 * 128, (int)max_pitch) : 4096;
     auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
-    for (; q < async_keys.size() && ap.n_jobs < kMaxRowJobs; ++q) {
-      const KeyPlan& k = plan[async_keys[q]];
-      const Field& f = ds->fields[(size_t)k.field];
+    int n_outs = 0;
+    for (; q < span_jobs.size() && ap.n_jobs < kMaxRowJobs && n_outs + (int)span_jobs[q].outs.size() <= kMaxRowOuts; ++q) {
+      const SpanJob& sj = span_jobs[q];
       AsyncJob& job = ap.jobs[ap.n_jobs++];
-      job.src = f.dptr;
-      job.dst = base + b->offsets[async_keys[q]];
-      job.stride = (uint32_t)f.stride;
-      job.row_bytes = (uint32_t)f.row_bytes;
-      job.cpr = (uint32_t)((f.row_bytes + 15) / 16);
+      job.src = sj.src;
+      job.stride = (uint32_t)sj.stride;
+      job.cpr = (uint32_t)(sj.bytes / 16);
+      job.spitch = job.cpr * 16u;
       job.cpr_magic = magic(job.cpr);
       job.chunk_dr = (uint8_t)(32 / job.cpr);
       job.chunk_dch = (uint8_t)(32 % job.cpr);
-      job.chunk_step = (uint32_t)job.chunk_dr * job.stride + (uint32_t)job.chunk_dch * 16u;
-      job.chunk_wrap = job.stride - job.cpr * 16u;
-      job.gap = (uint32_t)(f.stride - f.row_bytes);
-      if (f.row_bytes % 16 == 0 && job.gap == 0) {
-        job.drain = DRAIN_DENSE16;
-      } else if (f.row_bytes % 4 == 0) {
-        job.drain = DRAIN_WORDS;
-        job.epr = (uint32_t)(f.row_bytes / 4);
-      } else {
-        job.drain = DRAIN_ELEMS;
-        job.vec_log2 = (uint8_t)(f.row_bytes % 2 == 0 ? 1 : 0);
-        job.epr = (uint32_t)(f.row_bytes >> job.vec_log2);
-      }
-      job.epr_magic = magic(job.epr);
-      size_t rpi = std::min<size_t>(32, (size_t)ap.stage_bytes / f.stride);
+      job.chunk_step = (uint32_t)job.chunk_dr * job.spitch + (uint32_t)job.chunk_dch * 16u;
+      size_t rpi = std::min<size_t>(32, (size_t)ap.stage_bytes / job.spitch);
       if (rpi > 4) rpi &= ~(size_t)3;   // items start on 16-byte boundaries of the dense output (16-byte drain stores)
       job.rows_per_item = (uint16_t)rpi;
-      job.slot = (uint8_t)k.slot;
+      job.slot = (uint8_t)sj.slot;
+      job.out_begin = (uint8_t)n_outs;
+      job.n_out = (uint8_t)sj.outs.size();
+      for (const auto& po : sj.outs) {
+        const Field& f = ds->fields[(size_t)plan[po.first].field];
+        AsyncOut& out = ap.outs[n_outs++];
+        out.dst = base + b->offsets[po.first];
+        out.soff = (uint32_t)po.second;
+        out.row_bytes = (uint32_t)f.row_bytes;
+        out.gap = job.spitch - (uint32_t)f.row_bytes;
+        if (f.row_bytes % 16 == 0 && out.gap == 0) {
+          out.drain = DRAIN_DENSE16;
+        } else if (f.row_bytes % 4 == 0 && po.second % 4 == 0) {
+          out.drain = DRAIN_WORDS;
+          out.epr = (uint32_t)(f.row_bytes / 4);
+        } else {
+          out.drain = DRAIN_ELEMS;
+          out.vec_log2 = (uint8_t)((f.row_bytes % 2 == 0 && po.second % 2 == 0) ? 1 : 0);
+          out.epr = (uint32_t)(f.row_bytes >> out.vec_log2);
+        }
+        out.epr_magic = magic(out.epr);
+      }
     }
     const size_t smem = (size_t)kAsyncWarps * kAsyncStages * ap.stage_bytes;
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
@@ -1583,7 +1711,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
     // else the index kernel itself (datasets whose rows are all <= 16 bytes)
     b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather_kernel"
-                : !async_keys.empty() ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
+                : any_async ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
     const bool prof_gathers = s->profile && !gather_launches.empty() && !fused_launch;
     if (prof_gathers) {
       cudaEventCreate(&b->prof_begin);

@@ -72,7 +72,8 @@ struct TinyJob {
   uint8_t size_log2;   // element size
   uint8_t n_elem;      // row = n_elem elements (<= 16 bytes in total)
   uint8_t row_bytes;
-  uint32_t pad2_;
+  uint16_t stride;     // resident row stride (row_bytes, or the stride of the packed record table)
+  uint16_t pad2_;
 };
 
 struct RelabelParams {
@@ -363,7 +364,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
       if (j0 + u < p.n_tiny) {
         const TinyJob& job = p.tiny[j0 + u];
         const uint32_t row_bytes = job.row_bytes;
-        const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * row_bytes;
+        const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * job.stride;
         if (row_bytes == 4) v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp));
         else if (row_bytes == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp)); v[u].x = t.x; v[u].y = t.y; }
         else if (row_bytes == 16) v[u] = __ldg(reinterpret_cast<const uint4*>(sp));
@@ -385,7 +386,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
         else if (row_bytes == 12) {
           reinterpret_cast<uint32_t*>(dp)[0] = v[u].x; reinterpret_cast<uint32_t*>(dp)[1] = v[u].y; reinterpret_cast<uint32_t*>(dp)[2] = v[u].z;
         } else {                                      // odd sizes: element by element
-          const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * row_bytes;
+          const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * job.stride;
           if (job.size_log2 == 1) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
           else if (job.size_log2 == 2) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
           else for (uint32_t e = 0; e < row_bytes; ++e) dp[e] = __ldg(sp + e);
@@ -572,26 +573,38 @@ constexpr int kAsyncMaxStride = 4096;
 
 enum : int { DRAIN_WORDS = 0, DRAIN_DENSE16 = 1, DRAIN_ELEMS = 2 };
 
-struct AsyncJob {
-  const uint8_t* src;
+// One output array of a job: a sub-field of the staged span, written densely (datasets.py:78-83: every field of the
+// dataset is gathered at the same rows, so one staged record feeds several keys).
+struct AsyncOut {
   uint8_t* dst;
-  uint32_t stride;        // resident row stride, multiple of 16
+  uint32_t soff;          // byte offset of the sub-field inside a staged row
   uint32_t row_bytes;
-  uint32_t cpr;           // 16-byte chunks copied per row = ceil(row_bytes / 16)
-  uint32_t cpr_magic;     // ceil(2^32 / cpr), or 0 when cpr == 1: e / cpr == umulhi(e, magic) for e * cpr < 2^32
-  uint32_t chunk_step;    // advance of a lane's stage offset per issue iteration: (32 / cpr) * stride + (32 % cpr) * 16
-  uint32_t chunk_wrap;    // extra advance when the chunk index wraps into the next row: stride - cpr * 16
   uint32_t epr;           // output elements per row: 4-byte words (DRAIN_WORDS) or 1 << vec_log2 bytes (DRAIN_ELEMS)
-  uint32_t epr_magic;
-  uint32_t gap;           // stride - row_bytes: padding between two rows in a stage
-  uint16_t rows_per_item; // rows of one stage
+  uint32_t epr_magic;     // ceil(2^32 / epr), or 0 when epr == 1
+  uint32_t gap;           // spitch - row_bytes: bytes between the end of this sub-field in one staged row and its start in the next
   uint8_t drain;          // DRAIN_*
   uint8_t vec_log2;       // DRAIN_ELEMS only
+  uint16_t pad_;
+};
+
+// One load job: the span [src, src + 16 * cpr) of every source row named by index vector `slot`
+struct AsyncJob {
+  const uint8_t* src;     // field base, or record table base + span offset; 16-byte aligned
+  uint32_t stride;        // source row stride, multiple of 16
+  uint32_t spitch;        // row pitch inside a stage = 16 * cpr
+  uint32_t cpr;           // 16-byte chunks copied per row
+  uint32_t cpr_magic;     // ceil(2^32 / cpr), or 0 when cpr == 1: e / cpr == umulhi(e, magic) for e * cpr < 2^32
+  uint32_t chunk_step;    // advance of a lane's stage offset per issue iteration: (32 / cpr) * spitch + (32 % cpr) * 16
+  uint16_t rows_per_item; // rows of one stage
   uint8_t slot;
   uint8_t chunk_dr;       // 32 / cpr
   uint8_t chunk_dch;      // 32 % cpr
+  uint8_t out_begin;      // first of this job's outputs in AsyncGatherParams::outs
+  uint8_t n_out;
   uint8_t pad_;
 };
+
+constexpr int kMaxRowOuts = 48;
 
 struct AsyncGatherParams {
   const int32_t* vec_rows;
@@ -600,6 +613,7 @@ struct AsyncGatherParams {
   int32_t n_jobs;
   int32_t stage_bytes;
   AsyncJob jobs[kMaxRowJobs];
+  AsyncOut outs[kMaxRowOuts];
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
@@ -723,14 +737,14 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
         }
       }
       const int rows = min((int)job.rows_per_item, c.n - c.sub);
-      const uint32_t cpr = job.cpr, stride = job.stride;
+      const uint32_t cpr = job.cpr, spitch = job.spitch;
       const int n_chunks = rows * (int)cpr;
       // lane -> (row r, chunk ch) of the item; both advance incrementally, no division inside the loop.
       // Source addresses are formed in 16-byte units (32-bit), so a field must stay below 64 GB (host-checked).
       uint32_t r = fast_div((uint32_t)lane, job.cpr_magic);
       uint32_t ch = (uint32_t)lane - r * cpr;
-      uint32_t soff = stage_u32 + r * stride + (ch << 4);
-      const uint32_t stride16 = stride >> 4;
+      uint32_t soff = stage_u32 + r * spitch + (ch << 4);
+      const uint32_t stride16 = job.stride >> 4;
       const uint32_t dr = job.chunk_dr, dch = job.chunk_dch, step = job.chunk_step;
       const uint4* __restrict__ src16 = reinterpret_cast<const uint4*>(job.src);
       r += (uint32_t)c.sub;
@@ -743,13 +757,12 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
           r += dr; soff += step;
         }
       } else {
-        const uint32_t wrap = job.chunk_wrap;
 #pragma unroll 2
         for (int e = lane; e - lane < n_chunks; e += 32) {
           const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, issue_rows, (int)r);
           if (e < n_chunks) cp_async16(soff, src16 + (src_row * stride16 + ch));
           r += dr; ch += dch; soff += step;
-          if (ch >= cpr) { ch -= cpr; ++r; soff += wrap; }
+          if (ch >= cpr) { ch -= cpr; ++r; }     // the stage pitch is exactly cpr chunks: soff needs no correction
         }
       }
     }
@@ -759,17 +772,23 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
   auto drain = [&](const ItemCursor& c, const uint32_t sbase) {
     const AsyncJob& job = p.jobs[c.j];
     const int rows = min((int)job.rows_per_item, c.n - c.sub);
-    uint8_t* dbase = job.dst + (size_t)(uint32_t)((c.wt << 5) + c.sub) * job.row_bytes;
-    if (job.drain == DRAIN_WORDS) {
-      if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_words(sbase, dbase, (uint32_t)rows * job.epr, job.epr_magic, job.gap, lane);
-      else drain_words_unaligned(sbase, dbase, (uint32_t)rows * job.epr, job.epr_magic, job.gap, lane);
-    } else if (job.drain == DRAIN_DENSE16) {
-      drain_dense16(sbase, dbase, (uint32_t)rows * job.row_bytes, lane);
-    } else {
-      const uint8_t* sgen = smem_ring + (size_t)(sbase - (uint32_t)__cvta_generic_to_shared(smem_ring));
-      const uint32_t n_elem = (uint32_t)rows * job.epr;
-      if (job.vec_log2 == 1) drain_flat<uint16_t>(sgen, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
-      else drain_flat<uint8_t>(sgen, dbase, n_elem, job.stride, job.epr, job.epr_magic, lane);
+    const uint32_t first_row = (uint32_t)((c.wt << 5) + c.sub);
+#pragma unroll 1
+    for (int o = job.out_begin; o < job.out_begin + job.n_out; ++o) {
+      const AsyncOut& out = p.outs[o];
+      uint8_t* dbase = out.dst + (size_t)first_row * out.row_bytes;
+      const uint32_t s0 = sbase + out.soff;
+      if (out.drain == DRAIN_WORDS) {
+        if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_words(s0, dbase, (uint32_t)rows * out.epr, out.epr_magic, out.gap, lane);
+        else drain_words_unaligned(s0, dbase, (uint32_t)rows * out.epr, out.epr_magic, out.gap, lane);
+      } else if (out.drain == DRAIN_DENSE16) {
+        drain_dense16(s0, dbase, (uint32_t)rows * out.row_bytes, lane);
+      } else {
+        const uint8_t* sgen = smem_ring + (size_t)(s0 - (uint32_t)__cvta_generic_to_shared(smem_ring));
+        const uint32_t n_elem = (uint32_t)rows * out.epr;
+        if (out.vec_log2 == 1) drain_flat<uint16_t>(sgen, dbase, n_elem, job.spitch, out.epr, out.epr_magic, lane);
+        else drain_flat<uint8_t>(sgen, dbase, n_elem, job.spitch, out.epr, out.epr_magic, lane);
+      }
     }
   };
 
