@@ -1201,11 +1201,13 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   };
   // When some key goes through the cp.async row gather, the index algebra is fused into that launch (one kernel per
   // sample() for vector observations); otherwise the index kernel runs on its own.
-  // Measured on B200 (c2/c3/c5 shapes): for launches of ~1M rows the split form is as fast or faster (the fused warps
-  // serialise their own index latency), for small launches the saved kernel launch wins.  OGB_FUSE=0/1 forces either.
+  // Measured on B200 with ~1M-row launches: fused wins for GCDataset shapes (C2 0.201 vs 0.216 ms, C5 0.356 vs 0.372)
+  // and loses for the heavier HGC algebra with its 16-row items (C3 0.757 vs 0.730 ms), so big HGC launches stay split;
+  // small launches always fuse (one kernel launch less).  Image batches keep the index kernel apart (it overlaps the
+  // previous call's frame gathers).  OGB_FUSE=0/1 forces either.
   static const char* fuse_env = getenv("OGB_FUSE");
   bool fuse = false;
-  if (!no_fuse && (fuse_env ? atoi(fuse_env) != 0 : (total < kOverlapMinRows && !any_frames)))
+  if (!no_fuse && (fuse_env ? atoi(fuse_env) != 0 : (!any_frames && (total < kOverlapMinRows || spec.kind != OGB_KIND_HGC))))
     for (const KeyPlan& k : plan)
       if (k.route == ROUTE_ROW && k.alias_of < 0 && takes_async_path(ds->fields[(size_t)k.field])) fuse = true;
   // Image batches are few rows with long gathers: their (latency-bound) index kernel always goes to the auxiliary
@@ -1462,8 +1464,16 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     size_t max_pitch = 0;
     const size_t q0 = q;
     for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) max_pitch = std::max(max_pitch, span_jobs[t].bytes);
+    // rows per item: the largest power of two whose rows fit the stage budget, so that the items of a 32-row tile are
+    // equal (an uneven split, e.g. 28 + 4 rows, makes the short item hold a pipeline slot for little data)
     static const int env_stage = getenv("OGB_STAGE_BYTES") ? atoi(getenv("OGB_STAGE_BYTES")) : 0;
-    ap.stage_bytes = env_stage ? std::max<int>((env_stage + 127) / 128 * 128, (int)max_pitch) : 4096;
+    // budget: 4 KB stages (2 CTAs per SM) for rows up to 256 bytes, 6 KB (16-row items, 1 CTA per SM) beyond -- C3's
+    // 384/288-byte spans run 15 % faster with 16-row items than with 8-row ones
+    const size_t budget = std::max<size_t>(env_stage ? (size_t)env_stage : (max_pitch > 256 ? 6144 : 4096), max_pitch);
+    auto rows_for = [&](size_t pitch) { size_t r = 32; while (r > 1 && r * pitch > budget) r >>= 1; return r; };
+    size_t stage = 0;
+    for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) stage = std::max(stage, rows_for(span_jobs[t].bytes) * span_jobs[t].bytes);
+    ap.stage_bytes = (int)round_up(stage, 128);
     auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
     int n_outs = 0;
     for (; q < span_jobs.size() && ap.n_jobs < kMaxRowJobs && n_outs + (int)span_jobs[q].outs.size() <= kMaxRowOuts; ++q) {
@@ -1477,9 +1487,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       job.chunk_dr = (uint8_t)(32 / job.cpr);
       job.chunk_dch = (uint8_t)(32 % job.cpr);
       job.chunk_step = (uint32_t)job.chunk_dr * job.spitch + (uint32_t)job.chunk_dch * 16u;
-      size_t rpi = std::min<size_t>(32, (size_t)ap.stage_bytes / job.spitch);
-      if (rpi > 4) rpi &= ~(size_t)3;   // items start on 16-byte boundaries of the dense output (16-byte drain stores)
-      job.rows_per_item = (uint16_t)rpi;
+      job.rows_per_item = (uint16_t)rows_for(job.spitch);   // >= 4 rows: items start on 16-byte boundaries of the dense output
       job.slot = (uint8_t)sj.slot;
       job.out_begin = (uint8_t)n_outs;
       job.n_out = (uint8_t)sj.outs.size();
