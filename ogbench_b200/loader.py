@@ -58,6 +58,40 @@ def load_dataset(dataset_path, ob_dtype=np.float32, action_dtype=np.float32, com
     return dataset
 
 
+def add_oracle_reps(env_name, env, dataset, num_cubes=None, num_buttons=None):
+    """Add oracle goal representations to the dataset (same contract as ogbench/relabel_utils.py:93-155).
+
+    `env` may be None when `num_cubes` / `num_buttons` are given (the reference reads them from
+    `env.unwrapped._num_cubes` / `_num_buttons`); the dataset must have been loaded with add_info=True ('qpos',
+    'button_states').  The sampler then serves goals from `oracle_reps` (datasets.py:348-357).
+    """
+    def count(attr, given):
+        return given if given is not None else getattr(env.unwrapped, attr)
+
+    qpos = dataset['qpos'] if ('maze' in env_name or 'soccer' in env_name or 'cube' in env_name or 'scene' in env_name) else None
+    if 'maze' in env_name or 'soccer' in env_name:
+        start = 0 if 'maze' in env_name else 15            # agent xy, or the ball's xy for antsoccer
+        oracle_reps = qpos[:, start:start + 2]
+    elif 'cube' in env_name or 'scene' in env_name or 'puzzle' in env_name:
+        obj0, cube_len = 14, 7
+        xyz_center = np.array([0.425, 0.0, 0.0])
+        if 'puzzle' in env_name:
+            oracle_reps = dataset['button_states'].copy()
+        else:
+            n_cubes = count('_num_cubes', num_cubes)
+            cube_xyzs = np.stack([qpos[:, obj0 + i * cube_len:obj0 + i * cube_len + 3] for i in range(n_cubes)], axis=1)
+            cube_reps = ((cube_xyzs - xyz_center) * 10.0).reshape(-1, n_cubes * 3)
+            if 'cube' in env_name:
+                oracle_reps = cube_reps
+            else:
+                drawer = obj0 + n_cubes * cube_len + count('_num_buttons', num_buttons)
+                oracle_reps = np.concatenate(
+                    [cube_reps, dataset['button_states'].copy(), qpos[:, [drawer]] * 18.0, qpos[:, [drawer + 1]] * 15.0], axis=-1)
+    else:
+        raise ValueError(f'Unsupported environment: {env_name}')
+    dataset['oracle_reps'] = oracle_reps.astype(np.float32)
+
+
 def load_gc_dataset(dataset_path, config, dataset_class=GCDataset, ob_dtype=np.float32, action_dtype=np.float32,
                     device: int = 0, **sampler_kwargs):
     """`.npz` -> compact layout (what impls/utils/env_utils.py:89-95 asks for) -> HBM -> device sampler."""

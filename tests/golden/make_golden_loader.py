@@ -44,7 +44,39 @@ CASES = [
 ]
 
 
+ORACLE_ENVS = [  # (env name, num_cubes, num_buttons)
+    ('antmaze-large-navigate-oraclerep-v0', None, None), ('antsoccer-arena-navigate-oraclerep-v0', None, None),
+    ('cube-double-play-oraclerep-v0', 2, None), ('scene-play-oraclerep-v0', 1, 2), ('puzzle-3x3-play-oraclerep-v0', None, None),
+]
+
+
+def oracle_inputs(seed=5, n=13):
+    rng = np.random.default_rng(seed)
+    return dict(qpos=rng.standard_normal((n, 40)), button_states=rng.integers(0, 2, (n, 9)).astype(np.int64))
+
+
+def load_reference_relabel():
+    spec = importlib.util.spec_from_file_location('ogb_reference_relabel', os.path.join(REF, 'ogbench', 'relabel_utils.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main_oracle_reps():
+    """ogbench/relabel_utils.py:93-155 run unmodified on synthetic qpos / button_states -> loader_oracle_reps.npz"""
+    ref = load_reference_relabel()
+    payload = {}
+    for name, cubes, buttons in ORACLE_ENVS:
+        env = types.SimpleNamespace(unwrapped=types.SimpleNamespace(_num_cubes=cubes, _num_buttons=buttons))
+        ds = oracle_inputs()
+        ref.add_oracle_reps(name, env, ds)
+        payload[name] = ds['oracle_reps']
+    np.savez_compressed(os.path.join(HERE, 'loader_oracle_reps.npz'), **payload)
+    print('loader_oracle_reps', len(payload), 'arrays')
+
+
 def main():
+    main_oracle_reps()
     ref = load_reference_utils()
     for name, raw_kw, load_kw in CASES:
         raw = os.path.join(HERE, name + '_raw.npz')

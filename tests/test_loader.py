@@ -26,6 +26,25 @@ def test_load_dataset_matches_reference(name, raw_kw, load_kw):
                 assert got[k].dtype == w.dtype and got[k].shape == w.shape and np.array_equal(got[k], w), (compact, add_info, k)
 
 
+def test_add_oracle_reps_matches_reference():
+    """add_oracle_reps (ogbench/relabel_utils.py:93-155) against arrays produced by the unmodified reference function."""
+    import types
+
+    from tests.golden.make_golden_loader import ORACLE_ENVS, oracle_inputs
+
+    want = np.load(os.path.join(HERE, 'loader_oracle_reps.npz'))
+    for name, cubes, buttons in ORACLE_ENVS:
+        ds = oracle_inputs()
+        loader.add_oracle_reps(name, None, ds, num_cubes=cubes, num_buttons=buttons)
+        assert ds['oracle_reps'].dtype == np.float32 and np.array_equal(ds['oracle_reps'], want[name]), name
+        env = types.SimpleNamespace(unwrapped=types.SimpleNamespace(_num_cubes=cubes, _num_buttons=buttons))
+        ds2 = oracle_inputs()
+        loader.add_oracle_reps(name, env, ds2)
+        assert np.array_equal(ds2['oracle_reps'], want[name]), name
+    with pytest.raises(ValueError):
+        loader.add_oracle_reps('powderworld-easy-play-v0', None, oracle_inputs())
+
+
 def test_list_shards(tmp_path):
     for n in ('b.npz', 'a.npz', 'a-val.npz', 'c.txt'):
         (tmp_path / n).write_bytes(b'')
