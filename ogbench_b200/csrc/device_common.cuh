@@ -61,6 +61,12 @@ __device__ __forceinline__ uint4 draw4(const RngKey& key, uint64_t batch, uint32
   return philox4x32_10(ctr, key);
 }
 
+// the same draw, out of line: for the draws that only some configurations make (actor mix coins, TRL midpoints, crop
+// shifts, the per-batch coin), so that their ten Philox rounds are not inlined into the hot path's instruction footprint
+__device__ __noinline__ uint4 draw4_cold(const RngKey& key, uint64_t batch, uint32_t row, uint32_t purpose) {
+  return draw4(key, batch, row, purpose);
+}
+
 // uniform integer in [0, n), n < 2^32, from 64 random bits: floor(((hi << 32) | lo) * n / 2^64), bias < n / 2^64
 __device__ __forceinline__ uint32_t bounded_u32n(uint32_t hi, uint32_t lo, uint32_t n) {
   const uint64_t t = (uint64_t)lo * n;
@@ -79,6 +85,12 @@ __device__ __forceinline__ double unit_double(uint32_t a, uint32_t b) {
 // evaluated.  Both branches return the value of the float64 expression.  Error budget of the estimate, with
 // uf = float(a) * 2^-32:  |uf - U| <= 2^-27 + 2^-24 U  ->  |dq| <= q * 6e-8 / (1-U) + 7.5e-9 / ((1-U) |log_1mp|);
 // log1pf 1 ulp, __fdividef 2 ulp, float(log_1mp) 0.5 ulp -> 4.2e-7 * q.  The margin below is twice that bound.
+// the rare float64 path, kept out of line: its log() expansion is ~200 instructions and would otherwise be inlined at
+// every goal set (the index code has to stay inside the 32 KB instruction cache level to issue well)
+__device__ __noinline__ double geometric_exact(uint32_t a, uint32_t b, double log_1mp) {
+  return ceil(log(1.0 - unit_double(a, b)) / log_1mp);
+}
+
 __device__ __forceinline__ int64_t geometric_from_words(uint32_t a, uint32_t b, double log_1mp, float abs_margin) {
   const float uf = __uint2float_rn(a) * 2.3283064365386962891e-10f;
   const float qf = __fdividef(log1pf(-uf), (float)log_1mp);
@@ -89,7 +101,7 @@ __device__ __forceinline__ int64_t geometric_from_words(uint32_t a, uint32_t b, 
   if (uf < 0.9999f && cf - qf > margin && qf - (cf - 1.0f) > margin) {
     x = (double)cf;
   } else {
-    x = ceil(log(1.0 - unit_double(a, b)) / log_1mp);
+    x = geometric_exact(a, b, log_1mp);
   }
   return x < 1.0 ? 1 : (int64_t)x;
 }

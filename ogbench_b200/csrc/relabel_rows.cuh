@@ -76,6 +76,29 @@ struct TinyJob {
   uint16_t pad2_;
 };
 
+// Tiny fields that sit next to each other in the packed record table and are gathered through the same index vector
+// (observations, actions, terminals, valids of a point-maze transition: 24 bytes of one 32-byte record) are loaded
+// ONCE: one or two 16-byte loads per group, the fields are then cut out of registers.  The index kernel is bound by
+// scattered-load wavefronts (L1TEX), not by ALU work, so trading three loads for a few selects pays.
+constexpr int kMaxTinyGroups = 2;
+constexpr int kMaxTinyFields = 16;
+struct TinyGroup {
+  const uint8_t* src;   // record table base + 16-byte aligned span offset
+  uint16_t stride;
+  uint8_t slot;
+  uint8_t n_vec;        // 16-byte loads: 1 or 2
+  uint8_t first_field;  // into RelabelParams::tiny_fields
+  uint8_t n_fields;
+  uint16_t pad_;
+};
+struct TinyField {
+  uint8_t* dst;
+  uint8_t word;         // first 4-byte word of the field inside the group's span (0..7)
+  uint8_t n_words;      // 1..4
+  uint8_t group;
+  uint8_t pad_[5];
+};
+
 struct RelabelParams {
   // ---- dataset-side tables (all int32, resident) ----
   const int32_t* term;         // terminal_locs (datasets.py:186)
@@ -91,6 +114,8 @@ struct RelabelParams {
   const int4* seg_table;       // valid_mode 3: {c[m], final_state(segment m), final_state(segment m+1), 0}
   const int32_t* seg_bucket;   //               lower_bound(c, b << seg_shift); a bucket holds at most one c[m]
   int32_t seg_shift;
+  int32_t n_seg_table;         // entries of seg_table / seg_bucket (for the shared-memory copy of the index kernel)
+  int32_t n_seg_bucket;
   int32_t pad_seg_;
   // ---- sampler config ----
   GoalSpec goal[3];            // value, low-value, actor
@@ -140,30 +165,57 @@ struct RelabelParams {
   int32_t* vec_init;           // first row of each row's trajectory segment (frame stacking only; may be null)
   int8_t* crop_out;            // [total_rows][2] (dy, dx) or -128 when the batch is not augmented (may be null)
   // ---- rows of <= 16 bytes, copied by the index kernel ----
-  int32_t n_tiny;
+  int32_t n_tiny;              // the first n_tiny_fast of them have rows of 4, 8 or 16 bytes
+  int32_t n_tiny_fast;
   int32_t write_vecs;          // 0: no later kernel needs the index vectors (everything was tiny) and debug is off
   TinyJob tiny[kMaxTinyJobs];
+  int32_t n_tiny_groups;
+  int32_t n_tiny_fields;
+  TinyGroup tiny_groups[kMaxTinyGroups];
+  TinyField tiny_fields[kMaxTinyFields];
 };
+
+// word `i` (0..7) of the eight words held in two uint4
+__device__ __forceinline__ uint32_t select_word(const uint4& a, const uint4& b, const uint32_t i) {
+  const uint4 t = (i & 4u) ? b : a;
+  const uint2 h = (i & 2u) ? make_uint2(t.z, t.w) : make_uint2(t.x, t.y);
+  return (i & 1u) ? h.y : h.x;
+}
 
 // valid_mode 3 -- datasets whose invalid rows are far apart (every compact OGBench dataset: one per trajectory) and
 // whose trajectories end where their valid rows end.  Position pos among the valid rows falls into segment
 // m = #{invalid rows before it} = upper_bound(c, pos); buckets are narrower than the smallest gap between two c[m],
 // so a bucket holds at most one boundary and the search is ONE probe: two dependent loads give the row AND the
 // trajectory's final state (datasets.py:306 needs a second search in the reference).
-__device__ __forceinline__ int32_t valid_row_fast(const RelabelParams& p, const uint32_t pos, int32_t& fin) {
-  const int lo = __ldg(p.seg_bucket + (pos >> p.seg_shift));
-  const int4 e = __ldg(p.seg_table + lo);
+// Where the segment table is read from: global memory (read-only path), or the copy a persistent index kernel made in
+// shared memory (scattered 4/16-byte table reads then cost bank cycles instead of L1TEX tag lookups).
+struct SegView {
+  const int32_t* bucket;
+  const int4* table;
+};
+
+template <bool kSmemTables>
+__device__ __forceinline__ int32_t valid_row_fast(const RelabelParams& p, const SegView& seg, const uint32_t pos, int32_t& fin) {
+  const int lo = kSmemTables ? seg.bucket[pos >> p.seg_shift] : __ldg(seg.bucket + (pos >> p.seg_shift));
+  const int4 e = kSmemTables ? seg.table[lo] : __ldg(seg.table + lo);
   const bool past = e.x <= (int32_t)pos;
   fin = past ? e.z : e.y;
   return (int32_t)pos + lo + (past ? 1 : 0);
 }
 
-__device__ __forceinline__ int32_t valid_row(const RelabelParams& p, int64_t pos) {
-  if (p.valid_mode == 3) { int32_t unused; return valid_row_fast(p, (uint32_t)pos, unused); }
+// the general forms (no 'valids', explicit table, gap ranks with a binary search): out of line, the segment table
+// serves every compact OGBench dataset
+__device__ __noinline__ int32_t valid_row_general(const RelabelParams& p, int64_t pos) {
   if (p.valid_mode == 0) return (int32_t)pos;
   if (p.valid_mode == 1) return __ldg(p.valid_table + pos);
   const int j = (int)pos;
   return j + lower_bound_bucketed(p.gap_c, p.gap_bucket, p.gap_shift, j + 1);  // upper_bound(c, j)
+}
+
+template <bool kSmemTables>
+__device__ __forceinline__ int32_t valid_row(const RelabelParams& p, const SegView& seg, int64_t pos) {
+  if (p.valid_mode == 3) { int32_t unused; return valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, unused); }
+  return valid_row_general(p, pos);
 }
 
 // datasets.py:313-316 -- float64, separate multiply/add (no FMA contraction), round half to even
@@ -173,13 +225,14 @@ __device__ __forceinline__ int32_t uniform_future_goal(int32_t i, int32_t fin, d
 }
 
 // Validation mode: the reference's own draws (float64 uniforms, int64 offsets) decide.
-__device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
-                                                      const int64_t g) {
+template <bool kSmemTables>
+__device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, const SegView& seg, const int gs, const int32_t i,
+                                                      const int32_t fin, const int64_t g) {
   const GoalSpec& s = p.goal[gs];
   if (s.cur_only) return i;                                  // p_curgoal == 1.0  (datasets.py:317-318)
   const GoalInject& in = p.in_goal[gs];
   if (in.u_cur[g] < s.p_cur) return i;                       // np.where(rand < p_cur, idxs, ...)  :325
-  if (!(in.u_traj[g] < s.thr_traj)) return valid_row(p, in.rand_pos[g]);   // random goal  :303,:320-322
+  if (!(in.u_traj[g] < s.thr_traj)) return valid_row<kSmemTables>(p, seg, in.rand_pos[g]);   // random goal  :303,:320-322
   if (s.geom) {                                              // :309-310
     const int64_t t = (int64_t)i + in.offset[g];
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
@@ -189,12 +242,13 @@ __device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, co
 
 // Philox mode: `mix` = (u_traj, u_cur) as 32-bit words, `bits` = the 64 random bits of this goal set, spent either
 // on the random-goal position or on the geometric / distance uniform -- never both, since the mix decides first.
-__device__ __forceinline__ int32_t pick_goal_philox(const RelabelParams& p, const int gs, const int32_t i, const int32_t fin,
-                                                    const uint2 mix, const uint2 bits) {
+template <bool kSmemTables>
+__device__ __forceinline__ int32_t pick_goal_philox(const RelabelParams& p, const SegView& seg, const int gs, const int32_t i,
+                                                    const int32_t fin, const uint2 mix, const uint2 bits) {
   const GoalSpec& s = p.goal[gs];
   if (s.cur_only) return i;
   if (s.cur_always || mix.y < s.thr_cur32) return i;
-  if (!(s.traj_always || mix.x < s.thr_traj32)) return valid_row(p, bounded_u32n(bits.x, bits.y, (uint32_t)p.n_choices));
+  if (!(s.traj_always || mix.x < s.thr_traj32)) return valid_row<kSmemTables>(p, seg, bounded_u32n(bits.x, bits.y, (uint32_t)p.n_choices));
   if (s.geom) {
     const int64_t t = (int64_t)i + geometric_from_words(bits.x, bits.y, s.log_1mp, s.geo_abs_margin);
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
@@ -210,7 +264,8 @@ __device__ __forceinline__ void subgoal_step(int32_t i, int32_t fin, int32_t goa
   next = i + s;
 }
 
-__device__ __forceinline__ int32_t trajectory_first_row(const RelabelParams& p, int32_t x) {
+// (frame stacking only; out of line so that the put_slot sites do not each carry a search)
+__device__ __noinline__ int32_t trajectory_first_row(const RelabelParams& p, int32_t x) {
   // initial_locs[searchsorted(initial_locs, x, 'right') - 1] (datasets.py:361) expressed on terminal_locs:
   // with t = lower_bound(term, x) the start is 0 when t == 0, else term[t-1] + 1.
   x = x < p.n_rows_ds ? x : p.n_rows_ds - 1;
@@ -253,8 +308,8 @@ __device__ __forceinline__ void split_row(const RelabelParams& p, const int64_t 
 
 // All per-row work of sample(): index draws, goal relabelling, rewards/masks, the rows of <= 16 bytes, crop shifts.
 // On return sr[] holds the dataset row of every slot for batch row g.
-template <bool kInject, int kFlavour>
-__device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_t g, int32_t* sr) {
+template <bool kInject, int kFlavour, bool kSmemTables = false>
+__device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegView& seg, const int64_t g, int32_t* sr) {
   constexpr int kSlots = FlavourSlots<kFlavour>::value;
   uint64_t batch_id;
   uint32_t r;
@@ -267,8 +322,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
     i = (int32_t)p.given_idxs[g];
   } else {
     const int64_t pos = kInject ? p.in_idx_pos[g] : (int64_t)bounded_u32n(w0.x, w0.y, (uint32_t)p.n_choices);
-    if (p.valid_mode == 3) i = valid_row_fast(p, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe
-    else i = valid_row(p, pos);
+    if (p.valid_mode == 3) i = valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe
+    else i = valid_row<kSmemTables>(p, seg, pos);
   }
   put_slot(p, sr, SLOT_IDX, g, i);
   const int32_t nxt = p.stacked_next ? i + p.next_offset                                           // :231 / :408
@@ -279,17 +334,17 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
     uint4 gb = make_uint4(0, 0, 0, 0), amix = make_uint4(0, 0, 0, 0);
     if (!kInject) {
       gb = draw4(p.key, batch_id, r, PURPOSE_GOAL);
-      if (p.actor_mix) amix = draw4(p.key, batch_id, r, PURPOSE_MIX);
+      if (p.actor_mix) amix = draw4_cold(p.key, batch_id, r, PURPOSE_MIX);
     }
     if (fin < 0) {                                                      // final_state_idxs  :306,:505
       const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
       fin = __ldg(p.term + tl);
     }
     const double neg = p.gc_negative ? 1.0 : 0.0;
-    const int32_t vg = kInject ? pick_goal_injected(p, 0, i, fin, g)                   // :233-239 / :508-514
-                               : pick_goal_philox(p, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
-    const int32_t ag = kInject ? pick_goal_injected(p, 2, i, fin, g)                   // :240-246 / :585-591
-                               : pick_goal_philox(p, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
+    const int32_t vg = kInject ? pick_goal_injected<kSmemTables>(p, seg, 0, i, fin, g)                   // :233-239 / :508-514
+                               : pick_goal_philox<kSmemTables>(p, seg, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
+    const int32_t ag = kInject ? pick_goal_injected<kSmemTables>(p, seg, 2, i, fin, g)                   // :240-246 / :585-591
+                               : pick_goal_philox<kSmemTables>(p, seg, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
     const double succ = (i == vg) ? 1.0 : 0.0;                         // :250-252 / :579-582
     p.masks[g] = 1.0 - succ;
     p.rewards[g] = succ - neg;
@@ -302,7 +357,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
         if (kInject) {
           mid = (int32_t)p.in_trl_mid[g];
         } else {
-          const uint4 t = draw4(p.key, batch_id, r, PURPOSE_TRL_MID);
+          const uint4 t = draw4_cold(p.key, batch_id, r, PURPOSE_TRL_MID);
           mid = i + (int32_t)bounded_u32n(t.x, t.y, (uint32_t)span);   // randint(idxs, value_goal_idxs): [i, vg)
         }
         put_slot(p, sr, GC_TRL_MID, g, mid);
@@ -330,10 +385,10 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
       if (p.has_low_goal) {                                                         // :563-576
         int32_t lvg;
         if (kInject) {
-          lvg = pick_goal_injected(p, 1, i, fin, g);
+          lvg = pick_goal_injected<kSmemTables>(p, seg, 1, i, fin, g);
         } else {
-          const uint4 lb = draw4(p.key, batch_id, r, PURPOSE_GOAL_LOW);
-          lvg = pick_goal_philox(p, 1, i, fin, make_uint2(lb.z, lb.w), make_uint2(lb.x, lb.y));
+          const uint4 lb = draw4_cold(p.key, batch_id, r, PURPOSE_GOAL_LOW);
+          lvg = pick_goal_philox<kSmemTables>(p, seg, 1, i, fin, make_uint2(lb.z, lb.w), make_uint2(lb.x, lb.y));
         }
         put_slot(p, sr, HGC_LV_GOAL, g, lvg);
         const double s = (i == lvg) ? 1.0 : 0.0;
@@ -354,45 +409,78 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
     }
   }
 
-  // rows of <= 16 bytes: this thread copies them now (datasets.py:78-83 for the per-transition fields).  Rows of 4, 8,
-  // 12 or 16 bytes are loaded four jobs at a time before any is stored, so their L2 latencies overlap.
+  // grouped tiny fields: one record load per group, all groups' loads issued before any store.  (Unrolling the field
+  // and job loops completely, so that the descriptors sit at fixed constant-bank offsets, was measured: the code
+  // growth costs more than the saved LDCs, 0.052 vs 0.047 ms on C1 and 0.223 vs 0.203 ms on C2's fused kernel.)
+  {
+    uint4 ga[kMaxTinyGroups], gb[kMaxTinyGroups];
+#pragma unroll
+    for (int u = 0; u < kMaxTinyGroups; ++u) {
+      ga[u] = make_uint4(0, 0, 0, 0);
+      gb[u] = make_uint4(0, 0, 0, 0);
+      if (u < p.n_tiny_groups) {
+        const TinyGroup& grp = p.tiny_groups[u];
+        const uint4* sp = reinterpret_cast<const uint4*>(grp.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, grp.slot) * grp.stride);
+        ga[u] = __ldg(sp);
+        if (grp.n_vec > 1) gb[u] = __ldg(sp + 1);
+      }
+    }
 #pragma unroll 1
-  for (int j0 = 0; j0 < p.n_tiny; j0 += 4) {
+    for (int f = 0; f < p.n_tiny_fields; ++f) {
+      const TinyField& fld = p.tiny_fields[f];
+      uint4 a = ga[0], b = gb[0];
+#pragma unroll
+      for (int u = 1; u < kMaxTinyGroups; ++u)
+        if (fld.group == u) { a = ga[u]; b = gb[u]; }
+      uint32_t* dp = reinterpret_cast<uint32_t*>(fld.dst) + (size_t)g * fld.n_words;
+      const uint32_t w0 = select_word(a, b, fld.word);
+      if (fld.n_words == 1) {
+        dp[0] = w0;
+      } else if (fld.n_words == 2) {
+        *reinterpret_cast<uint2*>(dp) = make_uint2(w0, select_word(a, b, fld.word + 1u));
+      } else if (fld.n_words == 4) {
+        *reinterpret_cast<uint4*>(dp) = (fld.word & 4u) ? b : a;
+      } else {
+        dp[0] = w0; dp[1] = select_word(a, b, fld.word + 1u); dp[2] = select_word(a, b, fld.word + 2u);
+      }
+    }
+  }
+
+  // rows of <= 16 bytes: this thread copies them now (datasets.py:78-83 for the per-transition fields).  Rows of 4, 8
+  // or 16 bytes (the host lists them first) are loaded four jobs at a time before any is stored, so their L2 latencies
+  // overlap; any other size is copied element by element.
+#pragma unroll 1
+  for (int j0 = 0; j0 < p.n_tiny_fast; j0 += 4) {
     uint4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (j0 + u < p.n_tiny) {
+      if (j0 + u < p.n_tiny_fast) {
         const TinyJob& job = p.tiny[j0 + u];
-        const uint32_t row_bytes = job.row_bytes;
         const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * job.stride;
-        if (row_bytes == 4) v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp));
-        else if (row_bytes == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp)); v[u].x = t.x; v[u].y = t.y; }
-        else if (row_bytes == 16) v[u] = __ldg(reinterpret_cast<const uint4*>(sp));
-        else if (row_bytes == 12) {
-          v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp)); v[u].y = __ldg(reinterpret_cast<const uint32_t*>(sp) + 1);
-          v[u].z = __ldg(reinterpret_cast<const uint32_t*>(sp) + 2);
-        }
+        if (job.row_bytes == 4) v[u].x = __ldg(reinterpret_cast<const uint32_t*>(sp));
+        else if (job.row_bytes == 8) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(sp)); v[u].x = t.x; v[u].y = t.y; }
+        else v[u] = __ldg(reinterpret_cast<const uint4*>(sp));
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (j0 + u < p.n_tiny) {
+      if (j0 + u < p.n_tiny_fast) {
         const TinyJob& job = p.tiny[j0 + u];
-        const uint32_t row_bytes = job.row_bytes;
-        uint8_t* dp = job.dst + (size_t)g * row_bytes;
-        if (row_bytes == 4) *reinterpret_cast<uint32_t*>(dp) = v[u].x;
-        else if (row_bytes == 8) *reinterpret_cast<uint2*>(dp) = make_uint2(v[u].x, v[u].y);
-        else if (row_bytes == 16) *reinterpret_cast<uint4*>(dp) = v[u];
-        else if (row_bytes == 12) {
-          reinterpret_cast<uint32_t*>(dp)[0] = v[u].x; reinterpret_cast<uint32_t*>(dp)[1] = v[u].y; reinterpret_cast<uint32_t*>(dp)[2] = v[u].z;
-        } else {                                      // odd sizes: element by element
-          const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * job.stride;
-          if (job.size_log2 == 1) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
-          else if (job.size_log2 == 2) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
-          else for (uint32_t e = 0; e < row_bytes; ++e) dp[e] = __ldg(sp + e);
-        }
+        uint8_t* dp = job.dst + (size_t)g * job.row_bytes;
+        if (job.row_bytes == 4) *reinterpret_cast<uint32_t*>(dp) = v[u].x;
+        else if (job.row_bytes == 8) *reinterpret_cast<uint2*>(dp) = make_uint2(v[u].x, v[u].y);
+        else *reinterpret_cast<uint4*>(dp) = v[u];
       }
     }
+  }
+#pragma unroll 1
+  for (int j = p.n_tiny_fast; j < p.n_tiny; ++j) {
+    const TinyJob& job = p.tiny[j];
+    const uint8_t* sp = job.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, job.slot) * job.stride;
+    uint8_t* dp = job.dst + (size_t)g * job.row_bytes;
+    if (job.size_log2 == 2) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint32_t*>(dp)[e] = __ldg(reinterpret_cast<const uint32_t*>(sp) + e);
+    else if (job.size_log2 == 1) for (int e = 0; e < job.n_elem; ++e) reinterpret_cast<uint16_t*>(dp)[e] = __ldg(reinterpret_cast<const uint16_t*>(sp) + e);
+    else for (uint32_t e = 0; e < job.row_bytes; ++e) dp[e] = __ldg(sp + e);
   }
 
   if (p.crop_out != nullptr) {
@@ -402,7 +490,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
       if (kInject) {
         coin = p.in_coin;
       } else {
-        const uint4 c = draw4(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
+        const uint4 c = draw4_cold(p.key, batch_id, 0xFFFFFFFFu, PURPOSE_COIN);
         coin = unit_double(c.x, c.y);
       }
       if (coin < p.p_aug) {                                                         // :333
@@ -412,7 +500,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
           cx = (int)p.in_crop[2 * g + 1];
         } else {
           const uint32_t span = 2u * (uint32_t)p.crop_pad + 1u;
-          const uint4 cw = draw4(p.key, batch_id, r, PURPOSE_CROP);
+          const uint4 cw = draw4_cold(p.key, batch_id, r, PURPOSE_CROP);
           const uint32_t joint = __umulhi(cw.x, span * span);          // (cy, cx) jointly uniform on span x span
           cy = (int)(joint / span);
           cx = (int)(joint % span);
@@ -426,13 +514,26 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const int64_
   }
 }
 
-template <bool kInject, int kFlavour>
+// kSmemTables: a persistent grid (a few CTAs per SM) whose CTAs first copy the segment table into shared memory
+// (dynamic: 16 B * n_seg_table + 4 B * n_seg_bucket) and then walk the rows with a grid stride.
+template <bool kInject, int kFlavour, bool kSmemTables>
 __global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
+  extern __shared__ __align__(16) uint8_t smem_tables[];
+  SegView seg{p.seg_bucket, p.seg_table};
+  if (kSmemTables) {
+    int4* s_table = reinterpret_cast<int4*>(smem_tables);
+    int32_t* s_bucket = reinterpret_cast<int32_t*>(s_table + p.n_seg_table);
+    for (int t = threadIdx.x; t < p.n_seg_table; t += blockDim.x) s_table[t] = __ldg(p.seg_table + t);
+    for (int t = threadIdx.x; t < p.n_seg_bucket; t += blockDim.x) s_bucket[t] = __ldg(p.seg_bucket + t);
+    __syncthreads();
+    seg.bucket = s_bucket;
+    seg.table = s_table;
+  }
   for (int64_t g = p.row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.row_end; g += (int64_t)gridDim.x * blockDim.x) {
     int32_t sr[kMaxSlots];
 #pragma unroll
     for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
-    relabel_row<kInject, kFlavour>(p, g, sr);
+    relabel_row<kInject, kFlavour, kSmemTables>(p, seg, g, sr);
   }
 }
 
@@ -728,7 +829,7 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
       const AsyncJob& job = p.jobs[c.j];
       if (c.sub == 0) {                                        // entering the next (tile, job) pair
         if (kFused) {
-          if (c.j == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, ((int64_t)c.wt << 5) + lane, sr);
+          if (c.j == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, SegView{rp.seg_bucket, rp.seg_table}, ((int64_t)c.wt << 5) + lane, sr);
           issue_rows = pick_slot<kSlots>(sr, job.slot);
         } else {
           issue_rows = pref_rows;
