@@ -129,7 +129,10 @@ int ogb_dataset_destroy(ogb_dataset* ds);
 int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uint64_t seed, uint32_t stream_id,
                        ogb_sampler** out);
 int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream);    /* launch on the caller's stream instead */
-int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep_index_vectors);
+int ogb_sampler_set_debug(ogb_sampler* s, int32_t flags);         /* bit 0: keep the index vectors readable; bit 1: canary fill */
+int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks); /* batches headed for host memory (ogb_batch_copy_to_host): issue
+                                                                     big launches in up to n_chunks row chunks and copy each
+                                                                     chunk out while the next is computed */
 int ogb_sampler_set_profile(ogb_sampler* s, int32_t on);          /* record CUDA events around the dominant kernel of each call */
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out);   /* len(dataset.valid_idxs) as this sampler sees it (TRL overrides it) */
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out);
@@ -171,6 +174,7 @@ int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream);/* make a cons
 int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return */
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes); /* one key, D2H, synchronous */
 int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host); /* debug: needs set_debug(1) */
+int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad);           /* debug: needs set_debug(2); bytes written outside every key */
 int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host);       /* debug: [rows,2] applied (cy,cx), -1 if none */
 /* DLPack export of key i (DLManagedTensor*, legacy v0 ABI); the deleter drops one reference on the batch. */
 int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out_dl_managed_tensor);

@@ -84,6 +84,7 @@ SIGNATURES = [
     ('ogb_sampler_set_stream', C.c_int, [_P, _P]),
     ('ogb_sampler_set_debug', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_set_profile', C.c_int, [_P, C.c_int32]),
+    ('ogb_sampler_set_host_chunks', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_num_choices', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_num_terminals', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_write_row', C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.c_int32]),
@@ -105,6 +106,7 @@ SIGNATURES = [
     ('ogb_batch_wait_on_stream', C.c_int, [_P, _P]),
     ('ogb_batch_copy_to_host', C.c_int, [_P, _P, C.c_size_t]),
     ('ogb_batch_copy_key_to_host', C.c_int, [_P, C.c_int32, _P, C.c_size_t]),
+    ('ogb_batch_check_gaps', C.c_int, [_P, _P]),
     ('ogb_batch_index_vector', C.c_int, [_P, C.c_int32, _P]),
     ('ogb_batch_crop_shifts', C.c_int, [_P, _P]),
     ('ogb_batch_dlpack', C.c_int, [_P, C.c_int32, C.POINTER(_P)]),

@@ -251,7 +251,12 @@ struct ogb_sampler {
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
   bool debug = false;
+  bool canary = false;                   // debug: fill every batch block with 0xA5 first, so that tests can verify that
+                                         // no kernel wrote outside the keys (ogb_batch_check_gaps)
   bool profile = false;                  // record timing events around the dominant kernel of every call
+  int host_chunks = 1;                   // > 1: big launches are issued in row chunks so that the D2H copy of a finished
+                                         // chunk overlaps the kernels of the next (output='numpy' of the Python wrapper)
+  cudaStream_t copy_stream = nullptr;
   // trajectory tables
   std::vector<int32_t> term_host;
   int32_t* d_term = nullptr;
@@ -304,6 +309,8 @@ struct ogb_batch {
   int8_t* crop = nullptr;
   int n_slots = 0;
   int launches = 0;
+  std::vector<int64_t> chunk_end;                          // host-output pipelining: rows [chunk_end[c-1], chunk_end[c]) ...
+  std::vector<cudaEvent_t> chunk_done;                     // ... are complete once chunk_done[c] has fired
   cudaEvent_t prof_begin = nullptr, prof_end = nullptr;   // profile mode: brackets of the dominant kernel
   const char* dominant = "";                               // its name
   cudaEvent_t ready = nullptr;
@@ -404,6 +411,7 @@ void sampler_unref(ogb_sampler* s) {
   cudaSetDevice(s->ds->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
+  if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
   for (auto& ev : s->chunk_events) cudaEventDestroy(ev);
   for (auto& blk : s->block_cache) {
     for (cudaEvent_t ev : blk.free_after) cudaEventDestroy(ev);
@@ -435,6 +443,7 @@ void batch_unref(ogb_batch* b) {
     cudaStreamSynchronize(s->stream);
     if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
   }
+  for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
   if (b->prof_begin) cudaEventDestroy(b->prof_begin);
   if (b->prof_end) cudaEventDestroy(b->prof_end);
   if (b->escaped) cudaDeviceSynchronize();
@@ -1018,6 +1027,12 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
   s->owns_stream = false;
   return 0;
 }
+int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  if (n_chunks < 1 || n_chunks > kMaxChunks) return fail(OGB_ERR_INVALID, "n_chunks must be in [1, %d]", kMaxChunks);
+  s->host_chunks = n_chunks;
+  return 0;
+}
 int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->profile = on != 0;
@@ -1025,7 +1040,8 @@ int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) {
 }
 int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
-  s->debug = keep != 0;
+  s->debug = (keep & 1) != 0;
+  s->canary = (keep & 2) != 0;
   return 0;
 }
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) {
@@ -1232,6 +1248,15 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     if (rc) return bail(rc);
   }
   uint8_t* base = b->block;
+  if (s->canary) {
+    cudaMemsetAsync(base, 0xA5, b->block_bytes, first);
+    if (first != s->stream) {   // the gathers on the main stream must not start before the fill has finished
+      cudaEvent_t ev = s->chunk_events[s->next_event];
+      s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
+      cudaEventRecord(ev, first);
+      cudaStreamWaitEvent(s->stream, ev, 0);
+    }
+  }
   b->vec_rows = (int32_t*)(base + off_rows);
   if (want_crop) b->crop = (int8_t*)(base + off_crop);
   if (want_init) b->vec_init = (int32_t*)(base + off_init);
@@ -1768,38 +1793,54 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       cudaEventRecord(ev, st);
       g_timeline.push_back(ev);
     };
-    stamp(first);
-    const bool prof_first = s->profile && (fused_launch || gather_launches.empty());
-    if (prof_first) {
-      cudaEventCreate(&b->prof_begin);
-      cudaEventCreate(&b->prof_end);
-      cudaEventRecord(b->prof_begin, first);
-    }
-    int rc = fused_launch ? fused_launch(0, total, first) : index_launch(0, total, first);
-    if (rc) return bail(rc);
-    if (prof_first) cudaEventRecord(b->prof_end, first);
-    stamp(first);
-    if (first != s->stream) {
-      cudaEvent_t ev = s->chunk_events[s->next_event];
-      s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
-      if (cudaEventRecord(ev, first) != cudaSuccess || cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess)
-        return bail(fail(OGB_ERR_CUDA, "stream join failed"));
-    }
-    stamp(s->stream);
     // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
     // else the index kernel itself (datasets whose rows are all <= 16 bytes)
     b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather_kernel"
                 : any_async ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
-    const bool prof_gathers = s->profile && !gather_launches.empty() && !fused_launch;
-    if (prof_gathers) {
-      cudaEventCreate(&b->prof_begin);
-      cudaEventCreate(&b->prof_end);
-      cudaEventRecord(b->prof_begin, s->stream);
+    // row chunks (multiples of 32 rows, each at least kChunkMinRows): one unless the batch is headed for host memory
+    constexpr int64_t kChunkMinRows = 16384;
+    int n_chunks = 1;
+    if (s->host_chunks > 1 && !draws && total >= 2 * kChunkMinRows) n_chunks = (int)std::min<int64_t>(std::min(s->host_chunks, kMaxChunks), total / kChunkMinRows);
+    const int64_t chunk_rows = ((total + n_chunks - 1) / n_chunks + 31) / 32 * 32;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t begin = (int64_t)c * chunk_rows, end = std::min<int64_t>(total, begin + chunk_rows);
+      if (begin >= end) break;
+      stamp(first);
+      const bool prof_first = s->profile && c == 0 && n_chunks == 1 && (fused_launch || gather_launches.empty());
+      if (prof_first) {
+        cudaEventCreate(&b->prof_begin);
+        cudaEventCreate(&b->prof_end);
+        cudaEventRecord(b->prof_begin, first);
+      }
+      int rc = fused_launch ? fused_launch(begin, end, first) : index_launch(begin, end, first);
+      if (rc) return bail(rc);
+      if (prof_first) cudaEventRecord(b->prof_end, first);
+      stamp(first);
+      if (first != s->stream) {
+        cudaEvent_t ev = s->chunk_events[s->next_event];
+        s->next_event = (s->next_event + 1) % (int)s->chunk_events.size();
+        if (cudaEventRecord(ev, first) != cudaSuccess || cudaStreamWaitEvent(s->stream, ev, 0) != cudaSuccess)
+          return bail(fail(OGB_ERR_CUDA, "stream join failed"));
+      }
+      stamp(s->stream);
+      const bool prof_gathers = s->profile && c == 0 && n_chunks == 1 && !gather_launches.empty() && !fused_launch;
+      if (prof_gathers) {
+        cudaEventCreate(&b->prof_begin);
+        cudaEventCreate(&b->prof_end);
+        cudaEventRecord(b->prof_begin, s->stream);
+      }
+      for (size_t q = 0; q < gather_launches.size() && !rc; ++q) rc = gather_launches[q](begin, end, s->stream);
+      if (rc) return bail(rc);
+      if (prof_gathers) cudaEventRecord(b->prof_end, s->stream);
+      stamp(s->stream);
+      if (n_chunks > 1) {
+        cudaEvent_t done;
+        if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(done, s->stream) != cudaSuccess)
+          return bail(fail(OGB_ERR_CUDA, "chunk event failed"));
+        b->chunk_done.push_back(done);
+        b->chunk_end.push_back(end);
+      }
     }
-    for (size_t q = 0; q < gather_launches.size() && !rc; ++q) rc = gather_launches[q](0, total, s->stream);
-    if (rc) return bail(rc);
-    if (prof_gathers) cudaEventRecord(b->prof_end, s->stream);
-    stamp(s->stream);
   }
   if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
     return bail(fail(OGB_ERR_CUDA, "ready event failed"));
@@ -1976,9 +2017,28 @@ int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
 int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) {
   if (!b || !dst) return fail(OGB_ERR_INVALID, "null argument");
   if (nbytes < b->keys_bytes) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, b->keys_bytes);
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
-  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, b->sampler->stream));
-  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  ogb_sampler* s = b->sampler;
+  OGB_CUDA(cudaSetDevice(s->ds->device));
+  if (b->chunk_done.size() > 1) {
+    // pipelined: chunk c's rows of every key travel as soon as chunk c's kernels are done, on a stream of their own,
+    // while the kernels of chunk c+1 are still running
+    if (!s->copy_stream) OGB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    int64_t begin = 0;
+    for (size_t c = 0; c < b->chunk_done.size(); ++c) {
+      const int64_t end = b->chunk_end[c];
+      OGB_CUDA(cudaStreamWaitEvent(s->copy_stream, b->chunk_done[c], 0));
+      for (size_t i = 0; i < b->keys.size(); ++i) {
+        if (b->keys[i].alias_of >= 0) continue;
+        const size_t rb = b->keys[i].row_bytes, off = b->offsets[i] + (size_t)begin * rb;
+        OGB_CUDA(cudaMemcpyAsync((uint8_t*)dst + off, b->block + off, (size_t)(end - begin) * rb, cudaMemcpyDeviceToHost, s->copy_stream));
+      }
+      begin = end;
+    }
+    OGB_CUDA(cudaStreamSynchronize(s->copy_stream));
+    return 0;
+  }
+  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->stream));
+  OGB_CUDA(cudaStreamSynchronize(s->stream));
   return 0;
 }
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) {
@@ -1988,6 +2048,25 @@ int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes
   OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
   OGB_CUDA(cudaMemcpyAsync(dst, b->block + b->offsets[(size_t)i], need, cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  return 0;
+}
+// debug (ogb_sampler_set_debug(s, 2)): bytes of the key area that belong to no key must still hold the 0xA5 fill
+int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) {
+  if (!b || !n_bad) return fail(OGB_ERR_INVALID, "null argument");
+  if (!b->sampler->canary) return fail(OGB_ERR_INVALID, "the sampler was not put into canary mode before this batch was drawn");
+  std::vector<uint8_t> host(b->keys_bytes);
+  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  OGB_CUDA(cudaMemcpyAsync(host.data(), b->block, host.size(), cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  std::vector<uint8_t> owned(host.size(), 0);
+  for (size_t i = 0; i < b->keys.size(); ++i) {
+    if (b->keys[i].alias_of >= 0) continue;
+    const size_t n = (size_t)b->total_rows * b->keys[i].row_bytes;
+    std::fill(owned.begin() + (long)b->offsets[i], owned.begin() + (long)(b->offsets[i] + n), 1);
+  }
+  int64_t bad = 0;
+  for (size_t k = 0; k < host.size(); ++k) bad += (!owned[k] && host[k] != 0xA5) ? 1 : 0;
+  *n_bad = bad;
   return 0;
 }
 int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {

@@ -127,6 +127,54 @@ def test_oracle_sweep_long_trajectories(spec, layout):
         assert np.array_equal(got[k][~knife], want[k][~knife]), (k, layout)
 
 
+CANARY = [
+    # kind, obs_shape, obs dtype, act_dim, frame_stack, batch, n_batches
+    ('gc', (29,), np.float32, 8, None, 1000, 1),      # ragged last warp tile
+    ('gc', (29,), np.float32, 8, None, 33, 40),       # batch not a multiple of 32, many batches
+    ('gc', (2,), np.float32, 2, None, 77, 5),         # everything tiny: index kernel only
+    ('hgc', (69,), np.float32, 21, None, 250, 3),     # long rows: 16-row items, split launch
+    ('hgc', (55,), np.float32, 5, None, 4096, 9),     # big enough for the auxiliary-stream path (>= 32768 rows)
+    ('gc', (7,), np.float16, 3, None, 129, 3),        # 14-byte rows: two-byte element drain
+    ('gc', (13,), np.uint8, 5, None, 95, 2),          # odd-sized byte rows
+    ('gc', (64, 64, 3), np.uint8, 5, 3, 19, 2),       # frames (TMA) + small record span
+    ('gc', (20, 12, 4), np.uint8, 5, 3, 21, 1),       # frames (generic kernel)
+    ('gc', (300,), np.float32, 4, None, 64, 2),       # 1200-byte rows: few rows per stage
+    ('gc', (1100,), np.float32, 4, None, 40, 1),      # 4400-byte rows: register-staged kernel
+]
+
+
+@pytest.mark.parametrize('spec', CANARY, ids=[f'{s[0]}-{"x".join(map(str, s[1]))}-{np.dtype(s[2]).name}-B{s[5]}x{s[6]}' for s in CANARY])
+def test_no_writes_outside_the_keys(spec):
+    """Canary mode: the batch block is filled with 0xA5 before the kernels run; afterwards every byte that belongs to no
+    key (the alignment gaps between keys) must be untouched, and gathered keys must be exact copies of dataset rows."""
+    import ctypes as C
+    from ogbench_b200 import _native
+
+    kind, obs_shape, dtype, act_dim, fs, B, K = spec
+    pixel = len(obs_shape) == 3
+    seed = abs(hash(str(spec))) % 1000
+    lengths = ragged(seed, 12 if pixel else 160, 4, 20 if pixel else 120)
+    fields = toy_fields(seed, lengths, obs_shape, act_dim, dtype)
+    if np.dtype(dtype) == np.float16:
+        fields['observations'] = np.random.default_rng(seed).standard_normal((len(fields['terminals']), *obs_shape)).astype(np.float16)
+    config = cfg(frame_stack=fs, p_aug=0.5 if pixel else 0.0, subgoal_steps=5)
+    sampler = device_sampler(fields, config, kind, seed=seed)
+    sampler._sampler.set_debug(3)
+    for evaluation in (False, True):
+        handle = sampler._sampler.sample_native(B, n_batches=K, evaluation=evaluation)
+        bad = C.c_int64(-1)
+        _native.check(_native.lib().ogb_batch_check_gaps(handle.ptr, C.byref(bad)))
+        assert bad.value == 0, (spec, evaluation)
+        out = to_host(sampler._sampler.wrap(handle))
+        n = B * K
+        idx = np.empty(n, dtype=np.int64)
+        _native.check(_native.lib().ogb_batch_index_vector(handle.ptr, 0, idx.ctypes.data_as(C.c_void_p)))
+        assert np.array_equal(out['actions'].reshape(n, -1), fields['actions'][idx])
+        assert np.array_equal(out['terminals'].reshape(n), fields['terminals'][idx])
+        if fs is None:
+            assert np.array_equal(out['observations'].reshape(n, *obs_shape), fields['observations'][idx])
+
+
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')
     sampler = device_sampler(case['fields'], case['cfg'], 'hgc')
