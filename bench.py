@@ -218,6 +218,7 @@ def run_gpu_arm(args):
 
     rank, world, local = dist_util.env_rank()
     torch.cuda.set_device(local)
+    numa = dist_util.bind_to_gpu_numa(local) if world > 1 and not os.environ.get('OGB_NO_NUMA_BIND') else None
     dist_util.init('nccl', device=torch.device('cuda', local))
     w = synthetic.WORKLOADS[args.config]
     L = args.batches_per_launch or default_batches_per_launch(w)
@@ -320,7 +321,7 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
         dt = dist_util.reduce_scalar(dt, 'max', device=f'cuda:{local}')
-        e2e = {'value': world * steps_e * rows / dt, 'unit': UNIT, 'h2d_bytes_per_step': rows * 8, 'd2h_bytes_per_step': int(d2h),
+        e2e = {'value': world * steps_e * rows / dt, 'unit': UNIT, 'numa_bound': numa is not None, 'h2d_bytes_per_step': rows * 8, 'd2h_bytes_per_step': int(d2h),
                'steps': steps_e, 'batches_per_step': Le, 'api': "GCDataset(..., output='numpy').sample_many(L, B, idxs=host)"}
         lib.ogb_host_free(pinned)
 

@@ -1231,7 +1231,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       if (k.route == ROUTE_ROW && k.alias_of < 0 && takes_async_path(ds->fields[(size_t)k.field])) fuse = true;
   // Image batches are few rows with long gathers: their (latency-bound) index kernel always goes to the auxiliary
   // stream, where it runs under the frame gathers of the previous call.
-  const bool use_aux = !fuse && !no_overlap && (total >= kOverlapMinRows || any_frames);
+  bool any_gather = any_frames;            // is there a gather launch for the index kernel to hide under?
+  for (const KeyPlan& k : plan)
+    if (k.route == ROUTE_ROW && k.alias_of < 0 && ds->fields[(size_t)k.field].row_bytes > 16) any_gather = true;
+  const bool use_aux = !fuse && !no_overlap && any_gather && (total >= kOverlapMinRows || any_frames);
   if (use_aux) {
     int rc = ensure_aux(s);
     if (rc) return bail(rc);

@@ -32,6 +32,39 @@ def init(backend: str, device=None):
     return rank, world
 
 
+def _parse_cpulist(text: str):
+    cpus = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned host buffers of the
+    host-output path are first-touched on that node and the D2H copies do not cross the inter-socket link.  Returns
+    (numa_node, n_cpus) or None when the topology is not exposed (single node, container without sysfs).  Only
+    narrows the affinity the process already has."""
+    try:
+        import torch
+
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read())
+        if node < 0:
+            return None
+        cpus = set(_parse_cpulist(open(f'/sys/devices/system/node/node{node}/cpulist').read()))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, len(allowed)
+    except Exception:
+        return None
+
+
 def barrier():
     import torch.distributed as dist
 
