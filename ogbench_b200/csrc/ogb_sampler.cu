@@ -251,6 +251,7 @@ struct ogb_sampler {
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
   bool debug = false;
+  bool prefer_ws = false;                // debug bit 2: use the warp-specialised fused kernel
   bool canary = false;                   // debug: fill every batch block with 0xA5 first, so that tests can verify that
                                          // no kernel wrote outside the keys (ogb_batch_check_gaps)
   bool profile = false;                  // record timing events around the dominant kernel of every call
@@ -1042,6 +1043,7 @@ int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->debug = (keep & 1) != 0;
   s->canary = (keep & 2) != 0;
+  s->prefer_ws = (keep & 4) != 0;
   return 0;
 }
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) {
@@ -1619,6 +1621,14 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       std::shared_ptr<FusedParams> keep(fp);
       const int flavour = p.kind == OGB_KIND_GC ? FLAVOUR_GC : (p.kind == OGB_KIND_HGC ? FLAVOUR_HGC : FLAVOUR_PLAIN);
       const bool inject = draws != nullptr;
+      // large launches: the warp-specialised form (index warps feed the gather warps through a shared-memory queue)
+      // Measured on B200: equal to the same-warp fusion on C2 (0.200 vs 0.203 ms) and slower on C5 (0.371 vs 0.361 ms) --
+      // the index algebra costs the SM the same whichever warp runs it -- so it is off unless asked for
+      // (OGB_WS=1 or ogb_sampler_set_debug bit 2).
+      static const char* ws_env = getenv("OGB_WS");
+      const int n_slots_fl = flavour == FLAVOUR_GC ? GC_TRL_NUM_SLOTS : (flavour == FLAVOUR_HGC ? HGC_NUM_SLOTS : 2);
+      const size_t ws_smem = smem + (size_t)kAsyncWarps * ((size_t)kQueueDepth * n_slots_fl * 128 + 16 * kQueueDepth);
+      const bool ws = (ws_env ? atoi(ws_env) != 0 : s->prefer_ws) && ws_smem <= 113 * 1024;
       fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
@@ -1626,16 +1636,21 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         const int64_t n_warp_tiles = (end - begin + 31) / 32;
         const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * ctas_per_sm);
         const void* fn = nullptr;
-        if (inject) fn = flavour == FLAVOUR_GC ? (const void*)relabel_gather_kernel<true, FLAVOUR_GC>
-                       : flavour == FLAVOUR_HGC ? (const void*)relabel_gather_kernel<true, FLAVOUR_HGC>
-                                                : (const void*)relabel_gather_kernel<true, FLAVOUR_PLAIN>;
-        else fn = flavour == FLAVOUR_GC ? (const void*)relabel_gather_kernel<false, FLAVOUR_GC>
-                : flavour == FLAVOUR_HGC ? (const void*)relabel_gather_kernel<false, FLAVOUR_HGC>
-                                         : (const void*)relabel_gather_kernel<false, FLAVOUR_PLAIN>;
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+#define OGB_PICK_FUSED(KERNEL, INJ)                                                      \
+        fn = flavour == FLAVOUR_GC ? (const void*)KERNEL<INJ, FLAVOUR_GC>                   \
+           : flavour == FLAVOUR_HGC ? (const void*)KERNEL<INJ, FLAVOUR_HGC>                 \
+                                    : (const void*)KERNEL<INJ, FLAVOUR_PLAIN>
+        if (ws && inject) { OGB_PICK_FUSED(relabel_gather_ws_kernel, true); }
+        else if (ws) { OGB_PICK_FUSED(relabel_gather_ws_kernel, false); }
+        else if (inject) { OGB_PICK_FUSED(relabel_gather_kernel, true); }
+        else { OGB_PICK_FUSED(relabel_gather_kernel, false); }
+#undef OGB_PICK_FUSED
+        const size_t smem_bytes = ws ? ws_smem : smem;
+        const unsigned threads = ws ? (kAsyncWarps + kIndexWarps) * 32 : kAsyncWarps * 32;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
           return fail(OGB_ERR_CUDA, "cudaFuncSetAttribute(relabel_gather_kernel) failed");
         void* args[] = {(void*)&f};
-        if (cudaLaunchKernel(fn, dim3(grid), dim3(kAsyncWarps * 32), args, smem, st) != cudaSuccess)
+        if (cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem_bytes, st) != cudaSuccess)
           return fail(OGB_ERR_CUDA, "relabel_gather_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         b->launches++;
         return 0;
@@ -1798,7 +1813,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     };
     // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
     // else the index kernel itself (datasets whose rows are all <= 16 bytes)
-    b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather_kernel"
+    b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather"
                 : any_async ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
     // row chunks (multiples of 32 rows, each at least kChunkMinRows): one unless the batch is headed for host memory
     constexpr int64_t kChunkMinRows = 16384;

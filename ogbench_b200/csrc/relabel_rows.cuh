@@ -733,6 +733,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v;
 }
 
+// Output rows are written once and read by another kernel much later: store them with the streaming (evict-first)
+// policy so that they do not push dataset rows out of L2 (OGB_PLAIN_STORES at build time restores plain stores).
+// (The converse hint -- loading the rows with an L2 evict-last policy -- was measured as well: no effect on C2/C3/C5.)
+__device__ __forceinline__ void store_out(uint4* p, const uint4 v) {
+#ifdef OGB_PLAIN_STORES
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+
 // generic element drain (rows whose size is not a multiple of 4 bytes): flat element index, coalesced stores
 template <typename V>
 __device__ __forceinline__ void drain_flat(const uint8_t* __restrict__ sbase, uint8_t* __restrict__ dbase, const uint32_t n_elem,
@@ -757,7 +768,7 @@ __device__ __forceinline__ void drain_words(const uint32_t sbase, uint8_t* __res
     const uint32_t a2 = sbase + 4u * w + 8u + gap * fast_div(w + 2u, epr_magic);
     const uint32_t a3 = sbase + 4u * w + 12u + gap * fast_div(w + 3u, epr_magic);
     const uint32_t v0 = lds32(a0), v1 = lds32(a1), v2 = lds32(a2), v3 = lds32(a3);
-    reinterpret_cast<uint4*>(dbase)[q] = make_uint4(v0, v1, v2, v3);
+    store_out(reinterpret_cast<uint4*>(dbase) + q, make_uint4(v0, v1, v2, v3));
   }
   for (uint32_t w = (n_quads << 2) + lane; w < n_words; w += 32)    // ragged last tile only
     reinterpret_cast<uint32_t*>(dbase)[w] = lds32(sbase + 4u * w + gap * fast_div(w, epr_magic));
@@ -774,7 +785,7 @@ __device__ __forceinline__ void drain_words_unaligned(const uint32_t sbase, uint
 __device__ __forceinline__ void drain_dense16(const uint32_t sbase, uint8_t* __restrict__ dbase, const uint32_t n_bytes, const int lane) {
   const uint32_t n16 = n_bytes >> 4;
 #pragma unroll 2
-  for (uint32_t i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dbase)[i] = lds128(sbase + (i << 4));
+  for (uint32_t i = lane; i < n16; i += 32) store_out(reinterpret_cast<uint4*>(dbase) + i, lds128(sbase + (i << 4)));
 }
 
 struct ItemCursor {
@@ -790,8 +801,41 @@ struct ItemCursor {
 // then a single launch.
 // (A TMA variant -- one cp.async.bulk per source row instead of 16-byte LDGSTS chunks -- was measured and dropped:
 // equal on 224/288-byte rows, 17 % slower on 128-byte rows.)
-template <bool kFused, bool kInject, int kFlavour>
-__device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& p, const RelabelParams& rp, uint8_t* smem_ring) {
+// Warp-specialised form (MODE_QUEUE): kIndexWarps extra warps per CTA run relabel_row for the tiles of the gather warps
+// and hand the rows of every slot over through a small shared-memory queue (kQueueDepth tiles per gather warp, one
+// full/empty mbarrier pair per queue slot), so the L2 lookup latency of the index algebra is taken by warps that hold
+// no cp.async ring and the gather warps never stop issuing.
+constexpr int kIndexWarps = 3;
+constexpr int kQueueDepth = 2;
+enum : int { MODE_VECTORS = 0, MODE_FUSED = 1, MODE_QUEUE = 2 };
+
+struct QueueView {          // shared-memory addresses of one gather warp's queue
+  uint32_t rows;            // int32 [kQueueDepth][kSlots][32]
+  uint32_t full;            // uint64 mbarrier [kQueueDepth]
+  uint32_t empty;           // uint64 mbarrier [kQueueDepth]
+};
+
+__device__ __forceinline__ void queue_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void queue_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void queue_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "QUEUE_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni QUEUE_WAIT_DONE;\n\t"
+      "bra.uni QUEUE_WAIT_LOOP;\n\t"
+      "QUEUE_WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+template <int kMode, bool kInject, int kFlavour>
+__device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& p, const RelabelParams& rp, uint8_t* smem_ring,
+                                                       const QueueView qv) {
+  constexpr bool kFused = kMode != MODE_VECTORS;
   constexpr int kSlots = FlavourSlots<kFlavour>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int32_t n_warps_global = (int32_t)gridDim.x * kAsyncWarps;
@@ -823,13 +867,25 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
   };
   int32_t pref_rows = 0;
   if (!kFused) pref_rows = load_rows(first_tile, 0);
+  uint32_t queue_k = 0;                  // MODE_QUEUE: ordinal of the next tile this warp takes from its queue
 
   auto issue = [&](const ItemCursor& c, const uint32_t stage_u32) {
     if (c.wt < n_warp_tiles) {
       const AsyncJob& job = p.jobs[c.j];
       if (c.sub == 0) {                                        // entering the next (tile, job) pair
-        if (kFused) {
+        if (kMode == MODE_FUSED) {
           if (c.j == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, SegView{rp.seg_bucket, rp.seg_table}, ((int64_t)c.wt << 5) + lane, sr);
+          issue_rows = pick_slot<kSlots>(sr, job.slot);
+        } else if (kMode == MODE_QUEUE) {
+          if (c.j == 0) {                                      // take this tile's rows from the index warps
+            const uint32_t qs = queue_k % kQueueDepth;
+            queue_mbar_wait(qv.full + 8u * qs, (queue_k / kQueueDepth) & 1u);
+#pragma unroll
+            for (int v = 0; v < kSlots; ++v) sr[v] = (int32_t)lds32(qv.rows + ((qs * kSlots + (uint32_t)v) * 32u + (uint32_t)lane) * 4u);
+            __syncwarp();
+            if (lane == 0) queue_mbar_arrive(qv.empty + 8u * qs);
+            ++queue_k;
+          }
           issue_rows = pick_slot<kSlots>(sr, job.slot);
         } else {
           issue_rows = pref_rows;
@@ -918,7 +974,7 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
 
 __global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
   extern __shared__ __align__(128) uint8_t smem_ring[];
-  gather_rows_async_body<false, false, FLAVOUR_PLAIN>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_ring);
+  gather_rows_async_body<MODE_VECTORS, false, FLAVOUR_PLAIN>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_ring, QueueView{0, 0, 0});
 }
 
 struct FusedParams {
@@ -930,7 +986,61 @@ struct FusedParams {
 template <bool kInject, int kFlavour>
 __global__ void __launch_bounds__(kAsyncWarps * 32) relabel_gather_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ __align__(128) uint8_t smem_ring[];
-  gather_rows_async_body<true, kInject, kFlavour>(p.gather, p.relabel, smem_ring);
+  gather_rows_async_body<MODE_FUSED, kInject, kFlavour>(p.gather, p.relabel, smem_ring, QueueView{0, 0, 0});
+}
+
+// sample() in one launch, warp-specialised: warps [0, kAsyncWarps) gather, warps [kAsyncWarps, +kIndexWarps) run the
+// index algebra ahead of them.  Dynamic shared memory: the rings, then the row queues, then the mbarriers.
+template <bool kInject, int kFlavour>
+__global__ void __launch_bounds__((kAsyncWarps + kIndexWarps) * 32) relabel_gather_ws_kernel(const __grid_constant__ FusedParams p) {
+  constexpr int kSlots = FlavourSlots<kFlavour>::value;
+  extern __shared__ __align__(128) uint8_t smem_ring[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ring_bytes = (uint32_t)kAsyncWarps * kAsyncStages * (uint32_t)p.gather.stage_bytes;
+  const uint32_t queue_u32 = (uint32_t)__cvta_generic_to_shared(smem_ring) + ring_bytes;
+  constexpr uint32_t kQueueBytesPerWarp = kQueueDepth * kSlots * 32 * 4;
+  const uint32_t bars_u32 = queue_u32 + (uint32_t)kAsyncWarps * kQueueBytesPerWarp;
+  auto view_of = [&](int w) { return QueueView{queue_u32 + (uint32_t)w * kQueueBytesPerWarp, bars_u32 + (uint32_t)w * (16u * kQueueDepth),
+                                               bars_u32 + (uint32_t)w * (16u * kQueueDepth) + 8u * kQueueDepth}; };
+  if (threadIdx.x < kAsyncWarps * kQueueDepth * 2) queue_mbar_init(bars_u32 + 8u * threadIdx.x, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  if (warp < kAsyncWarps) {
+    gather_rows_async_body<MODE_QUEUE, kInject, kFlavour>(p.gather, p.relabel, smem_ring, view_of(warp));
+    return;
+  }
+  // ---- index warps ----
+  const RelabelParams& rp = p.relabel;
+  const int ix = warp - kAsyncWarps;
+  const int32_t n_warps_global = (int32_t)gridDim.x * kAsyncWarps;
+  const int32_t n_warp_tiles = (int32_t)((p.gather.row_end + 31) >> 5);
+  const int32_t last_n = (int32_t)(p.gather.row_end - ((int64_t)(n_warp_tiles - 1) << 5));
+  const int32_t tile0 = (int32_t)(p.gather.row_begin >> 5) + (int32_t)blockIdx.x * kAsyncWarps;
+  const SegView seg{rp.seg_bucket, rp.seg_table};
+#pragma unroll 1
+  for (uint32_t k = 0;; ++k) {
+    bool any = false;
+#pragma unroll 1
+    for (int w = ix; w < kAsyncWarps; w += kIndexWarps) {
+      const int64_t tile = (int64_t)tile0 + w + (int64_t)k * n_warps_global;
+      if (tile >= n_warp_tiles) continue;
+      any = true;
+      const QueueView qv = view_of(w);
+      const uint32_t qs = k % kQueueDepth;
+      queue_mbar_wait(qv.empty + 8u * qs, ((k / kQueueDepth) & 1u) ^ 1u);     // first round: passes at once
+      const int n = tile == n_warp_tiles - 1 ? last_n : 32;
+      int32_t sr[kMaxSlots];
+#pragma unroll
+      for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
+      if (lane < n) relabel_row<kInject, kFlavour>(rp, seg, (tile << 5) + lane, sr);
+#pragma unroll
+      for (int v = 0; v < kSlots; ++v) sts32(qv.rows + ((qs * kSlots + (uint32_t)v) * 32u + (uint32_t)lane) * 4u, sr[v]);
+      __syncwarp();
+      if (lane == 0) queue_mbar_arrive(qv.full + 8u * qs);
+    }
+    if (!any) break;
+  }
 }
 
 }  // namespace ogb

@@ -88,6 +88,22 @@ def test_philox_mode_is_the_oracle_on_philox_draws(case):
             assert np.array_equal(got[k][ok], want[k][ok]), (k, call)
 
 
+def test_warp_specialised_kernel_equals_default():
+    """The optional warp-specialised fused kernel (index warps feeding gather warps through a shared-memory queue with
+    mbarriers) must produce the very same batches as the default kernels, small and large launches, ragged tail."""
+    lengths = ragged(21, 300, 30, 200)
+    fields = toy_fields(21, lengths, (29,), 8, np.float32)
+    config = cfg()
+    a = device_sampler(fields, config, 'gc', seed=5)
+    b = device_sampler(fields, config, 'gc', seed=5)
+    b._sampler.set_debug(4)
+    for K, B in ((1, 1000), (40, 1024), (3, 77)):
+        x, y = to_host(a.sample_many(K, B)), to_host(b.sample_many(K, B))
+        assert set(x) == set(y)
+        for k in x:
+            assert np.array_equal(x[k], y[k]), (k, K, B)
+
+
 def test_sample_many_equals_successive_calls():
     lengths = ragged(7, 60, 2, 90)
     fields = toy_fields(7, lengths, (11,), 3, np.float32)
