@@ -175,6 +175,28 @@ def test_no_writes_outside_the_keys(spec):
             assert np.array_equal(out['observations'].reshape(n, *obs_shape), fields['observations'][idx])
 
 
+def test_mixed_dtypes_against_oracle():
+    """float64 observations, discrete int32 actions (powderworld, ogbench/utils.py:197-198), extra int64 / bool / 2-D
+    fields: every dataset field is gathered at the sampled rows (datasets.py:78-83), whatever its dtype."""
+    rng = np.random.default_rng(3)
+    lengths = ragged(3, 120, 18, 70)
+    base = toy_fields(3, lengths, (9,), 2, np.float32)
+    n = len(base['terminals'])
+    fields = dict(base, observations=rng.standard_normal((n, 9)), actions=rng.integers(0, 5, n).astype(np.int32),
+                  step_id=np.arange(n, dtype=np.int64), flag=rng.integers(0, 2, n).astype(bool),
+                  qpos=rng.standard_normal((n, 3, 2)).astype(np.float32))
+    config = cfg()
+    for kind in ('gc', 'hgc'):
+        c = dict(config, subgoal_steps=6) if kind == 'hgc' else config
+        sampler = device_sampler(fields, c, kind, rng='numpy', output='numpy')
+        for it in range(2):
+            np.random.seed(40 + it)
+            _, want = oracle_with_draws(fields, c, kind, 777)
+            np.random.seed(40 + it)
+            got = sampler.sample(777)
+            assert_batches_identical(got, want, label=f'mixed/{kind}/{it}:')
+
+
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')
     sampler = device_sampler(case['fields'], case['cfg'], 'hgc')
