@@ -202,6 +202,19 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+L2_BYTES = 126e6
+
+
+def l2_note(out_bytes, resident_bytes):
+    """How the timed loop relates to the 126 MB L2: outputs rotate through three blocks, inputs are random rows of the
+    resident dataset."""
+    out = (f'each step writes {out_bytes / 1e6:.0f} MB into one of three rotating output blocks '
+           f'({"each larger than" if out_bytes > L2_BYTES else "together " + ("larger" if 3 * out_bytes > L2_BYTES else "smaller") + " than"} the 126 MB L2)')
+    src = (f'and gathers random rows of a {resident_bytes / 1e6:.0f} MB resident dataset '
+           f'({"larger than L2" if resident_bytes > L2_BYTES else "smaller than L2: it stays cache-resident, as the real dataset of this shape would"})')
+    return out + ' ' + src
+
+
 def default_batches_per_launch(w):
     # ~1M transitions per launch for vector workloads, 16 batches for the pixel workload: ~1.1 GB of output per launch
     # in both cases (>> 126 MB L2)
@@ -351,8 +364,7 @@ def run_gpu_arm(args):
             'workload': w.name, 'key': w.key, 'rows_resident_per_gpu': w.rows, 'batch': w.batch, 'batches_per_launch': L,
             'transitions_per_step_per_gpu': per_step, 'rng': 'on-device Philox4x32-10',
             'placement': 'trajectory-aligned shard per GPU' if args.config == 'c5' else 'replica per GPU',
-            'l2': f'each step writes {w.bytes_per_transition * per_step // 2 / 1e6:.0f} MB of fresh output (> 126 MB L2) '
-                  f'and gathers from a {dataset.native(local).resident_bytes() / 1e6:.0f} MB resident dataset',
+            'l2': l2_note(w.bytes_per_transition * per_step // 2, dataset.native(local).resident_bytes()),
         },
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                      'kernel': kernel_name, 'kernel_ms': kernel_ms, 'bytes_per_transition': w.bytes_per_transition,
