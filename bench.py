@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--config', default='c2', help='workload key (c1..c5), SURVEY.md 8(d); c2 is the headline config')
+    ap.add_argument('--config', default='c2', help='workload key (c1..c5, c3b/c4b/c5b), SURVEY.md 8(d); c2 is the headline config')
     ap.add_argument('--batches-per-launch', type=int, default=None)
     ap.add_argument('--e2e-batches', type=int, default=None, help='batches per e2e step')
     ap.add_argument('--cpu-seconds', type=float, default=10.0, help='budget of the cpu_baseline leg')
@@ -237,7 +237,7 @@ def run_gpu_arm(args):
     L = args.batches_per_launch or default_batches_per_launch(w)
 
     # each rank holds a replica (c1-c4) or its own trajectory-aligned shard (c5), generated directly in HBM
-    fields = synthetic.device_fields(w, device=local, seed=w.seed + (rank if args.config == 'c5' else 0))
+    fields = synthetic.device_fields(w, device=local, seed=w.seed + (rank if args.config.startswith('c5') else 0))
     dataset = Dataset.create(**fields)
     cls = GCDataset if w.kind == 'gc' else HGCDataset
     sampler = cls(dataset, w.config, device=local, seed=1234, stream_id=rank)
@@ -363,7 +363,7 @@ def run_gpu_arm(args):
         'config': {
             'workload': w.name, 'key': w.key, 'rows_resident_per_gpu': w.rows, 'batch': w.batch, 'batches_per_launch': L,
             'transitions_per_step_per_gpu': per_step, 'rng': 'on-device Philox4x32-10',
-            'placement': 'trajectory-aligned shard per GPU' if args.config == 'c5' else 'replica per GPU',
+            'placement': 'trajectory-aligned shard per GPU' if args.config.startswith('c5') else 'replica per GPU',
             'l2': l2_note(w.bytes_per_transition * per_step // 2, dataset.native(local).resident_bytes()),
         },
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,

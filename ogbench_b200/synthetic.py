@@ -50,6 +50,20 @@ WORKLOADS: Dict[str, Workload] = {
                    (64, 64, 3), 'uint8', 5, 'gc', 256, dict(_GCIQL, frame_stack=3, p_aug=0.5), 270408, 3),
     'c5': Workload('c5', 'cube-quadruple-play-100M shape, 1/8 trajectory-aligned shard per GPU, GCDataset, batch 4096', 12500, 1001,
                    (55,), 'float32', 5, 'gc', 4096, dict(_GCIQL), 1832, 4),
+    # ---- secondary runs named in SURVEY.md 8(d) (same shapes, the benchmark's other sampler settings) ----
+    # HIQL on humanoidmaze-giant with the benchmark's own subgoal_steps=100 (hyperparameters.sh:285)
+    'c3b': Workload('c3b', 'humanoidmaze-giant-navigate-v0 shape, HGCDataset (HIQL, subgoal_steps=100), batch 1024', 1000, 4001,
+                    (69,), 'float32', 21, 'hgc', 1024, dict(_GCIQL, discount=0.995, subgoal_steps=100), 4120, 2),
+    # HIQL on pixels, subgoal_steps=10 (hyperparameters.sh:857): 7 stacked images written, 19 distinct frames read
+    'c4b': Workload('c4b', 'visual-cube-double-play-v0 shape (64x64x3 u8), HGCDataset (HIQL, subgoal_steps=10), frame_stack=3, '
+                    'p_aug=0.5, batch 256', 1000, 1001, (64, 64, 3), 'uint8', 5, 'hgc', 256,
+                    dict(_GCIQL, frame_stack=3, p_aug=0.5, subgoal_steps=10), 7 * 36864 + 9 * 8 + 28 + 19 * 12288 + 28, 3),
+    # SHARSA's sampler settings (sharsa.py:410-422) on the 100M-shape shard: 7 distinct row gathers
+    'c5b': Workload('c5b', 'cube-quadruple-play-100M shape, 1/8 trajectory-aligned shard per GPU, HGCDataset (SHARSA mix), batch 4096',
+                    12500, 1001, (55,), 'float32', 5, 'hgc', 4096,
+                    dict(_GCIQL, value_geom_sample=False, actor_p_curgoal=0.0, actor_p_trajgoal=0.5, actor_p_randomgoal=0.5,
+                         actor_geom_sample=True, gc_negative=False, discount=0.999, subgoal_steps=25),
+                    7 * 220 + 28 + 7 * 220 + 28 + 9 * 8, 4),
 }
 
 
