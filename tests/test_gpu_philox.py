@@ -267,3 +267,86 @@ def test_full_size_properties_c2():
     assert ((ag > i) | (i == final)).all() and (ag <= final).all()
     assert np.array_equal(out['masks'], (vg != i).astype(np.float64)) and np.array_equal(out['rewards'], out['masks'] * -1.0)
     assert np.array_equal(out['value_goals'], fields['observations'][vg])
+
+
+def _torch_batch(batch):
+    import torch
+
+    return {k: torch.from_dlpack(v) for k, v in batch.items()}
+
+
+def test_full_size_properties_c3_hgc():
+    """BASELINE shape (4,001,000 x 69, HIQL subgoal_steps=25): the HGC index algebra (datasets.py:478-491, :505-619)
+    checked on a 1M-transition launch through relations that hold for every row, on the device (no 1 GB host copy)."""
+    import torch
+
+    from ogbench_b200 import Dataset, HGCDataset, synthetic
+
+    w = synthetic.WORKLOADS['c3']
+    fields = synthetic.device_fields(w)
+    n = w.rows
+    fields['observations'][:, 0] = torch.arange(n, dtype=torch.float32, device='cuda')      # exact below 2^24
+    obs, act = fields['observations'], fields['actions']
+    s = HGCDataset(Dataset.create(**fields), w.config, seed=11)
+    out = _torch_batch(s.sample_many(1024, w.batch))
+    torch.cuda.synchronize()
+    k = w.config['subgoal_steps']
+    row = lambda key: out[key][..., 0].long().reshape(-1)
+    i = row('observations')
+    final = (i // w.steps) * w.steps + w.steps - 2
+    flat = lambda key: out[key].reshape(-1, *out[key].shape[2:])
+    assert torch.equal(flat('observations'), obs[i]) and torch.equal(flat('actions'), act[i])
+    assert torch.equal(row('next_observations'), i + 1)
+    hv, ha = row('high_value_goals'), row('high_actor_goals')
+    assert torch.equal(flat('high_value_goals'), obs[hv]) and torch.equal(flat('value_goals'), obs[hv])
+    assert (hv <= torch.maximum(final, hv)).all() and ((ha > i) | (i == final)).all() and (ha <= final).all()
+    steps = out['high_value_subgoal_steps'].reshape(-1)
+    d = hv - i
+    want_steps = torch.minimum(torch.full_like(i, k), final - i)
+    want_steps = torch.where((d >= 0) & (d < want_steps), d, want_steps)
+    assert torch.equal(steps, want_steps)
+    assert torch.equal(row('high_value_next_observations'), i + steps) and torch.equal(row('high_value_actions'), i + steps)
+    assert torch.equal(out['high_value_offsets'].reshape(-1), d)
+    succ = (steps < k).double()
+    assert torch.equal(out['high_value_masks'].reshape(-1), 1.0 - succ)
+    lut = torch.from_numpy(-(1 - w.config['discount'] ** np.arange(k + 1)) / (1 - w.config['discount'])).cuda()
+    assert torch.equal(out['high_value_rewards'].reshape(-1), lut[steps])                    # numpy-built table, bit-exact
+    assert torch.equal(out['low_value_subgoal_steps'].reshape(-1), steps)                    # low_subgoal_steps == subgoal_steps
+    assert torch.equal(row('low_actor_goals'), torch.minimum(i + k, final))
+    assert torch.equal(out['masks'].reshape(-1), (hv != i).double()) and torch.equal(out['rewards'].reshape(-1), (hv == i).double() - 1.0)
+    da = ha - i
+    a_steps = torch.minimum(torch.full_like(i, k), final - i)
+    a_steps = torch.where((da >= 0) & (da < a_steps), da, a_steps)
+    assert torch.equal(row('high_actor_targets'), i + a_steps) and torch.equal(row('low_actor_next_observations'), i + a_steps)
+
+
+def test_full_size_properties_c5_shard():
+    """One 12.5M-row shard of the 100M shape (55-D observations, batch 4096): copies are exact, goals stay inside their
+    trajectory, random goals stay inside the shard, and the goal mix has the configured proportions."""
+    import torch
+
+    from ogbench_b200 import Dataset, GCDataset, synthetic
+
+    w = synthetic.WORKLOADS['c5']
+    fields = synthetic.device_fields(w)
+    n = w.rows
+    fields['observations'][:, 0] = torch.arange(n, dtype=torch.float32, device='cuda')      # 12,512,500 < 2^24
+    obs, act = fields['observations'], fields['actions']
+    s = GCDataset(Dataset.create(**fields), w.config, seed=3, stream_id=6)
+    out = _torch_batch(s.sample_many(256, w.batch))
+    torch.cuda.synchronize()
+    row = lambda key: out[key][..., 0].long().reshape(-1)
+    flat = lambda key: out[key].reshape(-1, *out[key].shape[2:])
+    i, vg, ag = row('observations'), row('value_goals'), row('actor_goals')
+    assert torch.equal(flat('observations'), obs[i]) and torch.equal(flat('actions'), act[i])
+    assert torch.equal(flat('value_goals'), obs[vg]) and torch.equal(flat('actor_goals'), obs[ag])
+    assert torch.equal(row('next_observations'), i + 1)
+    assert (flat('valids') == 1).all() and (i % w.steps != w.steps - 1).all()                # only valid rows are drawn
+    final = (i // w.steps) * w.steps + w.steps - 2
+    assert ((ag > i) | (i == final)).all() and (ag <= final).all()                           # actor goals: trajectory future
+    assert (vg >= 0).all() and (vg < n).all() and (vg % w.steps != w.steps - 1).all()        # goals are valid rows of the shard
+    same_traj = (vg // w.steps) == (i // w.steps)
+    cur = (vg == i).double().mean().item()
+    assert abs(cur - 0.2) < 0.01                                                             # value_p_curgoal (+ tiny geometric mass at 0? no: offsets >= 1)
+    assert abs((same_traj & (vg > i)).double().mean().item() - 0.5) < 0.02                   # value_p_trajgoal (random goals rarely land in the same trajectory)
+    assert torch.equal(out['masks'].reshape(-1), (vg != i).double())
