@@ -350,3 +350,47 @@ def test_full_size_properties_c5_shard():
     assert abs(cur - 0.2) < 0.01                                                             # value_p_curgoal (+ tiny geometric mass at 0? no: offsets >= 1)
     assert abs((same_traj & (vg > i)).double().mean().item() - 0.5) < 0.02                   # value_p_trajgoal (random goals rarely land in the same trajectory)
     assert torch.equal(out['masks'].reshape(-1), (vg != i).double())
+
+
+def test_full_size_pixels_c4():
+    """BASELINE shape (1,001,000 x 64x64x3 uint8, 12.3 GB resident, frame_stack=3, crop): every key of an augmented batch
+    against a torch restatement of datasets.py:359-366 (stack) and :17-33 (edge-padded crop) on the same rows/shifts."""
+    import ctypes as C
+
+    import torch
+
+    from ogbench_b200 import Dataset, GCDataset, _native, synthetic
+
+    w = synthetic.WORKLOADS['c4']
+    fields = synthetic.device_fields(w)
+    frames = fields['observations']
+    s = GCDataset(Dataset.create(**fields), dict(w.config, p_aug=1.0), seed=8)
+    s._sampler.set_debug(1)
+    B, K = w.batch, 4
+    handle = s._sampler.sample_native(B, n_batches=K)
+    out = _torch_batch(s._sampler.wrap(handle))
+    torch.cuda.synchronize()
+    n = B * K
+    lib = _native.lib()
+    crop = np.empty((n, 2), dtype=np.int64)
+    _native.check(lib.ogb_batch_crop_shifts(handle.ptr, crop.ctypes.data_as(C.c_void_p)))
+    assert (crop >= 0).all() and (crop <= 6).all() and len(np.unique(crop, axis=0)) > 20   # p_aug = 1: every batch is cropped
+    dy = torch.from_numpy(crop[:, 0] - 3).cuda()
+    dx = torch.from_numpy(crop[:, 1] - 3).cuda()
+    ar = torch.arange(64, device='cuda')
+    ys = (ar[None, :] + dy[:, None]).clamp(0, 63)            # out[y, x] = img[clip(y + cy - 3), clip(x + cx - 3)]
+    xs = (ar[None, :] + dx[:, None]).clamp(0, 63)
+
+    def expected(slot):
+        idx = np.empty(n, dtype=np.int64)
+        _native.check(lib.ogb_batch_index_vector(handle.ptr, slot, idx.ctypes.data_as(C.c_void_p)))
+        i = torch.from_numpy(idx).cuda()
+        first = (torch.clamp(i, max=w.rows - 1) // w.steps) * w.steps
+        first = torch.where(i % w.steps == w.steps - 1, i, first)       # a trajectory's last row starts its own segment (quirk 2)
+        stack = torch.cat([frames[torch.maximum(i - k, first)] for k in (2, 1, 0)], dim=-1)   # oldest frame first
+        rows = torch.arange(n, device='cuda')[:, None, None]
+        return stack[rows, ys[:, :, None], xs[:, None, :]]
+
+    for key, slot in (('observations', 0), ('next_observations', 1), ('value_goals', 2), ('actor_goals', 3)):
+        got = out[key].reshape(n, 64, 64, 9)
+        assert torch.equal(got, expected(slot)), key
