@@ -1512,6 +1512,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   typedef std::function<int(int64_t, int64_t, cudaStream_t)> LaunchFn;
   std::vector<LaunchFn> gather_launches;
   LaunchFn fused_launch;
+  const char* fused_name = "relabel_gather_kernel";
 
   LaunchFn index_launch = [&, p](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
     p.row_begin = begin;
@@ -1629,6 +1630,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       const int n_slots_fl = flavour == FLAVOUR_GC ? GC_TRL_NUM_SLOTS : (flavour == FLAVOUR_HGC ? HGC_NUM_SLOTS : 2);
       const size_t ws_smem = smem + (size_t)kAsyncWarps * ((size_t)kQueueDepth * n_slots_fl * 128 + 16 * kQueueDepth);
       const bool ws = (ws_env ? atoi(ws_env) != 0 : s->prefer_ws) && ws_smem <= 113 * 1024;
+      fused_name = ws ? "relabel_gather_ws_kernel" : "relabel_gather_kernel";
       fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
@@ -1813,7 +1815,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     };
     // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
     // else the index kernel itself (datasets whose rows are all <= 16 bytes)
-    b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? "relabel_gather"
+    b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? fused_name
                 : any_async ? "gather_rows_async_kernel" : !lsu_keys.empty() ? "gather_rows_kernel" : "relabel_index_kernel";
     // row chunks (multiples of 32 rows, each at least kChunkMinRows): one unless the batch is headed for host memory
     constexpr int64_t kChunkMinRows = 16384;
