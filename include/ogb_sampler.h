@@ -134,6 +134,9 @@ int ogb_sampler_set_debug(ogb_sampler* s, int32_t flags);         /* bit 0: keep
 int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks); /* batches headed for host memory (ogb_batch_copy_to_host): issue
                                                                      big launches in up to n_chunks row chunks and copy each
                                                                      chunk out while the next is computed */
+int ogb_sampler_set_deferred_index_check(ogb_sampler* s, int32_t on); /* given `idxs` are range-checked by the kernel instead of a
+                                                                     host scan; OGB_ERR_INDEX then comes from ogb_batch_copy_to_host
+                                                                     or ogb_batch_sync (batches that are read on the host anyway) */
 int ogb_sampler_set_profile(ogb_sampler* s, int32_t on);          /* record CUDA events around the dominant kernel of each call */
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out);   /* len(dataset.valid_idxs) as this sampler sees it (TRL overrides it) */
 int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out);

@@ -84,6 +84,7 @@ SIGNATURES = [
     ('ogb_sampler_set_stream', C.c_int, [_P, _P]),
     ('ogb_sampler_set_debug', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_set_profile', C.c_int, [_P, C.c_int32]),
+    ('ogb_sampler_set_deferred_index_check', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_set_host_chunks', C.c_int, [_P, C.c_int32]),
     ('ogb_sampler_num_choices', C.c_int, [_P, C.POINTER(C.c_int64)]),
     ('ogb_sampler_num_terminals', C.c_int, [_P, C.POINTER(C.c_int64)]),

@@ -251,6 +251,8 @@ struct ogb_sampler {
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
   bool debug = false;
+  bool defer_index_check = false;        // host-output mode: given indices are range-checked by the kernel, the error
+                                         // surfaces at ogb_batch_copy_to_host / ogb_batch_sync instead of at sample()
   bool prefer_ws = false;                // debug bit 2: use the warp-specialised fused kernel
   bool canary = false;                   // debug: fill every batch block with 0xA5 first, so that tests can verify that
                                          // no kernel wrote outside the keys (ogb_batch_check_gaps)
@@ -312,6 +314,7 @@ struct ogb_batch {
   int launches = 0;
   std::vector<int64_t> chunk_end;                          // host-output pipelining: rows [chunk_end[c-1], chunk_end[c]) ...
   std::vector<cudaEvent_t> chunk_done;                     // ... are complete once chunk_done[c] has fired
+  int32_t* idx_error = nullptr;                            // device flag of the deferred index check (inside the block)
   cudaEvent_t prof_begin = nullptr, prof_end = nullptr;   // profile mode: brackets of the dominant kernel
   const char* dominant = "";                               // its name
   cudaEvent_t ready = nullptr;
@@ -1034,6 +1037,11 @@ int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks) {
   s->host_chunks = n_chunks;
   return 0;
 }
+int ogb_sampler_set_deferred_index_check(ogb_sampler* s, int32_t on) {
+  if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  s->defer_index_check = on != 0;
+  return 0;
+}
 int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->profile = on != 0;
@@ -1130,9 +1138,11 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   const int64_t total = batch_size * (int64_t)n_batches;
   if (total > (int64_t)1 << 31) return fail(OGB_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
   const bool stacked_next = (cfg.frame_stack > 0 && spec.kind != OGB_KIND_PLAIN) || spec.kind == OGB_KIND_ATC;
-  if (idxs) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
+  const int64_t idx_last = (stacked_next ? ds->size - spec.next_offset : ds->size) - 1;
+  const bool defer_check = idxs && s->defer_index_check;
+  if (idxs && !defer_check) {  // numpy fancy indexing would raise IndexError (negative wrap-around is not supported here)
     // branch-free scan (vectorises): idx < 0 or idx > last sets the sign bit of idx | (last - idx)
-    const int64_t last = (stacked_next ? ds->size - spec.next_offset : ds->size) - 1;
+    const int64_t last = idx_last;
     int64_t bad = 0;
     for (int64_t r = 0; r < total; ++r) bad |= idxs[r] | (last - idxs[r]);
     if (bad < 0)
@@ -1198,6 +1208,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   if (want_init) off_init = carve((size_t)spec.n_slots * total * 4);
   if (want_crop) off_crop = carve((size_t)total * 2);
   if (idxs) off_idxs = carve((size_t)total * 8);
+  size_t off_idx_error = 0;
+  if (defer_check) off_idx_error = carve(4);
   if (draws) {
     off_draw_i64[0] = carve((size_t)batch_size * 8);
     for (int gs = 0; gs < 3; ++gs) {
@@ -1343,6 +1355,12 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   if (idxs) {
     if (h2d(off_idxs, idxs, (size_t)total * 8) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "H2D of idxs failed"));
     p.given_idxs = (const int64_t*)(base + off_idxs);
+    if (defer_check) {
+      b->idx_error = (int32_t*)(base + off_idx_error);
+      if (cudaMemsetAsync(b->idx_error, 0, 4, first) != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "memset of the index flag failed"));
+      p.idx_error = b->idx_error;
+      p.idx_last = idx_last;
+    }
   }
   if (draws) {
     cudaError_t e = cudaSuccess;
@@ -2022,6 +2040,11 @@ int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) {
 int ogb_batch_sync(ogb_batch* b) {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   OGB_CUDA(cudaEventSynchronize(b->ready));
+  if (b->idx_error) {
+    int32_t flag = 0;
+    OGB_CUDA(cudaMemcpy(&flag, b->idx_error, 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)b->sampler->ds->size);
+  }
   return 0;
 }
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
@@ -2058,7 +2081,10 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) {
     return 0;
   }
   OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->stream));
+  int32_t flag = 0;
+  if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->stream));
   OGB_CUDA(cudaStreamSynchronize(s->stream));
+  if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
   return 0;
 }
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) {

@@ -143,6 +143,8 @@ struct RelabelParams {
   const int64_t* in_crop;
   double in_coin;
   const int64_t* given_idxs;
+  int32_t* idx_error;          // deferred index check (host-output mode): set to 1 when a given index is out of range
+  int64_t idx_last;            //   largest admissible index
   // ---- launch shape ----
   int64_t batch;               // rows per sample() call
   uint64_t batch_magic;        // ceil(2^64 / batch), 0 when batch == 1: g / batch == umul64hi(g, magic) for g < 2^32
@@ -319,7 +321,12 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
   if (!kInject) w0 = draw4(p.key, batch_id, r, PURPOSE_IDX);
   int32_t i, fin = -1;
   if (p.given_idxs != nullptr) {
-    i = (int32_t)p.given_idxs[g];
+    const int64_t given = p.given_idxs[g];
+    i = (int32_t)given;
+    if (p.idx_error != nullptr && (uint64_t)given > (uint64_t)p.idx_last) {   // negative or too large: report, stay in bounds
+      *p.idx_error = 1;
+      i = 0;
+    }
   } else {
     const int64_t pos = kInject ? p.in_idx_pos[g] : (int64_t)bounded_u32n(w0.x, w0.y, (uint32_t)p.n_choices);
     if (p.valid_mode == 3) i = valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe

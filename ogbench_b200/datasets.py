@@ -360,6 +360,9 @@ class _Sampler:
         _native.check(_native.lib().ogb_sampler_create(self._nds.ptr, C.byref(cfg), kind, seed, stream_id, C.byref(out)))
         self.ptr = out
         self._finalizer = weakref.finalize(self, _native.lib().ogb_sampler_destroy, out)
+        if output == 'numpy':  # the batch is read on the host anyway: let the kernel range-check given idxs (IndexError at the copy)
+            _native.check(_native.lib().ogb_sampler_set_deferred_index_check(out, 1))
+        self._layouts: Dict[Any, Any] = {}
         # ogb_sampler_set_host_chunks(n > 1) would issue big host-bound launches in row chunks and copy each finished
         # chunk out under the next one's kernels.  Measured on B200 (C2, 67 MB per call): the 36 per-key, per-chunk copies
         # lose more PCIe efficiency (1.33 vs 1.21 ms) than the overlap gains (the kernels are 0.05 ms), so it stays off.
@@ -440,34 +443,47 @@ class _Sampler:
         _native.check(_native.lib().ogb_sampler_copy_atc_anchors(self.ptr, int(k), out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def wrap(self, handle: BatchHandle) -> Dict[str, Any]:
+    def wrap(self, handle: BatchHandle, layout_key=None) -> Dict[str, Any]:
         lib = _native.lib()
-        n = C.c_int32()
-        _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
-        infos = []
-        for i in range(n.value):
-            info = _native.KeyInfo()
-            _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
-            infos.append(info)
         if self.output == 'device':
-            return {info.name.decode(): DeviceArray(handle, i, info) for i, info in enumerate(infos)}
-        # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it
-        nbytes = C.c_size_t()
-        _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
-        block = _PINNED.take(max(nbytes.value, 1))
+            n = C.c_int32()
+            _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
+            out = {}
+            for i in range(n.value):
+                info = _native.KeyInfo()
+                _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
+                out[info.name.decode()] = DeviceArray(handle, i, info)
+            return out
+        # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it.  The layout of
+        # the block (name, dtype, shape, offset of every key) is a function of the call's shape only, so it is read once
+        # per (batch_size, n_batches, evaluation, ...) and reused.
+        layout = self._layouts.get(layout_key) if layout_key is not None else None
+        if layout is None:
+            n = C.c_int32()
+            _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
+            keys = []
+            for i in range(n.value):
+                info = _native.KeyInfo()
+                _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
+                keys.append((info.name.decode(), _native.CODE_TO_DTYPE[info.dtype], tuple(int(info.shape[d]) for d in range(info.ndim)),
+                             int(info.offset), int(info.nbytes)))
+            nbytes = C.c_size_t()
+            _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
+            layout = (max(nbytes.value, 1), keys)
+            if layout_key is not None:
+                self._layouts[layout_key] = layout
+        total, keys = layout
+        block = _PINNED.take(total)
         _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
-        raw = (C.c_ubyte * max(nbytes.value, 1)).from_address(block.ptr)
+        raw = (C.c_ubyte * total).from_address(block.ptr)
         raw._owner = block  # numpy views -> ctypes buffer -> pinned block: returned to the pool when all views die
         flat = np.frombuffer(raw, dtype=np.uint8)
-        out = {}
-        for info in infos:
-            shape = tuple(int(info.shape[d]) for d in range(info.ndim))
-            dtype = _native.CODE_TO_DTYPE[info.dtype]
-            out[info.name.decode()] = flat[info.offset:info.offset + info.nbytes].view(dtype).reshape(shape)
-        return out
+        return {name: flat[off:off + nb].view(dtype).reshape(shape) for name, dtype, shape, off, nb in keys}
 
     def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1):
-        return self.wrap(self.sample_native(batch_size, n_batches, idxs, evaluation, draws))
+        handle = self.sample_native(batch_size, n_batches, idxs, evaluation, draws)
+        n_rows = len(idxs) // int(n_batches) if idxs is not None else int(batch_size)
+        return self.wrap(handle, ('sample', n_rows, int(n_batches), bool(evaluation)))
 
 
 def _pack_draws(draws, keep) -> _native.Draws:

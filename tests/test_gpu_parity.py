@@ -224,6 +224,18 @@ def test_given_idxs_out_of_range_raises():
         sampler.sample(2, idxs=np.array([0, sampler.size]))
 
 
+def test_given_idxs_out_of_range_raises_in_host_output_mode():
+    """output='numpy': the kernel range-checks the given indices (no host scan) and the IndexError still comes out of
+    the same sample() call; a following valid call is unaffected."""
+    case = load_case('gc_state_gcivl')
+    sampler = device_sampler(case['fields'], case['cfg'], 'gc', output='numpy')
+    for bad in ([0, sampler.size], [-1, 3], [2 ** 40, 1]):
+        with pytest.raises(IndexError):
+            sampler.sample(2, idxs=np.array(bad))
+    good = sampler.sample(3, idxs=np.array([0, 1, 2]))
+    assert np.array_equal(good['observations'], case['fields']['observations'][:3])
+
+
 def test_constructor_asserts():
     from ogbench_b200 import Dataset, GCDataset
 
