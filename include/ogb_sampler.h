@@ -160,6 +160,18 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
  * observations (frame-stacked as configured; which = 0) or of the goal representation (which = 1). */
 int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out);
 
+/* The reference's helper methods, for explicit rows (host arrays in and out).
+ * GCDataset.sample_goals (datasets.py:296-327): `draws` NULL = on-device Philox (advances the sampler's counter by one),
+ * else the reference's own draws for this call (rand_pos, offset or dist, u_traj, u_cur). */
+int ogb_sampler_sample_goals(ogb_sampler* s, const int64_t* idxs, int64_t n, double p_curgoal, double p_trajgoal, int32_t geom_sample,
+                             double discount, const ogb_goal_draws* draws, int64_t* out_goal_idxs);
+/* HGCDataset.compute_high_next_idxs (datasets.py:478-491) */
+int ogb_sampler_compute_high_next_idxs(ogb_sampler* s, const int64_t* idxs, const int64_t* final_state_idxs, const int64_t* goal_idxs,
+                                       int64_t n, int64_t subgoal_steps, int64_t* out_next, int64_t* out_steps);
+/* GCDataset.augment / batched_random_crop (datasets.py:329-339, :17-33) for one image array: rows `idxs` of the
+ * observations, row r cropped at crop[r] = (cy, cx) after edge padding by `padding`. */
+int ogb_sampler_gather_cropped(ogb_sampler* s, const int64_t* idxs, int64_t n, const int64_t* crop, int32_t padding, ogb_batch** out);
+
 /* ATCDataset (datasets.py:369-464), for samplers created with OGB_KIND_ATC.  The anchor set of a temporal offset k
  * (get_valid_atc_idxs, :417-436) is built once per k and cached, like the reference's _atc_valid_cache. */
 int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out);

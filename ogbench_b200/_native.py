@@ -95,6 +95,9 @@ SIGNATURES = [
     ('ogb_sampler_destroy', C.c_int, [_P]),
     ('ogb_sampler_sample', C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.POINTER(Draws), C.POINTER(_P)]),
     ('ogb_sampler_gather', C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(_P)]),
+    ('ogb_sampler_gather_cropped', C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.POINTER(_P)]),
+    ('ogb_sampler_sample_goals', C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_double, _P, _P]),
+    ('ogb_sampler_compute_high_next_idxs', C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     ('ogb_sampler_num_atc_anchors', C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
     ('ogb_sampler_copy_atc_anchors', C.c_int, [_P, C.c_int64, _P]),
     ('ogb_sampler_sample_atc', C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.POINTER(Draws), C.POINTER(_P)]),

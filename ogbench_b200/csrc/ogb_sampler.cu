@@ -1125,6 +1125,7 @@ struct RunSpec {
   const int32_t* choice_table = nullptr; // ATC: anchor rows for this k (replaces the valid-row table)
   int64_t n_choices = -1;
   bool trl = false;
+  int crop_padding = -1;                 // >= 0: crop every image key with the injected shifts and this padding (augment())
 };
 
 int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
@@ -1152,7 +1153,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   }
   const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->active_rows : ds->n_valid);
   if (n_choices < 1) return fail(OGB_ERR_INVALID, "nothing to sample from: the dataset holds no rows yet");
-  const bool aug_mode = cfg.has_p_aug && !evaluation && spec.kind != OGB_KIND_PLAIN;
+  const bool forced_crop = spec.crop_padding >= 0;
+  const bool aug_mode = forced_crop || (cfg.has_p_aug && !evaluation && spec.kind != OGB_KIND_PLAIN);
+  const double p_aug_eff = forced_crop ? 1.0 : cfg.p_aug;
+  const int crop_pad_eff = forced_crop ? spec.crop_padding : cfg.crop_padding;
   const int n_goal_sets = (spec.kind == OGB_KIND_GC || spec.kind == OGB_KIND_HGC) ? 3 : 0;
   const bool geom[3] = {cfg.value_geom_sample != 0, true, cfg.actor_geom_sample != 0};
   const bool cur_only[3] = {cfg.value_p_curgoal == 1.0, cfg.value_p_curgoal == 1.0, cfg.actor_p_curgoal == 1.0};
@@ -1171,7 +1175,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       for (int64_t r = 0; r < batch_size; ++r)
         if (draws->idx_pos[r] < 0 || draws->idx_pos[r] >= n_choices) return fail(OGB_ERR_INDEX, "idx_pos out of range");
     if (aug_mode && !draws->has_aug_coin) return fail(OGB_ERR_INVALID, "validation mode: the augmentation coin is missing");
-    if (aug_mode && draws->aug_coin < cfg.p_aug && !draws->crop) return fail(OGB_ERR_INVALID, "validation mode: crop draws are missing");
+    if (aug_mode && draws->aug_coin < p_aug_eff && !draws->crop) return fail(OGB_ERR_INVALID, "validation mode: crop draws are missing");
   }
   OGB_CUDA(cudaSetDevice(ds->device));
   std::lock_guard<std::mutex> lock(s->mu);
@@ -1337,8 +1341,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   p.gc_negative = cfg.gc_negative;
   p.stacked_next = stacked_next;
   p.aug_mode = aug_mode;
-  p.crop_pad = cfg.crop_padding;
-  p.p_aug = cfg.p_aug;
+  p.crop_pad = crop_pad_eff;
+  p.p_aug = p_aug_eff;
   p.key = make_rng_key(s->seed, s->stream_id);
   p.batch0 = s->counter;
   p.batch = batch_size;
@@ -1766,7 +1770,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         for (int d = 1; d < f.ndim - 1; ++d) outer *= f.shape[d];
         fp.H = 1; fp.W = (int)outer; fp.inner_bytes = (int)((f.ndim > 1 ? f.shape[f.ndim - 1] : 1) * f.itemsize);
       }
-      const bool tma = tma_eligible(f, cfg, ka.fs);
+      const bool tma = tma_eligible(f, cfg, ka.fs) && crop_pad_eff <= 4;
       for (size_t c = a; c < frame_keys.size() && fp.n_jobs < kMaxFrameJobs; ++c) {
         const KeyPlan& kc = plan[frame_keys[c]];
         if (taken[c] || kc.field != ka.field || kc.fs != ka.fs) continue;
@@ -1780,7 +1784,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         job.fs = kc.fs;
       }
       if (tma) {
-        const int rb = band_rows_for(fp.H, cfg.crop_padding);
+        const int rb = band_rows_for(fp.H, crop_pad_eff);
         if (rb == 0) return bail(fail(OGB_ERR_UNSUPPORTED, "no band size for image height %d", fp.H));
         fp.band_rows = rb;
         fp.n_bands = fp.H / rb;
@@ -1926,6 +1930,193 @@ int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64
   const int fs = s->cfg.frame_stack;
   if (fs > 0 && s->term_host.empty()) return fail(OGB_ERR_INVALID, "frame stacking needs trajectory boundaries");
   return run_sample(s, spec, n, 1, idxs, 1, nullptr, out);
+}
+
+// GCDataset.augment (datasets.py:329-339) for one image array: rows `idxs` of the observations, each cropped with its
+// own (cy, cx) shift after edge padding by `padding` (datasets.py:17-33).  `crop` is [n, 2] int64 (host), the
+// reference's randint(0, 2 * padding + 1, (n, 2)).
+int ogb_sampler_gather_cropped(ogb_sampler* s, const int64_t* idxs, int64_t n, const int64_t* crop, int32_t padding, ogb_batch** out) {
+  if (!s || !idxs || !crop || !out || n < 1 || padding < 0) return fail(OGB_ERR_INVALID, "ogb_sampler_gather_cropped: bad argument");
+  for (int64_t r = 0; r < 2 * n; ++r)
+    if (crop[r] < 0 || crop[r] > 2 * (int64_t)padding) return fail(OGB_ERR_INVALID, "crop shift out of [0, 2 * padding]");
+  PlanBuilder pb;
+  pb.ds = s->ds;
+  pb.cfg = &s->cfg;
+  pb.crop_possible = true;
+  for (int v = 0; v < ogb::kMaxSlots; ++v) pb.slot_canon[v] = v;
+  pb.obs_key("observations", ogb::SLOT_IDX, true);
+  RunSpec spec;
+  spec.kind = OGB_KIND_PLAIN;
+  spec.plan = &pb.keys;
+  spec.n_slots = 2;
+  spec.crop_padding = padding;
+  ogb_draws d;
+  memset(&d, 0, sizeof(d));
+  d.has_aug_coin = 1;
+  d.aug_coin = 0.0;
+  d.crop = crop;
+  return run_sample(s, spec, n, 1, idxs, 0, &d, out);
+}
+
+}  // extern "C"
+
+namespace {
+struct GoalsParams {
+  ogb::RelabelParams r;
+  const int64_t* idxs;
+  int64_t* out;
+  int64_t n;
+};
+
+// GCDataset.sample_goals (datasets.py:296-327) for explicit rows
+template <bool kInject>
+__global__ void __launch_bounds__(256) sample_goals_kernel(const __grid_constant__ GoalsParams q) {
+  using namespace ogb;
+  const RelabelParams& p = q.r;
+  const SegView seg{p.seg_bucket, p.seg_table};
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < q.n; g += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t i = (int32_t)q.idxs[g];
+    const int tl = lower_bound_bucketed(p.term, p.term_bucket, p.term_shift, i);
+    const int32_t fin = __ldg(p.term + tl);
+    int32_t goal;
+    if (kInject) {
+      goal = pick_goal_injected<false>(p, seg, 0, i, fin, g);
+    } else {
+      const uint4 w0 = draw4(p.key, p.batch0, (uint32_t)g, PURPOSE_IDX);
+      const uint4 gb = draw4(p.key, p.batch0, (uint32_t)g, PURPOSE_GOAL);
+      goal = pick_goal_philox<false>(p, seg, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
+    }
+    q.out[g] = goal;
+  }
+}
+
+// HGCDataset.compute_high_next_idxs (datasets.py:478-491)
+__global__ void high_next_kernel(const int64_t* __restrict__ idxs, const int64_t* __restrict__ fin, const int64_t* __restrict__ goal,
+                                 int64_t k, int64_t n, int64_t* __restrict__ next, int64_t* __restrict__ steps) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+    int64_t st = fin[g] - idxs[g] < k ? fin[g] - idxs[g] : k;
+    const int64_t d = goal[g] - idxs[g];
+    if (0 <= d && d < st) st = d;
+    next[g] = idxs[g] + st;
+    steps[g] = st;
+  }
+}
+
+struct DeviceScratch {   // a few temporary device arrays of a helper call
+  std::vector<void*> ptrs;
+  ~DeviceScratch() { for (void* q : ptrs) cudaFree(q); }
+  template <typename T>
+  int upload(const T* host, int64_t n, T** out) {
+    OGB_CUDA(cudaMalloc((void**)out, (size_t)std::max<int64_t>(n, 1) * sizeof(T)));
+    ptrs.push_back(*out);
+    if (host) OGB_CUDA(cudaMemcpy(*out, host, (size_t)n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int ogb_sampler_sample_goals(ogb_sampler* s, const int64_t* idxs, int64_t n, double p_curgoal, double p_trajgoal, int32_t geom_sample,
+                             double discount, const ogb_goal_draws* draws, int64_t* out_goal_idxs) {
+  using namespace ogb;
+  if (!s || !idxs || !out_goal_idxs || n < 1) return fail(OGB_ERR_INVALID, "ogb_sampler_sample_goals: bad argument");
+  if (s->term_host.empty()) return fail(OGB_ERR_INVALID, "this sampler has no trajectory boundaries");
+  if (!(discount > 0.0 && discount < 1.0)) return fail(OGB_ERR_INVALID, "discount must be in (0, 1)");
+  const ogb_dataset* ds = s->ds;
+  for (int64_t r = 0; r < n; ++r)
+    if (idxs[r] < 0 || idxs[r] >= ds->size) return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
+  const bool cur_only = p_curgoal == 1.0;
+  const int64_t n_choices = s->trl_rows.dev ? (int64_t)s->trl_rows.host.size() : (ds->valid_mode == 0 ? ds->active_rows : ds->n_valid);
+  if (draws) {
+    if (!draws->rand_pos || (geom_sample ? !draws->offset : !draws->dist) || (!cur_only && (!draws->u_traj || !draws->u_cur)))
+      return fail(OGB_ERR_INVALID, "sample_goals: missing draws");
+    for (int64_t r = 0; r < n; ++r)
+      if (draws->rand_pos[r] < 0 || draws->rand_pos[r] >= n_choices) return fail(OGB_ERR_INDEX, "rand_pos out of range");
+  }
+  OGB_CUDA(cudaSetDevice(ds->device));
+  std::lock_guard<std::mutex> lock(s->mu);
+  GoalsParams q;
+  memset(&q, 0, sizeof(q));
+  RelabelParams& p = q.r;
+  p.term = s->d_term;
+  p.term_bucket = s->d_term_bucket;
+  p.term_shift = s->term_shift;
+  p.valid_table = s->trl_rows.dev ? s->trl_rows.dev : ds->d_valid_table;
+  p.gap_c = ds->d_gap_c;
+  p.gap_bucket = ds->d_gap_bucket;
+  p.gap_shift = ds->gap_shift;
+  p.valid_mode = s->trl_rows.dev ? 1 : ds->valid_mode;
+  if (!s->trl_rows.dev && s->seg_shift >= 0) {
+    p.valid_mode = 3;
+    p.seg_table = s->d_seg_table;
+    p.seg_bucket = s->d_seg_bucket;
+    p.seg_shift = s->seg_shift;
+  }
+  p.n_choices = n_choices;
+  p.n_rows_ds = (int32_t)ds->size;
+  GoalSpec& spec = p.goal[0];
+  spec.geom = geom_sample != 0;
+  spec.cur_only = cur_only;
+  spec.p_cur = p_curgoal;
+  spec.thr_traj = cur_only ? 0.0 : p_trajgoal / (1.0 - p_curgoal);
+  spec.log_1mp = std::log(1.0 - (1.0 - discount));
+  spec.geo_abs_margin = (float)(1.5e-8 / std::fabs(spec.log_1mp));
+  auto word_threshold = [](double prob, uint32_t* thr, uint8_t* always) {
+    const double t = std::ceil(prob * 4294967296.0);
+    *always = t >= 4294967296.0 ? 1 : 0;
+    *thr = t <= 0.0 ? 0u : (t >= 4294967296.0 ? 0xFFFFFFFFu : (uint32_t)t);
+  };
+  word_threshold(spec.thr_traj, &spec.thr_traj32, &spec.traj_always);
+  word_threshold(spec.p_cur, &spec.thr_cur32, &spec.cur_always);
+  p.key = make_rng_key(s->seed, s->stream_id);
+  p.batch0 = s->counter;
+  DeviceScratch tmp;
+  int64_t *d_idxs = nullptr, *d_out = nullptr;
+  OGB_TRY(tmp.upload(idxs, n, &d_idxs));
+  OGB_TRY(tmp.upload<int64_t>(nullptr, n, &d_out));
+  q.idxs = d_idxs;
+  q.out = d_out;
+  q.n = n;
+  if (draws) {
+    int64_t *d_pos = nullptr, *d_off = nullptr;
+    double *d_dist = nullptr, *d_ut = nullptr, *d_uc = nullptr;
+    OGB_TRY(tmp.upload(draws->rand_pos, n, &d_pos));
+    p.in_goal[0].rand_pos = d_pos;
+    if (draws->offset) { OGB_TRY(tmp.upload(draws->offset, n, &d_off)); p.in_goal[0].offset = d_off; }
+    if (draws->dist) { OGB_TRY(tmp.upload(draws->dist, n, &d_dist)); p.in_goal[0].dist = d_dist; }
+    if (draws->u_traj) { OGB_TRY(tmp.upload(draws->u_traj, n, &d_ut)); p.in_goal[0].u_traj = d_ut; }
+    if (draws->u_cur) { OGB_TRY(tmp.upload(draws->u_cur, n, &d_uc)); p.in_goal[0].u_cur = d_uc; }
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ds->sm_count * 8);
+  if (draws) sample_goals_kernel<true><<<grid, 256, 0, s->stream>>>(q);
+  else sample_goals_kernel<false><<<grid, 256, 0, s->stream>>>(q);
+  OGB_CUDA(cudaGetLastError());
+  OGB_CUDA(cudaMemcpyAsync(out_goal_idxs, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+  OGB_CUDA(cudaStreamSynchronize(s->stream));
+  if (!draws) s->counter += 1;
+  return 0;
+}
+
+int ogb_sampler_compute_high_next_idxs(ogb_sampler* s, const int64_t* idxs, const int64_t* final_state_idxs, const int64_t* goal_idxs,
+                                       int64_t n, int64_t subgoal_steps, int64_t* out_next, int64_t* out_steps) {
+  if (!s || !idxs || !final_state_idxs || !goal_idxs || !out_next || !out_steps || n < 1)
+    return fail(OGB_ERR_INVALID, "ogb_sampler_compute_high_next_idxs: bad argument");
+  OGB_CUDA(cudaSetDevice(s->ds->device));
+  std::lock_guard<std::mutex> lock(s->mu);
+  DeviceScratch tmp;
+  int64_t *d_i = nullptr, *d_f = nullptr, *d_g = nullptr, *d_n = nullptr, *d_s = nullptr;
+  OGB_TRY(tmp.upload(idxs, n, &d_i));
+  OGB_TRY(tmp.upload(final_state_idxs, n, &d_f));
+  OGB_TRY(tmp.upload(goal_idxs, n, &d_g));
+  OGB_TRY(tmp.upload<int64_t>(nullptr, n, &d_n));
+  OGB_TRY(tmp.upload<int64_t>(nullptr, n, &d_s));
+  high_next_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)s->ds->sm_count * 8), 256, 0, s->stream>>>(d_i, d_f, d_g, subgoal_steps, n, d_n, d_s);
+  OGB_CUDA(cudaGetLastError());
+  OGB_CUDA(cudaMemcpyAsync(out_next, d_n, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+  OGB_CUDA(cudaMemcpyAsync(out_steps, d_s, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+  OGB_CUDA(cudaStreamSynchronize(s->stream));
+  return 0;
 }
 
 namespace {

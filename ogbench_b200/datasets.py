@@ -544,6 +544,20 @@ class _HostDraws:
         self.goals.append(g)
 
 
+def _crop_array(arr, crop_froms, padding, device, output):
+    """batched_random_crop (datasets.py:17-33) of one [B, H, W, C] array on the device: the array becomes a temporary
+    resident dataset whose rows are gathered with the crop fused in (the same kernels as sample())."""
+    ds = Dataset.create(freeze=False, observations=arr)
+    sampler = _Sampler(ds, None, _native.KIND_PLAIN, device=device, output=output)
+    n = len(crop_froms)
+    idxs = np.arange(n, dtype=np.int64)
+    crop = np.ascontiguousarray(crop_froms, dtype=np.int64)
+    out = C.c_void_p()
+    _native.check(_native.lib().ogb_sampler_gather_cropped(sampler.ptr, idxs.ctypes.data_as(C.c_void_p), n,
+                                                           crop.ctypes.data_as(C.c_void_p), int(padding), C.byref(out)))
+    return next(iter(sampler.wrap(BatchHandle(out, device, None)).values()))
+
+
 class GCDataset:
     """Dataset class for goal-conditioned RL, device-resident (reference: datasets.py:149-366).
 
@@ -635,6 +649,43 @@ class GCDataset:
         assert self.config['frame_stack'] is not None
         return self._sampler.gather(0, idxs)
 
+    def sample_goals(self, idxs, p_curgoal, p_trajgoal, p_randomgoal, geom_sample, discount=None):
+        """Sample goals for the given indices (datasets.py:296-327); returns int64 row indices on the host.
+
+        rng='numpy' makes the reference's own np.random calls (randint, geometric or rand, rand, rand) and the device
+        computes the goals from them; rng='philox' draws on the device."""
+        idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64).reshape(-1)
+        n = len(idxs)
+        if discount is None:
+            discount = self.config['discount']
+        c_draws, keep = None, []
+        if self.rng == 'numpy':
+            d = _HostDraws()
+            d.goal(self._n_choices, n, geom_sample, discount, p_curgoal)
+            g = d.goals[0]
+            c_draws = _native.GoalDraws()
+            for name, dtype in (('rand_pos', np.int64), ('offset', np.int64), ('dist', np.float64), ('u_traj', np.float64), ('u_cur', np.float64)):
+                arr = getattr(g, name)
+                if arr is not None:
+                    arr = np.ascontiguousarray(arr, dtype=dtype)
+                    keep.append(arr)
+                    setattr(c_draws, name, arr.ctypes.data)
+        out = np.empty(n, dtype=np.int64)
+        _native.check(_native.lib().ogb_sampler_sample_goals(
+            self._sampler.ptr, idxs.ctypes.data_as(C.c_void_p), n, float(p_curgoal), float(p_trajgoal), int(bool(geom_sample)),
+            float(discount), C.byref(c_draws) if c_draws is not None else None, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def augment(self, batch, keys):
+        """Apply image augmentation to the given keys, in place (datasets.py:329-339): one (cy, cx) shift per sample from
+        np.random.randint -- the reference's own call -- shared by all keys; arrays that are not 4-D pass through."""
+        padding = 3
+        batch_size = len(batch[keys[0]])
+        crop_froms = np.random.randint(0, 2 * padding + 1, (batch_size, 2))
+        for key in keys:
+            if len(batch[key].shape) == 4:
+                batch[key] = _crop_array(batch[key], crop_froms, padding, self._sampler.device, self._sampler.output)
+
     # ---- checkpointable sampler state: one integer ----
     def state_dict(self):
         return {'counter': self._sampler.counter}
@@ -650,6 +701,19 @@ class HGCDataset(GCDataset):
     """
 
     _KIND = _native.KIND_HGC
+
+    def compute_high_next_idxs(self, idxs, final_state_idxs, high_goal_idxs, subgoal_steps):
+        """Compute the next indices for high-level goals (datasets.py:478-491); returns (idxs + steps, steps)."""
+        arrs = [np.ascontiguousarray(np.asarray(a), dtype=np.int64).reshape(-1) for a in (idxs, final_state_idxs, high_goal_idxs)]
+        n = len(arrs[0])
+        nxt, steps = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        _native.check(_native.lib().ogb_sampler_compute_high_next_idxs(
+            self._sampler.ptr, *[a.ctypes.data_as(C.c_void_p) for a in arrs], n, int(subgoal_steps),
+            nxt.ctypes.data_as(C.c_void_p), steps.ctypes.data_as(C.c_void_p)))
+        return nxt, steps
+
+    def get_high_actions(self, target_idxs, cur_idxs):
+        return self.get_goal_observations(target_idxs)  # datasets.py:493-494
 
     def _goal_sets(self):
         cfg = self.config

@@ -286,6 +286,57 @@ def test_get_observations_helpers():
             assert np.array_equal(np.asarray(sampler.get_stacked_observations(idxs)), oracle._obs(idxs)), name
 
 
+def test_reference_helper_methods():
+    """sample_goals, compute_high_next_idxs, get_high_actions, augment (datasets.py:296-339, :478-494) as public methods,
+    computed on the device, against the oracle's restatement under the same np.random state."""
+    from oracle.replay_oracle import (NumpyGlobalSource, OracleSampler, final_rows, pick_goals, shifted_edge_crop,
+                                      subgoal_step)
+
+    for layout_seed, lo_len in ((31, 2), (32, 20)):      # ragged short trajectories (general searches) and long ones (segment table)
+        lengths = ragged(layout_seed, 80, lo_len, 90)
+        fields = toy_fields(layout_seed, lengths, (6,), 3, np.float32)
+        config = cfg(subgoal_steps=7)
+        sampler = device_sampler(fields, config, 'hgc', rng='numpy', output='numpy')
+        oracle = OracleSampler(fields, config, 'hgc')
+        rng = np.random.default_rng(layout_seed)
+        idxs = oracle.valid_table[rng.integers(0, len(oracle.valid_table), 500)]
+        final = final_rows(oracle.terminal_locs, idxs)
+        for p_cur, p_traj, p_rand, geom, disc in ((0.2, 0.5, 0.3, True, None), (0.0, 1.0, 0.0, False, None), (1.0, 0.0, 0.0, True, 0.9),
+                                                  (0.1, 0.3, 0.6, False, 0.95)):
+            np.random.seed(77)
+            want, _ = pick_goals(idxs, final, oracle.valid_table, p_cur, p_traj, geom, config['discount'] if disc is None else disc,
+                                 NumpyGlobalSource(), oracle.size)
+            np.random.seed(77)
+            got = sampler.sample_goals(idxs, p_cur, p_traj, p_rand, geom, discount=disc)
+            assert got.dtype == np.int64 and np.array_equal(got, want), (layout_seed, p_cur, geom)
+        goals = oracle.valid_table[rng.integers(0, len(oracle.valid_table), 500)]
+        goals[::3] = np.minimum(idxs[::3] + rng.integers(0, 12, len(idxs[::3])), final[::3])
+        for k in (1, 7, 1000):
+            want_next, want_steps = subgoal_step(idxs, final, goals, k)
+            got_next, got_steps = sampler.compute_high_next_idxs(idxs, final, goals, k)
+            assert np.array_equal(got_next, want_next) and np.array_equal(got_steps, want_steps), k
+        assert np.array_equal(sampler.get_high_actions(idxs[:9], idxs[:9]), fields['observations'][idxs[:9]])
+        # the on-device RNG mode returns goals with the right structure
+        dev = device_sampler(fields, config, 'hgc', seed=3)
+        g = dev.sample_goals(idxs, 0.0, 1.0, 0.0, True)
+        assert ((g > idxs) | (idxs == final)).all() and (g <= final).all()
+
+    # augment: one shift per sample shared by the keys, non-image keys untouched, in place like the reference
+    case = load_case('gc_pixel_fs3_aug')
+    for output in ('numpy', 'device'):
+        sampler = device_sampler(case['fields'], case['cfg'], 'gc', output=output)
+        batch = sampler.sample(16, evaluation=True)
+        before = to_host(batch)
+        np.random.seed(5)
+        crop = np.random.randint(0, 7, (16, 2))
+        np.random.seed(5)
+        sampler.augment(batch, ['observations', 'value_goals', 'actions'])
+        after = to_host(batch)
+        for key in ('observations', 'value_goals'):
+            assert np.array_equal(after[key], shifted_edge_crop(before[key], crop, 3)), (output, key)
+        assert np.array_equal(after['actions'], before['actions']) and np.array_equal(after['next_observations'], before['next_observations'])
+
+
 def test_atc_anchor_sets_match_oracle():
     from oracle.replay_oracle import OracleATCSampler
 
