@@ -751,7 +751,21 @@ class ATCDataset:
         return self._sampler.atc_anchors(k)
 
     def get_observations(self, idxs):
+        """Return the observations for the given indices, frame-stacked as configured (datasets.py:451-456)."""
         return self._sampler.gather(0, idxs)
+
+    def get_stacked_observations(self, idxs):
+        """Return the frame-stacked observations for the given indices (datasets.py:458-464)."""
+        assert self.config['frame_stack'] is not None
+        return self._sampler.gather(0, idxs)
+
+    def augment(self, batch, keys):
+        """Apply random-shift augmentation to image observations, in place (datasets.py:438-448)."""
+        batch_size = len(batch[keys[0]])
+        crop_froms = np.random.randint(0, 2 * self._padding + 1, (batch_size, 2))
+        for key in keys:
+            if len(batch[key].shape) == 4:
+                batch[key] = _crop_array(batch[key], crop_froms, self._padding, self._sampler.device, self._sampler.output)
 
     def _host_draws(self, batch_size, k, evaluation) -> _HostDraws:
         d = _HostDraws()

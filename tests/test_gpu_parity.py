@@ -337,6 +337,25 @@ def test_reference_helper_methods():
         assert np.array_equal(after['actions'], before['actions']) and np.array_equal(after['next_observations'], before['next_observations'])
 
 
+def test_atc_augment_method():
+    """ATCDataset.augment (datasets.py:438-448): padding from config['augment_padding'] (4 by default)."""
+    from oracle.replay_oracle import shifted_edge_crop
+
+    case = load_case('atc_pixel_fs3_aug')
+    sampler = device_sampler(case['fields'], case['cfg'], 'atc', output='numpy')
+    pad = int(case['cfg'].get('augment_padding', 4))
+    batch = sampler.sample(12, case['k'], evaluation=True)
+    before = {k: v.copy() for k, v in batch.items()}
+    np.random.seed(9)
+    crop = np.random.randint(0, 2 * pad + 1, (12, 2))
+    np.random.seed(9)
+    sampler.augment(batch, ['observations', 'positive_observations'])
+    for key in ('observations', 'positive_observations'):
+        assert np.array_equal(batch[key], shifted_edge_crop(before[key], crop, pad)), key
+    idxs = np.array([0, 3, 5])
+    assert np.array_equal(np.asarray(sampler.get_stacked_observations(idxs)), np.asarray(sampler.get_observations(idxs)))
+
+
 def test_atc_anchor_sets_match_oracle():
     from oracle.replay_oracle import OracleATCSampler
 
