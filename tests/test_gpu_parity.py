@@ -197,6 +197,22 @@ def test_mixed_dtypes_against_oracle():
             assert_batches_identical(got, want, label=f'mixed/{kind}/{it}:')
 
 
+@pytest.mark.parametrize('kind', ['gc', 'hgc'])
+def test_large_batch_numpy_rng_matches_oracle(kind):
+    """One sample() of 40,000 rows (>= 32,768: the big-launch code paths -- auxiliary stream, persistent index kernel with
+    the segment table in shared memory for HGC, fused launch for GC) in the mode that replays np.random."""
+    lengths = ragged(41, 400, 25, 120)
+    fields = toy_fields(41, lengths, (13,), 4, np.float32)
+    config = cfg(subgoal_steps=9)
+    sampler = device_sampler(fields, config, kind, rng='numpy', output='numpy')
+    for it in range(2):
+        np.random.seed(500 + it)
+        _, want = oracle_with_draws(fields, config, kind, 40000)
+        np.random.seed(500 + it)
+        got = sampler.sample(40000)
+        assert_batches_identical(got, want, label=f'large/{kind}/{it}:')
+
+
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')
     sampler = device_sampler(case['fields'], case['cfg'], 'hgc')

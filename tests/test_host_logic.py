@@ -107,3 +107,29 @@ def test_host_draw_schedule_matches_reference_order():
         assert [k for k, _ in rec.log] == case['meta']['draw_kinds'], name
         for (_, got), (_, want) in zip(rec.log, case['log']):
             assert np.array_equal(got, want), name
+
+
+def test_cpulist_parser_and_l2_note():
+    import bench
+    from ogbench_b200 import dist_util
+
+    assert dist_util._parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    assert dist_util._parse_cpulist('') == []
+    small = bench.l2_note(59e6, 32e6)
+    assert 'smaller than L2' in small and 'together larger' in small
+    big = bench.l2_note(537e6, 256e6)
+    assert 'each larger than' in big and 'larger than L2' in big
+
+
+def test_workload_catalogue_is_consistent():
+    """Algorithmic bytes per transition of the bench workloads follow from their shapes."""
+    from ogbench_b200 import synthetic
+
+    w = synthetic.WORKLOADS
+    obs = {k: int(np.prod(v.obs_shape)) * (1 if v.obs_dtype == 'uint8' else 4) for k, v in w.items()}
+    act = {k: v.act_dim * 4 for k, v in w.items()}
+    for k in ('c1', 'c2', 'c5'):      # GC: 4 row gathers in and out, actions, terminals + valids, masks + rewards
+        assert w[k].bytes_per_transition == (4 * obs[k] + act[k] + 8) + (4 * obs[k] + act[k] + 8 + 16), k
+    assert w['c3'].bytes_per_transition == (7 * obs['c3'] + act['c3'] + 8) + (7 * obs['c3'] + act['c3'] + 8 + 9 * 8)
+    assert w['c4'].bytes_per_transition == (10 * obs['c4'] + act['c4'] + 8) + (4 * 3 * obs['c4'] + act['c4'] + 8 + 16)
+    assert w['c5'].rows == 12_512_500 and w['c3'].rows == 4_001_000
