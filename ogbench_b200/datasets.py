@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
-from typing import Any, Dict, Mapping, Optional
+from typing import Any, Dict, Mapping
 
 import numpy as np
 

@@ -11,7 +11,6 @@ thread while the current one is being sampled, so the swap every `dataset_replac
 from __future__ import annotations
 
 import glob
-import os
 import threading
 from typing import Any, Callable, List, Optional
 

@@ -88,7 +88,7 @@ def test_philox_draws_feed_the_oracle():
 
 def test_host_draw_schedule_matches_reference_order():
     """rng='numpy' consumes np.random exactly as the reference does: checked against the golden draw logs without a GPU."""
-    from ogbench_b200.datasets import GCDataset, HGCDataset, _HostDraws
+    from ogbench_b200.datasets import GCDataset, HGCDataset
     from tests.golden_util import case_names, load_case
     from oracle.refshim import DrawRecorder
 
