@@ -230,8 +230,10 @@ def run_gpu_arm(args):
     from ogbench_b200 import Dataset, GCDataset, HGCDataset, _native, dist_util, synthetic
 
     rank, world, local = dist_util.env_rank()
-    if world > 1:   # NCCL prints its version / debug lines to stdout by default: keep stdout for the one JSON line
+    if world > 1:   # NCCL prints its version / debug lines to stdout: keep stdout for the one JSON line
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'        # (an explicit INFO/TRACE request from the caller is left alone)
     torch.cuda.set_device(local)
     numa = dist_util.bind_to_gpu_numa(local) if world > 1 and not os.environ.get('OGB_NO_NUMA_BIND') else None
     dist_util.init('nccl', device=torch.device('cuda', local))
