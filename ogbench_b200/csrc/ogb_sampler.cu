@@ -491,15 +491,17 @@ int build_segment_table(ogb_sampler* s) {
     fin[m] = *it;
   }
   fin[n_gaps + 1] = fin[n_gaps];
-  std::vector<int4> table(n_gaps + 1);
-  for (size_t m = 0; m <= n_gaps; ++m)
-    table[m] = make_int4(m < n_gaps ? c[m] : 0x7fffffff, fin[m], fin[m + 1], 0);
-  std::vector<int32_t> bucket = build_buckets(c, ds->n_valid + 1, shift);
+  // one entry per bucket: everything a position in that bucket can need (valid_row_fast)
+  const std::vector<int32_t> bucket = build_buckets(c, ds->n_valid + 1, shift);
+  std::vector<int4> table(bucket.size());
+  for (size_t bi = 0; bi < bucket.size(); ++bi) {
+    const size_t lo = (size_t)bucket[bi];
+    table[bi] = make_int4(lo < n_gaps ? c[lo] : 0x7fffffff, fin[lo], fin[lo + 1], (int)lo);
+  }
   OGB_TRY(upload_vector(table, &s->d_seg_table));
-  OGB_TRY(upload_vector(bucket, &s->d_seg_bucket));
   s->seg_shift = shift;
   s->n_seg_table = (int)table.size();
-  s->n_seg_bucket = (int)bucket.size();
+  s->n_seg_bucket = 0;
   return 0;
 }
 

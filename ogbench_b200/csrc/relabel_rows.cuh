@@ -111,8 +111,9 @@ struct RelabelParams {
   int32_t term_shift;
   int32_t gap_shift;
   int32_t valid_mode;          // 0: no 'valids'; 1: table; 2: gap ranks; 3: segment table (one probe, see valid_row_fast)
-  const int4* seg_table;       // valid_mode 3: {c[m], final_state(segment m), final_state(segment m+1), 0}
-  const int32_t* seg_bucket;   //               lower_bound(c, b << seg_shift); a bucket holds at most one c[m]
+  const int4* seg_table;       // valid_mode 3, one entry per bucket b of 2^seg_shift positions, lo = lower_bound(c, b << seg_shift):
+                               //   {c[lo] (INT_MAX past the end), final_state(segment lo), final_state(segment lo+1), lo}
+  const int32_t* seg_bucket;   // (unused: the bucket table is folded into seg_table)
   int32_t seg_shift;
   int32_t n_seg_table;         // entries of seg_table / seg_bucket (for the shared-memory copy of the index kernel)
   int32_t n_seg_bucket;
@@ -187,8 +188,10 @@ __device__ __forceinline__ uint32_t select_word(const uint4& a, const uint4& b, 
 // valid_mode 3 -- datasets whose invalid rows are far apart (every compact OGBench dataset: one per trajectory) and
 // whose trajectories end where their valid rows end.  Position pos among the valid rows falls into segment
 // m = #{invalid rows before it} = upper_bound(c, pos); buckets are narrower than the smallest gap between two c[m],
-// so a bucket holds at most one boundary and the search is ONE probe: two dependent loads give the row AND the
-// trajectory's final state (datasets.py:306 needs a second search in the reference).
+// so a bucket holds at most one boundary, and the table has one entry PER BUCKET that carries everything the bucket
+// can answer: {the boundary c[lo] inside or after it, final_state(segment lo), final_state(segment lo + 1), lo}.
+// One 16-byte load gives the row AND the trajectory's final state (datasets.py:306 needs a second search in the
+// reference).
 // Where the segment table is read from: global memory (read-only path), or the copy a persistent index kernel made in
 // shared memory (scattered 4/16-byte table reads then cost bank cycles instead of L1TEX tag lookups).
 struct SegView {
@@ -198,11 +201,10 @@ struct SegView {
 
 template <bool kSmemTables>
 __device__ __forceinline__ int32_t valid_row_fast(const RelabelParams& p, const SegView& seg, const uint32_t pos, int32_t& fin) {
-  const int lo = kSmemTables ? seg.bucket[pos >> p.seg_shift] : __ldg(seg.bucket + (pos >> p.seg_shift));
-  const int4 e = kSmemTables ? seg.table[lo] : __ldg(seg.table + lo);
+  const int4 e = kSmemTables ? seg.table[pos >> p.seg_shift] : __ldg(seg.table + (pos >> p.seg_shift));   // ONE 16-byte load
   const bool past = e.x <= (int32_t)pos;
   fin = past ? e.z : e.y;
-  return (int32_t)pos + lo + (past ? 1 : 0);
+  return (int32_t)pos + e.w + (past ? 1 : 0);
 }
 
 // the general forms (no 'valids', explicit table, gap ranks with a binary search): out of line, the segment table
