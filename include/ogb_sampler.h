@@ -115,8 +115,10 @@ const char* ogb_last_error(void);
 int ogb_abi_version(void);
 int ogb_device_count(int* out);
 
-/* Dataset.create + Dataset.__init__ (datasets.py:45-63): uploads every field into HBM (row stride padded to a
- * 16-byte multiple for rows > 16 B), builds the valid-row table from `valids`. */
+/* Dataset.create + Dataset.__init__ (datasets.py:45-63): uploads every field into HBM -- fields with rows of at most
+ * 2 KB as sub-fields of one packed record per dataset row (observations first; 16-byte offsets for sub-fields longer
+ * than 16 B; record padded to 32 B, 64 B or a multiple of 128 B), longer rows as arrays of their own -- and builds the
+ * valid-row tables from `valids`. */
 int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out);
 int ogb_dataset_size(const ogb_dataset* ds, int64_t* out);
 int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out);   /* -1 when the dataset has no 'valids' */
