@@ -106,6 +106,7 @@ SIGNATURES = [
     ('ogb_batch_nbytes', C.c_int, [_P, C.POINTER(C.c_size_t)]),
     ('ogb_batch_launches', C.c_int, [_P, C.POINTER(C.c_int32)]),
     ('ogb_batch_dominant_kernel', C.c_int, [_P, _P, _P]),
+    ('ogb_batch_keep_leading_axis', C.c_int, [_P, C.c_int32]),
     ('ogb_batch_sync', C.c_int, [_P]),
     ('ogb_batch_wait_on_stream', C.c_int, [_P, _P]),
     ('ogb_batch_copy_to_host', C.c_int, [_P, _P, C.c_size_t]),

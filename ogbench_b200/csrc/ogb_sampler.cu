@@ -312,6 +312,7 @@ struct ogb_batch {
   int8_t* crop = nullptr;
   int n_slots = 0;
   int launches = 0;
+  bool keep_axis = false;               // report the leading n_batches axis even when n_batches == 1 (sample_many)
   std::vector<int64_t> chunk_end;                          // host-output pipelining: rows [chunk_end[c-1], chunk_end[c]) ...
   std::vector<cudaEvent_t> chunk_done;                     // ... are complete once chunk_done[c] has fired
   int32_t* idx_error = nullptr;                            // device flag of the deferred index check (inside the block)
@@ -2199,7 +2200,7 @@ int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) {
   out->name = k.name.c_str();
   out->dtype = k.dtype;
   int nd = 0;
-  if (b->n_batches > 1) out->shape[nd++] = b->n_batches;
+  if (b->n_batches > 1 || b->keep_axis) out->shape[nd++] = b->n_batches;
   out->shape[nd++] = b->batch;
   for (int d = 0; d < k.ndim_tail; ++d) out->shape[nd++] = k.tail[d];
   out->ndim = nd;
@@ -2210,6 +2211,11 @@ int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) {
   return 0;
 }
 
+int ogb_batch_keep_leading_axis(ogb_batch* b, int32_t on) {
+  if (!b) return fail(OGB_ERR_INVALID, "null batch");
+  b->keep_axis = on != 0;
+  return 0;
+}
 int ogb_batch_nbytes(const ogb_batch* b, size_t* out) {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->keys_bytes;

@@ -428,12 +428,14 @@ class _Sampler:
         _native.check(_native.lib().ogb_sampler_gather(self.ptr, which, idxs.ctypes.data_as(C.c_void_p), len(idxs), C.byref(out)))
         return next(iter(self.wrap(BatchHandle(out, self.device, None)).values()))
 
-    def sample_atc(self, batch_size, k, evaluation=False, draws=None, n_batches=1):
+    def sample_atc(self, batch_size, k, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         keep = []
         c_draws = _pack_draws(draws, keep) if draws is not None else None
         out = C.c_void_p()
         _native.check(_native.lib().ogb_sampler_sample_atc(self.ptr, int(batch_size), int(n_batches), int(k), int(bool(evaluation)),
                                                            C.byref(c_draws) if c_draws is not None else None, C.byref(out)))
+        if keep_axis:
+            _native.check(_native.lib().ogb_batch_keep_leading_axis(out, 1))
         return self.wrap(BatchHandle(out, self.device, None))
 
     def atc_anchors(self, k) -> np.ndarray:
@@ -480,10 +482,12 @@ class _Sampler:
         flat = np.frombuffer(raw, dtype=np.uint8)
         return {name: flat[off:off + nb].view(dtype).reshape(shape) for name, dtype, shape, off, nb in keys}
 
-    def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1):
+    def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         handle = self.sample_native(batch_size, n_batches, idxs, evaluation, draws)
+        if keep_axis:   # sample_many: arrays are [n_batches, batch, ...] for every n_batches, 1 included
+            _native.check(_native.lib().ogb_batch_keep_leading_axis(handle.ptr, 1))
         n_rows = len(idxs) // int(n_batches) if idxs is not None else int(batch_size)
-        return self.wrap(handle, ('sample', n_rows, int(n_batches), bool(evaluation)))
+        return self.wrap(handle, ('sample', n_rows, int(n_batches), bool(evaluation), bool(keep_axis)))
 
 
 def _pack_draws(draws, keep) -> _native.Draws:
@@ -631,9 +635,9 @@ class GCDataset:
         return self._sampler.sample(batch_size, idxs, evaluation, draws)
 
     def sample_many(self, num_batches, batch_size, evaluation=False, idxs=None):
-        """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis.
+        """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis of that length.
         `idxs` (optional, num_batches * batch_size rows) plays the role of sample()'s `idxs`."""
-        return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches)
+        return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches, keep_axis=True)
 
     # ---- reference helpers that other scripts call (impls/pretrain_atc.py:195, pretrain_vae.py:162) ----
     def get_observations(self, idxs):
@@ -785,4 +789,4 @@ class ATCDataset:
         return self._sampler.sample_atc(batch_size, k, evaluation, draws)
 
     def sample_many(self, num_batches, batch_size, k, evaluation=False):
-        return self._sampler.sample_atc(batch_size, k, evaluation, None, n_batches=num_batches)
+        return self._sampler.sample_atc(batch_size, k, evaluation, None, n_batches=num_batches, keep_axis=True)

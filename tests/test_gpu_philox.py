@@ -104,6 +104,12 @@ def test_warp_specialised_kernel_equals_default():
             assert np.array_equal(x[k], y[k]), (k, K, B)
 
 
+def torch_from(x):
+    import torch
+
+    return torch.from_dlpack(x).cpu()
+
+
 def test_sample_many_equals_successive_calls():
     lengths = ragged(7, 60, 2, 90)
     fields = toy_fields(7, lengths, (11,), 3, np.float32)
@@ -118,6 +124,9 @@ def test_sample_many_equals_successive_calls():
             assert many[key].shape == (K,) + one[key].shape
             assert np.array_equal(many[key][k], one[key]), (key, k)
     assert a.state_dict() == b.state_dict() == {'counter': K}
+    single = a.sample_many(1, B)                       # the leading axis is there for one batch as well
+    assert single['observations'].shape[:2] == (1, B) and np.asarray(single['rewards']).shape == (1, B)
+    assert np.asarray(torch_from(single['observations'])).shape[:2] == (1, B)
 
 
 def test_counter_checkpoint_and_stream_independence():
