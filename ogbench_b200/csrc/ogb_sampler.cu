@@ -680,7 +680,8 @@ bool tma_eligible(const Field& f, const ogb_config& cfg, int fs) {
 }
 
 int band_rows_for(int64_t H, int pad) {
-  for (int rb = 32; rb > pad; --rb)
+  static const int env_rb = getenv("OGB_BAND_ROWS") ? atoi(getenv("OGB_BAND_ROWS")) : 0;   // A/B of the band height
+  for (int rb = env_rb > 0 ? env_rb : 32; rb > pad; --rb)
     if (H % rb == 0) return rb;
   return 0;
 }
