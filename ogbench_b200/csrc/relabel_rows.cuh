@@ -1,14 +1,17 @@
-// The index kernel and the row-gather kernel of the replay sampler.
+// The index algebra and the row-gather kernels of the replay sampler.
 //
-// relabel_index_kernel (one thread per batch row) restates the reference's per-row index algebra
+// relabel_row (one thread per batch row) restates the reference's per-row index algebra
 // (impls/utils/datasets.py:296-327 sample_goals, :478-491 compute_high_next_idxs, :250-252 and :533-582
 // rewards/masks) from either injected draws (validation mode) or Philox draws.  It writes the
-// scalar keys (masks, rewards, offsets, steps) and one int32 row-index vector per slot.
+// scalar keys (masks, rewards, offsets, steps), copies the fields whose rows are <= 16 bytes, and leaves the dataset
+// row of every index-vector slot in registers.  It runs inside
+//   relabel_index_kernel      stand-alone (rows go to int32 index vectors in memory for the gather kernels),
+//   relabel_gather_kernel     fused with the row gather: sample() is one launch,
+//   relabel_gather_ws_kernel  the same launch, warp-specialised (optional).
 //
-// gather_rows_kernel<V> (one warp per 32 batch rows) gathers the dataset rows those vectors name
-// (datasets.py:78-83 get_subset, :341-357 get_observations / get_goal_observations) into the dense output arrays.
-// The two are separate launches so that the gather runs at its own (high) occupancy: the index vectors are
-// 4 bytes per row and slot and stay in L2 between the launches.
+// gather_rows_async_body gathers the dataset rows those slots name (datasets.py:78-83 get_subset, :341-357
+// get_observations / get_goal_observations) into the dense output arrays: per-warp cp.async rings, span jobs over the
+// packed record table, coalesced 16-byte stores.  gather_rows_kernel<V> is the register-staged form for rows > 4 KB.
 #pragma once
 #include "device_common.cuh"
 
