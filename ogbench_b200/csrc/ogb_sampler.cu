@@ -1551,8 +1551,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     const size_t table_bytes = (size_t)p.n_seg_table * 16 + (size_t)p.n_seg_bucket * 4;
     // Used when the index kernel runs on the auxiliary stream under another call's gather: the persistent form with few
     // CTAs disturbs the gather less (C3 0.716 vs 0.730 ms); alone on its stream the plain grid is faster (C1 0.047 vs 0.049).
-    const bool smem_tables = !no_smem_tables && st != s->stream && p.valid_mode == 3 && table_bytes > 0 && table_bytes <= 48 * 1024 &&
-                             end - begin >= 65536;
+    static const bool force_smem_tables = getenv("OGB_SMEM_TABLES") != nullptr;
+    const bool smem_tables = !no_smem_tables && (st != s->stream || force_smem_tables) && p.valid_mode == 3 && table_bytes > 0 &&
+                             table_bytes <= 48 * 1024 && end - begin >= 65536;
     const void* fn = nullptr;
 #define OGB_PICK_INDEX_KERNEL(INJ, SM)                                                                                  \
     fn = flavour == FLAVOUR_GC ? (const void*)relabel_index_kernel<INJ, FLAVOUR_GC, SM>                                   \
