@@ -91,6 +91,49 @@ def add_oracle_reps(env_name, env, dataset, num_cubes=None, num_buttons=None):
     dataset['oracle_reps'] = oracle_reps.astype(np.float32)
 
 
+def make_datasets(dataset_name, dataset_dir='~/.ogbench/data', dataset_path=None, compact_dataset=False, add_info=False,
+                  env=None, num_cubes=None, num_buttons=None):
+    """The dataset half of `ogbench.make_env_and_datasets(..., dataset_only=True)` (ogbench/utils.py:134-235): resolves the
+    train / validation files of `dataset_name`, picks the dtypes by environment family, loads both splits and, for
+    '-oraclerep-' names, adds the oracle goal representations.  Returns (train_dataset, val_dataset) as dicts of host
+    arrays.  Nothing is downloaded (the files must exist), and 'singletask' names are refused: their reward relabelling
+    (ogbench/relabel_utils.py:4-90) needs the live environment's goal, which is outside this package.
+    """
+    import os
+
+    splits = dataset_name.split('-')
+    if 'singletask' in splits:
+        raise NotImplementedError("'singletask' datasets need the environment's task goal (ogbench/relabel_utils.py:4-90)")
+    dataset_add_info = add_info
+    if 'oraclerep' in splits:
+        env_name = '-'.join(splits[:-3] + splits[-1:])         # remove the dataset type and the word 'oraclerep'
+        dataset_name = '-'.join(splits[:-2] + splits[-1:])     # the files carry no 'oraclerep'
+        dataset_add_info = True
+    else:
+        env_name = '-'.join(splits[:-2] + splits[-1:])         # remove the dataset type
+    if dataset_path is None:
+        dataset_dir = os.path.expanduser(dataset_dir)
+        train_path = os.path.join(dataset_dir, f'{dataset_name}.npz')
+        val_path = os.path.join(dataset_dir, f'{dataset_name}-val.npz')
+    else:
+        train_path, val_path = dataset_path, dataset_path.replace('.npz', '-val.npz')
+    for path in (train_path, val_path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f'{path} (datasets are not downloaded by this loader)')
+    ob_dtype = np.uint8 if ('visual' in env_name or 'powderworld' in env_name) else np.float32
+    action_dtype = np.int32 if 'powderworld' in env_name else np.float32
+    out = []
+    for path in (train_path, val_path):
+        ds = load_dataset(path, ob_dtype=ob_dtype, action_dtype=action_dtype, compact_dataset=compact_dataset, add_info=dataset_add_info)
+        if 'oraclerep' in splits:
+            add_oracle_reps(env_name, env, ds, num_cubes=num_cubes, num_buttons=num_buttons)
+        if not add_info:
+            for k in ('qpos', 'qvel', 'button_states'):
+                ds.pop(k, None)
+        out.append(ds)
+    return out[0], out[1]
+
+
 def load_gc_dataset(dataset_path, config, dataset_class=GCDataset, ob_dtype=np.float32, action_dtype=np.float32,
                     device: int = 0, **sampler_kwargs):
     """`.npz` -> compact layout (what impls/utils/env_utils.py:89-95 asks for) -> HBM -> device sampler."""

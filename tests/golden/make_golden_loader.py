@@ -75,8 +75,66 @@ def main_oracle_reps():
     print('loader_oracle_reps', len(payload), 'arrays')
 
 
+MAKE_CASES = [  # (dataset name, pixel observations, num_cubes, add_info)
+    ('antmaze-large-navigate-v0', False, None, False),
+    ('visual-cube-single-play-v0', True, None, False),
+    ('powderworld-easy-play-v0', True, None, True),
+    ('cube-double-play-oraclerep-v0', False, 2, False),
+    ('pointmaze-medium-navigate-oraclerep-v0', False, None, True),
+]
+
+
+def make_raw_pair(directory, file_stem, pixel, seed):
+    """Raw train / validation files as the data-generation scripts write them (float64 observations/actions, bool terminals)."""
+    rng = np.random.default_rng(seed)
+    for suffix, lengths in (('', [6, 4, 7]), ('-val', [5, 3])):
+        n = int(np.sum(lengths))
+        obs = rng.integers(0, 256, (n, 4, 4, 3), dtype=np.uint8) if pixel else rng.standard_normal((n, 3))
+        terminals = np.zeros(n, dtype=bool)
+        terminals[np.cumsum(lengths) - 1] = True
+        np.savez_compressed(os.path.join(directory, f'{file_stem}{suffix}.npz'), observations=obs,
+                            actions=rng.uniform(-1, 1, (n, 2)) * (3 if 'powderworld' in file_stem else 1), terminals=terminals,
+                            qpos=rng.standard_normal((n, 30)), qvel=rng.standard_normal((n, 4)), button_states=rng.integers(0, 2, (n, 3)))
+
+
+def load_reference_utils_with_relabel():
+    """ogbench/utils.py with the real ogbench/relabel_utils.py behind it (gymnasium stubbed: dataset_only never calls it)."""
+    relabel = load_reference_relabel()
+    for name in ('gymnasium', 'ogbench'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['ogbench.relabel_utils'] = relabel
+    spec = importlib.util.spec_from_file_location('ogb_reference_utils2', os.path.join(REF, 'ogbench', 'utils.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def file_stem(name):
+    splits = name.split('-')
+    return '-'.join(splits[:-2] + splits[-1:]) if 'oraclerep' in splits else name
+
+
+def main_make_datasets():
+    """ogbench.make_env_and_datasets(..., dataset_only=True) run unmodified -> loader_make_datasets.npz (+ the raw files)."""
+    ref = load_reference_utils_with_relabel()
+    raw_dir = os.path.join(HERE, 'loader_raw')
+    os.makedirs(raw_dir, exist_ok=True)
+    payload = {}
+    for i, (name, pixel, cubes, add_info) in enumerate(MAKE_CASES):
+        make_raw_pair(raw_dir, file_stem(name), pixel, 50 + i)
+        env = types.SimpleNamespace(unwrapped=types.SimpleNamespace(_num_cubes=cubes, _num_buttons=None))
+        train, val = ref.make_env_and_datasets(name, dataset_path=os.path.join(raw_dir, file_stem(name) + '.npz'), compact_dataset=True,
+                                               dataset_only=True, cur_env=env, add_info=add_info)
+        for split, ds in (('train', train), ('val', val)):
+            for k, v in ds.items():
+                payload[f'{name}/{split}/{k}'] = v
+    np.savez_compressed(os.path.join(HERE, 'loader_make_datasets.npz'), **payload)
+    print('loader_make_datasets', len(payload), 'arrays')
+
+
 def main():
     main_oracle_reps()
+    main_make_datasets()
     ref = load_reference_utils()
     for name, raw_kw, load_kw in CASES:
         raw = os.path.join(HERE, name + '_raw.npz')

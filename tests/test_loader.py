@@ -45,6 +45,29 @@ def test_add_oracle_reps_matches_reference():
         loader.add_oracle_reps('powderworld-easy-play-v0', None, oracle_inputs())
 
 
+def test_make_datasets_matches_reference():
+    """make_datasets = the dataset half of ogbench.make_env_and_datasets(dataset_only=True) (ogbench/utils.py:134-235):
+    file resolution, dtypes per environment family, oraclerep handling, removal of the info keys."""
+    from tests.golden.make_golden_loader import MAKE_CASES, file_stem
+
+    want = np.load(os.path.join(HERE, 'loader_make_datasets.npz'))
+    raw_dir = os.path.join(HERE, 'loader_raw')
+    for name, _, cubes, add_info in MAKE_CASES:
+        got = loader.make_datasets(name, dataset_path=os.path.join(raw_dir, file_stem(name) + '.npz'), compact_dataset=True,
+                                   add_info=add_info, num_cubes=cubes)
+        for split, ds in zip(('train', 'val'), got):
+            prefix = f'{name}/{split}/'
+            keys = {k[len(prefix):] for k in want.files if k.startswith(prefix)}
+            assert set(ds) == keys, (name, split, set(ds) ^ keys)
+            for k in keys:
+                w = want[prefix + k]
+                assert ds[k].dtype == w.dtype and ds[k].shape == w.shape and np.array_equal(ds[k], w), (name, split, k)
+    with pytest.raises(NotImplementedError):
+        loader.make_datasets('cube-single-play-singletask-v0', dataset_path='x.npz')
+    with pytest.raises(FileNotFoundError):
+        loader.make_datasets('antmaze-large-navigate-v0', dataset_dir=raw_dir + '/missing')
+
+
 def test_list_shards(tmp_path):
     for n in ('b.npz', 'a.npz', 'a-val.npz', 'c.txt'):
         (tmp_path / n).write_bytes(b'')
