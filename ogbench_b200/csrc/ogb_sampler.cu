@@ -27,6 +27,51 @@
 namespace {
 
 thread_local std::string g_error;
+
+// Measurement switches, read once from the environment.  None of them is needed in production: each forces one of the
+// alternatives DESIGN.md's "measured alternatives" table compares, so that the A/B can be repeated on a box with
+// scratch/ab.sh without rebuilding.  Results are identical under every setting: they choose between kernels the parity tests cover.
+struct AbSwitches {
+  bool no_segments;      // OGB_NO_SEGMENTS     general bucketed searches instead of the segment table
+  bool no_records;       // OGB_NO_RECORDS      one array per field instead of the packed record table
+  int record_align;      // OGB_RECORD_ALIGN=n  record stride rounded to n bytes instead of 128
+  int band_rows;         // OGB_BAND_ROWS=n     first band height tried by the frame kernel instead of 32
+  bool no_overlap;       // OGB_NO_OVERLAP      index kernel on the main stream, never under the previous gather
+  bool no_fuse;          // OGB_NO_FUSE         never fuse the index algebra into the gather kernel
+  int fuse;              // OGB_FUSE=0|1        force the fused kernel off / on (-1: the built-in policy)
+  bool gather_lsu;       // OGB_GATHER=lsu      register-staged gather kernel instead of the cp.async rings
+  bool no_tiny_groups;   // OGB_NO_TINY_GROUPS  small fields copied one by one instead of grouped record loads
+  bool no_smem_tables;   // OGB_NO_SMEM_TABLES  index kernel never keeps the segment table in shared memory
+  bool smem_tables;      // OGB_SMEM_TABLES     ... and keeps it there on the main stream too
+  int stage_bytes;       // OGB_STAGE_BYTES=n   per-warp stage budget instead of 4096 / 6144
+  int ws;                // OGB_WS=0|1          warp-specialised fused kernel off / on (-1: ogb_sampler_set_debug decides)
+  bool timeline;         // OGB_TIMELINE        record an event per phase for ogb_debug_timeline
+};
+
+const AbSwitches& ab() {
+  static const AbSwitches sw = [] {
+    auto flag = [](const char* name) { return getenv(name) != nullptr; };
+    auto number = [](const char* name, int absent) { const char* v = getenv(name); return v ? atoi(v) : absent; };
+    const char* gather = getenv("OGB_GATHER");
+    AbSwitches a;
+    a.no_segments = flag("OGB_NO_SEGMENTS");
+    a.no_records = flag("OGB_NO_RECORDS");
+    a.record_align = number("OGB_RECORD_ALIGN", 0);
+    a.band_rows = number("OGB_BAND_ROWS", 0);
+    a.no_overlap = flag("OGB_NO_OVERLAP");
+    a.no_fuse = flag("OGB_NO_FUSE");
+    a.fuse = number("OGB_FUSE", -1);
+    a.gather_lsu = gather != nullptr && strcmp(gather, "lsu") == 0;
+    a.no_tiny_groups = flag("OGB_NO_TINY_GROUPS");
+    a.no_smem_tables = flag("OGB_NO_SMEM_TABLES");
+    a.smem_tables = flag("OGB_SMEM_TABLES");
+    a.stage_bytes = number("OGB_STAGE_BYTES", 0);
+    a.ws = number("OGB_WS", -1);
+    a.timeline = flag("OGB_TIMELINE");
+    return a;
+  }();
+  return sw;
+}
 std::vector<cudaEvent_t> g_timeline;   // OGB_TIMELINE=1: four events per sample() call (index begin/end, gather begin/end)
 
 int fail(int code, const char* fmt, ...) {
@@ -473,7 +518,7 @@ void batch_unref(ogb_batch* b) {
 // general searches.
 int build_segment_table(ogb_sampler* s) {
   const ogb_dataset* ds = s->ds;
-  if (ds->valid_mode != 2 || ds->gaps_host.empty() || static_cast<const char*>(getenv("OGB_NO_SEGMENTS")) != nullptr) return 0;
+  if (ds->valid_mode != 2 || ds->gaps_host.empty() || ab().no_segments) return 0;
   const std::vector<int32_t>& c = ds->gaps_host;
   const size_t n_gaps = c.size();
   int64_t min_gap = ds->n_valid;
@@ -680,8 +725,7 @@ bool tma_eligible(const Field& f, const ogb_config& cfg, int fs) {
 }
 
 int band_rows_for(int64_t H, int pad) {
-  static const int env_rb = getenv("OGB_BAND_ROWS") ? atoi(getenv("OGB_BAND_ROWS")) : 0;   // A/B of the band height
-  for (int rb = env_rb > 0 ? env_rb : 32; rb > pad; --rb)
+  for (int rb = ab().band_rows > 0 ? ab().band_rows : 32; rb > pad; --rb)
     if (H % rb == 0) return rb;
   return 0;
 }
@@ -766,7 +810,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   // gathers them all at the same row) then cost one aligned span instead of one granule each, and a goal row costs
   // ceil(obs_bytes / 64) granules.  Larger rows (image frames) keep an array of their own.
   constexpr size_t kRecordMaxRow = 2048, kRecordMaxBytes = 4096;
-  static const bool no_records = getenv("OGB_NO_RECORDS") != nullptr;
+  const bool no_records = ab().no_records;
   std::vector<int> order;
   for (int i = 0; i < n_fields; ++i) {
     const ogb_field& in = fields[i];
@@ -818,7 +862,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
       // 32- and 64-byte records stay sector / granule sized; longer ones are padded to whole 128-byte L2 lines, so that a
       // goal row (a prefix of the record) never straddles a line (measured on the 156-byte C2 record: stride 256 is
       // 8 % faster than 160 or 192 and 3 % faster than separate arrays)
-      static const int env_align = getenv("OGB_RECORD_ALIGN") ? atoi(getenv("OGB_RECORD_ALIGN")) : 0;
+      const int env_align = ab().record_align;
       ds->record_stride = cursor <= 32 ? 32 : cursor <= 64 ? 64 : round_up(cursor, env_align >= 32 ? (size_t)env_align : 128);
       const size_t bytes = (size_t)size * ds->record_stride;
       cudaError_t e = cudaMalloc((void**)&ds->record_base, bytes);
@@ -1233,12 +1277,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   // Phase-one work (uploads of validation draws, the index kernel) goes to `first`: for big launches that is the
   // auxiliary stream, so that the index kernel of this call overlaps the gathers of the previous call, which are
   // still running on the main stream.  The recycled block only has to wait for its own previous owner.
-  static const char* no_overlap = getenv("OGB_NO_OVERLAP");
-  static const char* no_fuse = getenv("OGB_NO_FUSE");
-  static const char* force_gather = getenv("OGB_GATHER");  // "lsu" forces the register-staged kernel (A/B measurements)
+  const bool no_overlap = ab().no_overlap, no_fuse = ab().no_fuse, gather_lsu = ab().gather_lsu;
   auto takes_async_path = [&](const Field& f) {
     return f.row_bytes > 16 && f.stride <= (size_t)ogb::kAsyncMaxStride && (size_t)ds->size * f.stride < ((size_t)1 << 36) &&
-           !(force_gather && strcmp(force_gather, "lsu") == 0);
+           !gather_lsu;
   };
   // When some key goes through the cp.async row gather, the index algebra is fused into that launch (one kernel per
   // sample() for vector observations); otherwise the index kernel runs on its own.
@@ -1246,9 +1288,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   // and loses for the heavier HGC algebra with its 16-row items (C3 0.757 vs 0.730 ms), so big HGC launches stay split;
   // small launches always fuse (one kernel launch less).  Image batches keep the index kernel apart (it overlaps the
   // previous call's frame gathers).  OGB_FUSE=0/1 forces either.
-  static const char* fuse_env = getenv("OGB_FUSE");
+  const int fuse_env = ab().fuse;
   bool fuse = false;
-  if (!no_fuse && (fuse_env ? atoi(fuse_env) != 0 : (!any_frames && (total < kOverlapMinRows || spec.kind != OGB_KIND_HGC))))
+  if (!no_fuse && (fuse_env >= 0 ? fuse_env != 0 : (!any_frames && (total < kOverlapMinRows || spec.kind != OGB_KIND_HGC))))
     for (const KeyPlan& k : plan)
       if (k.route == ROUTE_ROW && k.alias_of < 0 && takes_async_path(ds->fields[(size_t)k.field])) fuse = true;
   // Image batches are few rows with long gathers: their (latency-bound) index kernel always goes to the auxiliary
@@ -1443,7 +1485,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     for (size_t i = 0; i < plan.size(); ++i) {
       if (plan[i].route != ROUTE_ROW || plan[i].alias_of >= 0) continue;
       const Field& f = ds->fields[(size_t)plan[i].field];
-      if (f.in_record && f.stride <= (size_t)kAsyncMaxStride && !(force_gather && strcmp(force_gather, "lsu") == 0) &&
+      if (f.in_record && f.stride <= (size_t)kAsyncMaxStride && !gather_lsu &&
           (size_t)ds->size * f.stride < ((size_t)1 << 36)) {
         record_keys[plan[i].slot].push_back(i);
       } else if (add_tiny(i)) {
@@ -1478,7 +1520,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
           // all tiny.  Fields of whole 4-byte words whose span fits two 16-byte loads become one group of the index
           // kernel (one record load for all of them); whatever does not fit is copied field by field.
           size_t k = k0;
-          static const bool no_groups = getenv("OGB_NO_TINY_GROUPS") != nullptr;
+          const bool no_groups = ab().no_tiny_groups;
           while (!no_groups && k < k1 && p.n_tiny_groups < kMaxTinyGroups) {
             const Field& fa = ds->fields[(size_t)plan[keys[k]].field];
             const size_t glo = fa.rec_off & ~(size_t)15;
@@ -1547,11 +1589,11 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     const int flavour = p.kind == OGB_KIND_GC ? FLAVOUR_GC : (p.kind == OGB_KIND_HGC ? FLAVOUR_HGC : FLAVOUR_PLAIN);
     const bool inject = draws != nullptr;
     // Big launches over a dataset whose segment table is small: persistent CTAs keep the table in shared memory.
-    static const bool no_smem_tables = getenv("OGB_NO_SMEM_TABLES") != nullptr;
+    const bool no_smem_tables = ab().no_smem_tables;
     const size_t table_bytes = (size_t)p.n_seg_table * 16 + (size_t)p.n_seg_bucket * 4;
     // Used when the index kernel runs on the auxiliary stream under another call's gather: the persistent form with few
     // CTAs disturbs the gather less (C3 0.716 vs 0.730 ms); alone on its stream the plain grid is faster (C1 0.047 vs 0.049).
-    static const bool force_smem_tables = getenv("OGB_SMEM_TABLES") != nullptr;
+    const bool force_smem_tables = ab().smem_tables;
     const bool smem_tables = !no_smem_tables && (st != s->stream || force_smem_tables) && p.valid_mode == 3 && table_bytes > 0 &&
                              table_bytes <= 48 * 1024 && end - begin >= 65536;
     const void* fn = nullptr;
@@ -1594,7 +1636,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) max_pitch = std::max(max_pitch, span_jobs[t].bytes);
     // rows per item: the largest power of two whose rows fit the stage budget, so that the items of a 32-row tile are
     // equal (an uneven split, e.g. 28 + 4 rows, makes the short item hold a pipeline slot for little data)
-    static const int env_stage = getenv("OGB_STAGE_BYTES") ? atoi(getenv("OGB_STAGE_BYTES")) : 0;
+    const int env_stage = ab().stage_bytes;
     // budget: 4 KB stages (2 CTAs per SM) for rows up to 256 bytes, 6 KB (16-row items, 1 CTA per SM) beyond -- C3's
     // 384/288-byte spans run 15 % faster with 16-row items than with 8-row ones
     const size_t budget = std::max<size_t>(env_stage ? (size_t)env_stage : (max_pitch > 256 ? 6144 : 4096), max_pitch);
@@ -1653,10 +1695,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       // Measured on B200: equal to the same-warp fusion on C2 (0.200 vs 0.203 ms) and slower on C5 (0.371 vs 0.361 ms) --
       // the index algebra costs the SM the same whichever warp runs it -- so it is off unless asked for
       // (OGB_WS=1 or ogb_sampler_set_debug bit 2).
-      static const char* ws_env = getenv("OGB_WS");
+      const int ws_env = ab().ws;
       const int n_slots_fl = flavour == FLAVOUR_GC ? GC_TRL_NUM_SLOTS : (flavour == FLAVOUR_HGC ? HGC_NUM_SLOTS : 2);
       const size_t ws_smem = smem + (size_t)kAsyncWarps * ((size_t)kQueueDepth * n_slots_fl * 128 + 16 * kQueueDepth);
-      const bool ws = (ws_env ? atoi(ws_env) != 0 : s->prefer_ws) && ws_smem <= 113 * 1024;
+      const bool ws = (ws_env >= 0 ? ws_env != 0 : s->prefer_ws) && ws_smem <= 113 * 1024;
       fused_name = ws ? "relabel_gather_ws_kernel" : "relabel_gather_kernel";
       fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
         FusedParams& f = *keep;
@@ -1832,7 +1874,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
 
   // ---- issue: index kernel on `first`, gathers on the main stream behind it ----
   {
-    static const bool timeline = getenv("OGB_TIMELINE") != nullptr;   // debug: when did each phase run on the device
+    const bool timeline = ab().timeline;   // debug: when did each phase run on the device
     auto stamp = [&](cudaStream_t st) {
       if (!timeline) return;
       cudaEvent_t ev;
