@@ -185,6 +185,7 @@ int ogb_batch_num_keys(const ogb_batch* b, int32_t* out);
 int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out);
 int ogb_batch_keep_leading_axis(ogb_batch* b, int32_t on);        /* shapes keep the [n_batches] axis even when n_batches == 1 */
 int ogb_batch_nbytes(const ogb_batch* b, size_t* out);            /* size of the single device block */
+int ogb_batch_device_block(const ogb_batch* b, void** out);       /* its base: key i lives at base + ogb_key_info.offset */
 int ogb_batch_launches(const ogb_batch* b, int32_t* out);         /* kernels launched to produce it */
 int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms); /* the kernel that moved the batch's bytes and, in
                                                                      profile mode, its device time (host-waits for it); else -1 */

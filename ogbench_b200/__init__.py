@@ -6,5 +6,6 @@ HBM, hand-written sm_100a CUDA kernels behind a C-ABI (include/ogb_sampler.h).  
 
 from .datasets import ATCDataset, Dataset, GCDataset, HGCDataset, ReplayBuffer, get_size  # noqa: F401
 from .device_array import DeviceArray  # noqa: F401
+from .prefetch import Prefetcher  # noqa: F401
 
-__all__ = ['Dataset', 'GCDataset', 'HGCDataset', 'ATCDataset', 'ReplayBuffer', 'DeviceArray', 'get_size']
+__all__ = ['Dataset', 'GCDataset', 'HGCDataset', 'ATCDataset', 'ReplayBuffer', 'DeviceArray', 'Prefetcher', 'get_size']

@@ -104,6 +104,7 @@ SIGNATURES = [
     ('ogb_batch_num_keys', C.c_int, [_P, C.POINTER(C.c_int32)]),
     ('ogb_batch_key_info', C.c_int, [_P, C.c_int32, C.POINTER(KeyInfo)]),
     ('ogb_batch_nbytes', C.c_int, [_P, C.POINTER(C.c_size_t)]),
+    ('ogb_batch_device_block', C.c_int, [_P, C.POINTER(_P)]),
     ('ogb_batch_launches', C.c_int, [_P, C.POINTER(C.c_int32)]),
     ('ogb_batch_dominant_kernel', C.c_int, [_P, _P, _P]),
     ('ogb_batch_keep_leading_axis', C.c_int, [_P, C.c_int32]),

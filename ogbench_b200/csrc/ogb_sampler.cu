@@ -2265,6 +2265,11 @@ int ogb_batch_nbytes(const ogb_batch* b, size_t* out) {
   *out = b->keys_bytes;
   return 0;
 }
+int ogb_batch_device_block(const ogb_batch* b, void** out) {
+  if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
+  *out = b->block;
+  return 0;
+}
 int ogb_batch_launches(const ogb_batch* b, int32_t* out) {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->launches;

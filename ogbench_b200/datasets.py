@@ -426,7 +426,7 @@ class _Sampler:
         idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64).reshape(-1)
         out = C.c_void_p()
         _native.check(_native.lib().ogb_sampler_gather(self.ptr, which, idxs.ctypes.data_as(C.c_void_p), len(idxs), C.byref(out)))
-        return next(iter(self.wrap(BatchHandle(out, self.device, None)).values()))
+        return next(iter(self.wrap(BatchHandle(out, self.device, None), ('gather', int(which), len(idxs))).values()))
 
     def sample_atc(self, batch_size, k, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         keep = []
@@ -436,7 +436,7 @@ class _Sampler:
                                                            C.byref(c_draws) if c_draws is not None else None, C.byref(out)))
         if keep_axis:
             _native.check(_native.lib().ogb_batch_keep_leading_axis(out, 1))
-        return self.wrap(BatchHandle(out, self.device, None))
+        return self.wrap(BatchHandle(out, self.device, None), ('atc', int(batch_size), int(n_batches), int(k), bool(evaluation), bool(keep_axis)))
 
     def atc_anchors(self, k) -> np.ndarray:
         n = C.c_int64()
@@ -445,36 +445,38 @@ class _Sampler:
         _native.check(_native.lib().ogb_sampler_copy_atc_anchors(self.ptr, int(k), out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def wrap(self, handle: BatchHandle, layout_key=None) -> Dict[str, Any]:
+    def _read_layout(self, handle: BatchHandle):
+        """(block bytes, [(name, dtype, shape, offset, nbytes) per key]) of a batch, asked from the library."""
         lib = _native.lib()
-        if self.output == 'device':
-            n = C.c_int32()
-            _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
-            out = {}
-            for i in range(n.value):
-                info = _native.KeyInfo()
-                _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
-                out[info.name.decode()] = DeviceArray(handle, i, info)
-            return out
-        # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it.  The layout of
-        # the block (name, dtype, shape, offset of every key) is a function of the call's shape only, so it is read once
-        # per (batch_size, n_batches, evaluation, ...) and reused.
+        n = C.c_int32()
+        _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
+        keys = []
+        for i in range(n.value):
+            info = _native.KeyInfo()
+            _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
+            keys.append((info.name.decode(), _native.CODE_TO_DTYPE[info.dtype], tuple(int(info.shape[d]) for d in range(info.ndim)),
+                         int(info.offset), int(info.nbytes)))
+        nbytes = C.c_size_t()
+        _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
+        return (max(nbytes.value, 1), keys)
+
+    def wrap(self, handle: BatchHandle, layout_key=None) -> Dict[str, Any]:
+        """Batch handle -> dict of arrays.  The layout of a batch's block (name, dtype, shape, offset of every key) is a
+        function of the call's shape only, so it is read once per (batch_size, n_batches, evaluation, ...) and reused:
+        a steady-state call crosses the C boundary once or twice, not once per key."""
+        lib = _native.lib()
         layout = self._layouts.get(layout_key) if layout_key is not None else None
         if layout is None:
-            n = C.c_int32()
-            _native.check(lib.ogb_batch_num_keys(handle.ptr, C.byref(n)))
-            keys = []
-            for i in range(n.value):
-                info = _native.KeyInfo()
-                _native.check(lib.ogb_batch_key_info(handle.ptr, i, C.byref(info)))
-                keys.append((info.name.decode(), _native.CODE_TO_DTYPE[info.dtype], tuple(int(info.shape[d]) for d in range(info.ndim)),
-                             int(info.offset), int(info.nbytes)))
-            nbytes = C.c_size_t()
-            _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
-            layout = (max(nbytes.value, 1), keys)
+            layout = self._read_layout(handle)
             if layout_key is not None:
                 self._layouts[layout_key] = layout
         total, keys = layout
+        if self.output == 'device':
+            base = C.c_void_p()
+            _native.check(lib.ogb_batch_device_block(handle.ptr, C.byref(base)))
+            base = base.value or 0
+            return {name: DeviceArray(handle, i, name, dtype, shape, base + off, nb) for i, (name, dtype, shape, off, nb) in enumerate(keys)}
+        # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it
         block = _PINNED.take(total)
         _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
         raw = (C.c_ubyte * total).from_address(block.ptr)

@@ -71,14 +71,14 @@ class DeviceArray:
 
     __slots__ = ('_batch', '_index', 'shape', 'dtype', 'ptr', 'nbytes', 'name')
 
-    def __init__(self, batch: BatchHandle, index: int, info: '_native.KeyInfo'):
+    def __init__(self, batch: BatchHandle, index: int, name: str, dtype, shape, ptr: int, nbytes: int):
         self._batch = batch
         self._index = index
-        self.shape = tuple(int(info.shape[d]) for d in range(info.ndim))
-        self.dtype = _native.CODE_TO_DTYPE[info.dtype]
-        self.ptr = int(info.device_ptr)
-        self.nbytes = int(info.nbytes)
-        self.name = info.name.decode()
+        self.shape = shape
+        self.dtype = dtype
+        self.ptr = ptr
+        self.nbytes = nbytes
+        self.name = name
 
     # ---- array-ish surface ----
     @property

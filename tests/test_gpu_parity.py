@@ -212,6 +212,25 @@ def test_large_batch_numpy_rng_matches_oracle(kind):
         got = sampler.sample(40000)
         assert_batches_identical(got, want, label=f'large/{kind}/{it}:')
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('output', ['device', 'numpy'])
+def test_cached_key_layout_across_calls(output):
+    """The Python wrapper reads a batch's key layout once per call shape and reuses it (`_Sampler.wrap`): successive calls
+    of alternating shapes, with and without given idxs, must keep returning the oracle's arrays."""
+    lengths = ragged(43, 60, 5, 40)
+    fields = toy_fields(43, lengths, (6,), 3, np.float32)
+    config = cfg(subgoal_steps=4)
+    for kind in ('gc', 'hgc'):
+        sampler = device_sampler(fields, config, kind, rng='numpy', output=output)
+        for it, B in enumerate([100, 37, 100, 37, 1, 100]):
+            idxs = np.arange(B) * 2 if it in (2, 3) else None
+            np.random.seed(900 + it)
+            _, want = oracle_with_draws(fields, config, kind, B, idxs=idxs, evaluation=(it == 5))
+            np.random.seed(900 + it)
+            got = sampler.sample(B, idxs=idxs, evaluation=(it == 5))
+            assert_batches_identical(to_host(got), want, label=f'layout/{kind}/{it}:')
+        assert len(sampler._sampler._layouts) == 4      # (100), (37), (1), (100, evaluation)
+
 
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')

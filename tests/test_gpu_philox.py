@@ -403,3 +403,22 @@ def test_full_size_pixels_c4():
     for key, slot in (('observations', 0), ('next_observations', 1), ('value_goals', 2), ('actor_goals', 3)):
         got = out[key].reshape(n, 64, 64, 9)
         assert torch.equal(got, expected(slot)), key
+
+
+@pytest.mark.parametrize('output', ['device', 'numpy'])
+def test_prefetcher_returns_the_direct_call_sequence(output):
+    """Prefetcher (batches drawn by a worker thread, ahead of the consumer) yields exactly the batches that direct
+    sample() calls on a sampler with the same seed return, in order."""
+    from ogbench_b200 import Dataset, GCDataset, Prefetcher
+    from tests.golden.make_golden import cfg, ragged, toy_fields
+
+    fields = toy_fields(77, ragged(77, 50, 5, 60), (9,), 3, np.float32)
+    config = cfg()
+    direct = GCDataset(Dataset.create(**{k: v.copy() for k, v in fields.items()}), config, seed=5, output=output)
+    ahead = GCDataset(Dataset.create(**{k: v.copy() for k, v in fields.items()}), config, seed=5, output=output)
+    with Prefetcher(ahead, 64, depth=3) as batches:
+        for step in range(12):
+            want, got = direct.sample(64), next(batches)
+            assert set(want) == set(got)
+            for k in want:
+                assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), (step, k)

@@ -133,3 +133,46 @@ def test_workload_catalogue_is_consistent():
     assert w['c3'].bytes_per_transition == (7 * obs['c3'] + act['c3'] + 8) + (7 * obs['c3'] + act['c3'] + 8 + 9 * 8)
     assert w['c4'].bytes_per_transition == (10 * obs['c4'] + act['c4'] + 8) + (4 * 3 * obs['c4'] + act['c4'] + 8 + 16)
     assert w['c5'].rows == 12_512_500 and w['c3'].rows == 4_001_000
+
+
+def test_prefetcher_order_errors_and_close():
+    """Prefetcher hands out dataset.sample() results in call order, passes keyword arguments on, surfaces the worker's
+    exception at the consumer, refuses the np.random replay mode and stops cleanly."""
+    import time
+
+    from ogbench_b200.prefetch import Prefetcher
+
+    class Fake:
+        rng = 'philox'
+
+        def __init__(self, fail_at=None):
+            self.calls, self.fail_at = 0, fail_at
+
+        def sample(self, batch_size, evaluation=False):
+            if self.calls == self.fail_at:
+                raise RuntimeError('boom')
+            self.calls += 1
+            return {'n': self.calls, 'batch_size': batch_size, 'evaluation': evaluation}
+
+    fake = Fake()
+    with Prefetcher(fake, 7, depth=3, evaluation=True) as batches:
+        got = [next(batches) for _ in range(20)]
+        assert [g['n'] for g in got] == list(range(1, 21))
+        assert all(g['batch_size'] == 7 and g['evaluation'] for g in got)
+        time.sleep(0.05)
+        assert fake.calls <= 20 + 3 + 1          # at most depth queued + one in hand
+        worker = batches._thread
+    assert not worker.is_alive()
+    with pytest.raises(StopIteration):
+        next(batches)
+
+    failing = Prefetcher(Fake(fail_at=2), 4)
+    assert next(failing)['n'] == 1 and next(failing)['n'] == 2
+    with pytest.raises(RuntimeError, match='boom'):
+        next(failing)
+    failing.close()
+
+    numpy_mode = Fake()
+    numpy_mode.rng = 'numpy'
+    with pytest.raises(ValueError):
+        Prefetcher(numpy_mode, 4)
