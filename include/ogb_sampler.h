@@ -5,7 +5,8 @@
  * impls/utils/datasets.py.  This header is the boundary a ctypes stub binds; each entry
  * point cites the reference interface it stands in for.  Plain pointers and sizes only, no torch types.
  * All functions return 0 on success and a negative ogb_status on failure; ogb_last_error() gives the message
- * (thread-local).  There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * (thread-local).  No C++ exception crosses this boundary: an internal one (e.g. host memory exhausted) comes back
+ * as a status code.  There is no CPU fallback: without a CUDA device every compute entry point fails with
  * OGB_ERR_CUDA.
  */
 #ifndef OGB_SAMPLER_H_

@@ -84,6 +84,21 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// No C++ exception may cross the C boundary (the callers are ctypes / cgo-style bindings): every entry point is a
+// function-try-block that turns an exception into a status code and a message for ogb_last_error().
+int fail_from_exception() {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    return fail(OGB_ERR_UNSUPPORTED, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(OGB_ERR_INVALID, "internal error: %s", e.what());
+  } catch (...) {
+    return fail(OGB_ERR_INVALID, "internal error: unknown exception");
+  }
+}
+#define OGB_CATCH_ALL catch (...) { return fail_from_exception(); }
+
 #define OGB_CUDA(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t err_ = (expr);                                                                           \
@@ -766,13 +781,13 @@ extern "C" {
 const char* ogb_last_error(void) { return g_error.c_str(); }
 int ogb_abi_version(void) { return OGB_ABI_VERSION; }
 
-int ogb_device_count(int* out) {
+int ogb_device_count(int* out) try {
   if (!out) return fail(OGB_ERR_INVALID, "null out");
   OGB_CUDA(cudaGetDeviceCount(out));
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out) {
+int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out) try {
   if (!fields || n_fields <= 0 || !out) return fail(OGB_ERR_INVALID, "ogb_dataset_create: bad arguments");
   OGB_CUDA(cudaSetDevice(device));
   ogb_dataset* ds = new ogb_dataset();
@@ -962,36 +977,36 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   }
   *out = ds;
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_dataset_size(const ogb_dataset* ds, int64_t* out) {
+int ogb_dataset_size(const ogb_dataset* ds, int64_t* out) try {
   if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = ds->size;
   return 0;
-}
-int ogb_dataset_set_active_rows(ogb_dataset* ds, int64_t n) {
+} OGB_CATCH_ALL
+int ogb_dataset_set_active_rows(ogb_dataset* ds, int64_t n) try {
   if (!ds) return fail(OGB_ERR_INVALID, "null dataset");
   if (n < 0 || n > ds->size) return fail(OGB_ERR_INVALID, "active rows must be in [0, %lld]", (long long)ds->size);
   ds->active_rows = n;
   return 0;
-}
-int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out) {
+} OGB_CATCH_ALL
+int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out) try {
   if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = ds->n_valid;
   return 0;
-}
-int ogb_dataset_resident_bytes(const ogb_dataset* ds, size_t* out) {
+} OGB_CATCH_ALL
+int ogb_dataset_resident_bytes(const ogb_dataset* ds, size_t* out) try {
   if (!ds || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = ds->resident_bytes;
   return 0;
-}
-int ogb_dataset_destroy(ogb_dataset* ds) {
+} OGB_CATCH_ALL
+int ogb_dataset_destroy(ogb_dataset* ds) try {
   if (!ds) return fail(OGB_ERR_INVALID, "null dataset");
   dataset_unref(ds);
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uint64_t seed, uint32_t stream_id, ogb_sampler** out) {
+int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uint64_t seed, uint32_t stream_id, ogb_sampler** out) try {
   if (!ds || !cfg || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_create: null argument");
   if (kind < OGB_KIND_GC || kind > OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "unknown sampler kind %d", kind);
   if (stream_id >= (1u << 24)) return fail(OGB_ERR_INVALID, "stream_id must be < 2^24");
@@ -1067,9 +1082,9 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
   s->plan[1] = build_plan(s, true);
   *out = s;
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
+int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   std::lock_guard<std::mutex> lock(s->mu);
   if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks may still be in flight on the old stream
@@ -1078,40 +1093,40 @@ int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) {
   s->stream = (cudaStream_t)cuda_stream;
   s->owns_stream = false;
   return 0;
-}
-int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks) {
+} OGB_CATCH_ALL
+int ogb_sampler_set_host_chunks(ogb_sampler* s, int32_t n_chunks) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   if (n_chunks < 1 || n_chunks > kMaxChunks) return fail(OGB_ERR_INVALID, "n_chunks must be in [1, %d]", kMaxChunks);
   s->host_chunks = n_chunks;
   return 0;
-}
-int ogb_sampler_set_deferred_index_check(ogb_sampler* s, int32_t on) {
+} OGB_CATCH_ALL
+int ogb_sampler_set_deferred_index_check(ogb_sampler* s, int32_t on) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->defer_index_check = on != 0;
   return 0;
-}
-int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) {
+} OGB_CATCH_ALL
+int ogb_sampler_set_profile(ogb_sampler* s, int32_t on) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->profile = on != 0;
   return 0;
-}
-int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) {
+} OGB_CATCH_ALL
+int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->debug = (keep & 1) != 0;
   s->canary = (keep & 2) != 0;
   s->prefer_ws = (keep & 4) != 0;
   return 0;
-}
-int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) {
+} OGB_CATCH_ALL
+int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   if (s->trl_rows.dev) *out = (int64_t)s->trl_rows.host.size();
   else *out = s->ds->valid_mode == 0 ? s->ds->active_rows : s->ds->n_valid;
   return 0;
-}
+} OGB_CATCH_ALL
 
 // ReplayBuffer.add_transition (datasets.py:134-142): overwrite row `row` of every field, ordered on the sampler's
 // stream after the sample() calls already issued and before the ones that follow.
-int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_rows, int32_t n_fields) {
+int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_rows, int32_t n_fields) try {
   if (!s || !field_rows) return fail(OGB_ERR_INVALID, "null argument");
   ogb_dataset* ds = s->ds;
   if (row < 0 || row >= ds->size) return fail(OGB_ERR_INDEX, "row %lld out of range", (long long)row);
@@ -1130,35 +1145,35 @@ int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_
     OGB_CUDA(cudaMemcpyAsync(f.dptr + (size_t)row * f.stride, field_rows[i], f.row_bytes, cudaMemcpyHostToDevice, s->stream));
   }
   return 0;
-}
-int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out) {
+} OGB_CATCH_ALL
+int ogb_sampler_num_terminals(const ogb_sampler* s, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = (int64_t)s->term_host.size();
   return 0;
-}
-int ogb_sampler_copy_bounds(const ogb_sampler* s, int64_t* terminal_locs, int64_t* initial_locs) {
+} OGB_CATCH_ALL
+int ogb_sampler_copy_bounds(const ogb_sampler* s, int64_t* terminal_locs, int64_t* initial_locs) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   for (size_t i = 0; i < s->term_host.size(); ++i) {
     if (terminal_locs) terminal_locs[i] = s->term_host[i];
     if (initial_locs) initial_locs[i] = i == 0 ? 0 : (int64_t)s->term_host[i - 1] + 1;  // datasets.py:187
   }
   return 0;
-}
-int ogb_sampler_get_counter(const ogb_sampler* s, uint64_t* out) {
+} OGB_CATCH_ALL
+int ogb_sampler_get_counter(const ogb_sampler* s, uint64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = s->counter;
   return 0;
-}
-int ogb_sampler_set_counter(ogb_sampler* s, uint64_t counter) {
+} OGB_CATCH_ALL
+int ogb_sampler_set_counter(ogb_sampler* s, uint64_t counter) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   s->counter = counter;
   return 0;
-}
-int ogb_sampler_destroy(ogb_sampler* s) {
+} OGB_CATCH_ALL
+int ogb_sampler_destroy(ogb_sampler* s) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
   sampler_unref(s);
   return 0;
-}
+} OGB_CATCH_ALL
 
 }  // extern "C"
 
@@ -1943,7 +1958,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
 extern "C" {
 
 int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
-                       const ogb_draws* draws, ogb_batch** out) {
+                       const ogb_draws* draws, ogb_batch** out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
   if (s->kind == OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "an ATC sampler is sampled with ogb_sampler_sample_atc");
   RunSpec spec;
@@ -1956,11 +1971,11 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
     spec.n_choices = (int64_t)s->trl_rows.host.size();
   }
   return run_sample(s, spec, batch_size, n_batches, idxs, evaluation, draws, out);
-}
+} OGB_CATCH_ALL
 
 // get_observations / get_goal_observations (datasets.py:341-357): rows `idxs` of the observations (frame-stacked as
 // the sampler's config says) or of the goal representation.
-int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out) {
+int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out) try {
   if (!s || !idxs || !out || n < 1) return fail(OGB_ERR_INVALID, "ogb_sampler_gather: bad argument");
   if (which < 0 || which > 1) return fail(OGB_ERR_INVALID, "which must be 0 (observations) or 1 (goal observations)");
   PlanBuilder pb;
@@ -1977,12 +1992,12 @@ int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64
   const int fs = s->cfg.frame_stack;
   if (fs > 0 && s->term_host.empty()) return fail(OGB_ERR_INVALID, "frame stacking needs trajectory boundaries");
   return run_sample(s, spec, n, 1, idxs, 1, nullptr, out);
-}
+} OGB_CATCH_ALL
 
 // GCDataset.augment (datasets.py:329-339) for one image array: rows `idxs` of the observations, each cropped with its
 // own (cy, cx) shift after edge padding by `padding` (datasets.py:17-33).  `crop` is [n, 2] int64 (host), the
 // reference's randint(0, 2 * padding + 1, (n, 2)).
-int ogb_sampler_gather_cropped(ogb_sampler* s, const int64_t* idxs, int64_t n, const int64_t* crop, int32_t padding, ogb_batch** out) {
+int ogb_sampler_gather_cropped(ogb_sampler* s, const int64_t* idxs, int64_t n, const int64_t* crop, int32_t padding, ogb_batch** out) try {
   if (!s || !idxs || !crop || !out || n < 1 || padding < 0) return fail(OGB_ERR_INVALID, "ogb_sampler_gather_cropped: bad argument");
   for (int64_t r = 0; r < 2 * n; ++r)
     if (crop[r] < 0 || crop[r] > 2 * (int64_t)padding) return fail(OGB_ERR_INVALID, "crop shift out of [0, 2 * padding]");
@@ -2003,7 +2018,7 @@ int ogb_sampler_gather_cropped(ogb_sampler* s, const int64_t* idxs, int64_t n, c
   d.aug_coin = 0.0;
   d.crop = crop;
   return run_sample(s, spec, n, 1, idxs, 0, &d, out);
-}
+} OGB_CATCH_ALL
 
 }  // extern "C"
 
@@ -2065,7 +2080,7 @@ struct DeviceScratch {   // a few temporary device arrays of a helper call
 extern "C" {
 
 int ogb_sampler_sample_goals(ogb_sampler* s, const int64_t* idxs, int64_t n, double p_curgoal, double p_trajgoal, int32_t geom_sample,
-                             double discount, const ogb_goal_draws* draws, int64_t* out_goal_idxs) {
+                             double discount, const ogb_goal_draws* draws, int64_t* out_goal_idxs) try {
   using namespace ogb;
   if (!s || !idxs || !out_goal_idxs || n < 1) return fail(OGB_ERR_INVALID, "ogb_sampler_sample_goals: bad argument");
   if (s->term_host.empty()) return fail(OGB_ERR_INVALID, "this sampler has no trajectory boundaries");
@@ -2143,10 +2158,10 @@ int ogb_sampler_sample_goals(ogb_sampler* s, const int64_t* idxs, int64_t n, dou
   OGB_CUDA(cudaStreamSynchronize(s->stream));
   if (!draws) s->counter += 1;
   return 0;
-}
+} OGB_CATCH_ALL
 
 int ogb_sampler_compute_high_next_idxs(ogb_sampler* s, const int64_t* idxs, const int64_t* final_state_idxs, const int64_t* goal_idxs,
-                                       int64_t n, int64_t subgoal_steps, int64_t* out_next, int64_t* out_steps) {
+                                       int64_t n, int64_t subgoal_steps, int64_t* out_next, int64_t* out_steps) try {
   if (!s || !idxs || !final_state_idxs || !goal_idxs || !out_next || !out_steps || n < 1)
     return fail(OGB_ERR_INVALID, "ogb_sampler_compute_high_next_idxs: bad argument");
   OGB_CUDA(cudaSetDevice(s->ds->device));
@@ -2164,7 +2179,7 @@ int ogb_sampler_compute_high_next_idxs(ogb_sampler* s, const int64_t* idxs, cons
   OGB_CUDA(cudaMemcpyAsync(out_steps, d_s, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
   OGB_CUDA(cudaStreamSynchronize(s->stream));
   return 0;
-}
+} OGB_CATCH_ALL
 
 namespace {
 // get_valid_atc_idxs (datasets.py:417-436): anchors i with i + k < size and i + k <= final_state(i), valid rows only
@@ -2191,7 +2206,7 @@ int atc_anchors(ogb_sampler* s, int64_t k, const std::vector<int32_t>** host, co
 }
 }  // namespace
 
-int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) {
+int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
   std::lock_guard<std::mutex> lock(s->mu);
@@ -2199,19 +2214,19 @@ int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) {
   OGB_TRY(atc_anchors(s, k, &host, nullptr));
   *out = (int64_t)host->size();
   return 0;
-}
-int ogb_sampler_copy_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) {
+} OGB_CATCH_ALL
+int ogb_sampler_copy_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lock(s->mu);
   const std::vector<int32_t>* host;
   OGB_TRY(atc_anchors(s, k, &host, nullptr));
   for (size_t i = 0; i < host->size(); ++i) out[i] = (*host)[i];
   return 0;
-}
+} OGB_CATCH_ALL
 
 // ATCDataset.sample (datasets.py:401-415): anchor rows for the temporal offset k, observations at idx and idx + k
 int ogb_sampler_sample_atc(ogb_sampler* s, int64_t batch_size, int32_t n_batches, int64_t k, int32_t evaluation,
-                           const ogb_draws* draws, ogb_batch** out) {
+                           const ogb_draws* draws, ogb_batch** out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   if (s->kind != OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "not an ATC sampler");
   if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
@@ -2229,15 +2244,15 @@ int ogb_sampler_sample_atc(ogb_sampler* s, int64_t batch_size, int32_t n_batches
   spec.choice_table = dev;
   spec.n_choices = (int64_t)host->size();
   return run_sample(s, spec, batch_size, n_batches, nullptr, evaluation, draws, out);
-}
+} OGB_CATCH_ALL
 
-int ogb_batch_num_keys(const ogb_batch* b, int32_t* out) {
+int ogb_batch_num_keys(const ogb_batch* b, int32_t* out) try {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = (int32_t)b->keys.size();
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) {
+int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) try {
   if (!b || !out || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad key index");
   const KeyPlan& k = b->keys[(size_t)i];
   memset(out, 0, sizeof(*out));
@@ -2253,29 +2268,29 @@ int ogb_batch_key_info(const ogb_batch* b, int32_t i, ogb_key_info* out) {
   out->nbytes = (size_t)b->total_rows * k.row_bytes;
   out->alias_of = k.alias_of;
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_batch_keep_leading_axis(ogb_batch* b, int32_t on) {
+int ogb_batch_keep_leading_axis(ogb_batch* b, int32_t on) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   b->keep_axis = on != 0;
   return 0;
-}
-int ogb_batch_nbytes(const ogb_batch* b, size_t* out) {
+} OGB_CATCH_ALL
+int ogb_batch_nbytes(const ogb_batch* b, size_t* out) try {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->keys_bytes;
   return 0;
-}
-int ogb_batch_device_block(const ogb_batch* b, void** out) {
+} OGB_CATCH_ALL
+int ogb_batch_device_block(const ogb_batch* b, void** out) try {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->block;
   return 0;
-}
-int ogb_batch_launches(const ogb_batch* b, int32_t* out) {
+} OGB_CATCH_ALL
+int ogb_batch_launches(const ogb_batch* b, int32_t* out) try {
   if (!b || !out) return fail(OGB_ERR_INVALID, "null argument");
   *out = b->launches;
   return 0;
-}
-int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) {
+} OGB_CATCH_ALL
+int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) try {
   if (!b || !name || !ms) return fail(OGB_ERR_INVALID, "null argument");
   *name = b->dominant;
   *ms = -1.0f;
@@ -2284,8 +2299,8 @@ int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) {
     OGB_CUDA(cudaEventElapsedTime(ms, b->prof_begin, b->prof_end));
   }
   return 0;
-}
-int ogb_batch_sync(ogb_batch* b) {
+} OGB_CATCH_ALL
+int ogb_batch_sync(ogb_batch* b) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   OGB_CUDA(cudaEventSynchronize(b->ready));
   if (b->idx_error) {
@@ -2294,8 +2309,8 @@ int ogb_batch_sync(ogb_batch* b) {
     if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)b->sampler->ds->size);
   }
   return 0;
-}
-int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
+} OGB_CATCH_ALL
+int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   cudaStream_t c = (cudaStream_t)consumer_stream;
   if (c == b->sampler->stream) { b->main_stream_consumer = true; return 0; }
@@ -2304,8 +2319,8 @@ int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) {
   std::lock_guard<std::mutex> lock(b->mu);
   if (std::find(b->consumers.begin(), b->consumers.end(), c) == b->consumers.end()) b->consumers.push_back(c);
   return 0;
-}
-int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) {
+} OGB_CATCH_ALL
+int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
   if (!b || !dst) return fail(OGB_ERR_INVALID, "null argument");
   if (nbytes < b->keys_bytes) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, b->keys_bytes);
   ogb_sampler* s = b->sampler;
@@ -2334,8 +2349,8 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) {
   OGB_CUDA(cudaStreamSynchronize(s->stream));
   if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
   return 0;
-}
-int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) {
+} OGB_CATCH_ALL
+int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) try {
   if (!b || !dst || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad argument");
   const size_t need = (size_t)b->total_rows * b->keys[(size_t)i].row_bytes;
   if (nbytes < need) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, need);
@@ -2343,9 +2358,9 @@ int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes
   OGB_CUDA(cudaMemcpyAsync(dst, b->block + b->offsets[(size_t)i], need, cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   return 0;
-}
+} OGB_CATCH_ALL
 // debug (ogb_sampler_set_debug(s, 2)): bytes of the key area that belong to no key must still hold the 0xA5 fill
-int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) {
+int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) try {
   if (!b || !n_bad) return fail(OGB_ERR_INVALID, "null argument");
   if (!b->sampler->canary) return fail(OGB_ERR_INVALID, "the sampler was not put into canary mode before this batch was drawn");
   std::vector<uint8_t> host(b->keys_bytes);
@@ -2362,8 +2377,8 @@ int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) {
   for (size_t k = 0; k < host.size(); ++k) bad += (!owned[k] && host[k] != 0xA5) ? 1 : 0;
   *n_bad = bad;
   return 0;
-}
-int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {
+} OGB_CATCH_ALL
+int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) try {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
   if (slot < 0 || slot >= b->n_slots) return fail(OGB_ERR_INVALID, "bad slot");
   std::vector<int32_t> tmp((size_t)b->total_rows);
@@ -2372,8 +2387,8 @@ int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) {
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   for (size_t i = 0; i < tmp.size(); ++i) dst_host[i] = tmp[i];
   return 0;
-}
-int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) {
+} OGB_CATCH_ALL
+int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) try {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
   if (!b->crop) return fail(OGB_ERR_INVALID, "this batch has no image keys, hence no crop shifts");
   std::vector<int8_t> tmp((size_t)b->total_rows * 2);
@@ -2383,7 +2398,7 @@ int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) {
   const int pad = b->sampler->cfg.crop_padding;
   for (size_t i = 0; i < tmp.size(); ++i) dst_host[i] = tmp[i] == -128 ? -1 : tmp[i] + pad;
   return 0;
-}
+} OGB_CATCH_ALL
 
 static void dl_deleter(DLManagedTensor_* t) {
   if (!t) return;
@@ -2393,7 +2408,7 @@ static void dl_deleter(DLManagedTensor_* t) {
   batch_unref(b);
 }
 
-int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) {
+int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) try {
   if (!b || !out || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad key index");
   ogb_key_info info;
   OGB_TRY(ogb_batch_key_info(b, i, &info));
@@ -2421,35 +2436,35 @@ int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) {
   b->refs.fetch_add(1);
   *out = t;
   return 0;
-}
-int ogb_batch_mark_escaped(ogb_batch* b) {
+} OGB_CATCH_ALL
+int ogb_batch_mark_escaped(ogb_batch* b) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   b->escaped = true;
   return 0;
-}
-int ogb_batch_retain(ogb_batch* b) {
+} OGB_CATCH_ALL
+int ogb_batch_retain(ogb_batch* b) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   b->refs.fetch_add(1);
   return 0;
-}
-int ogb_batch_release(ogb_batch* b) {
+} OGB_CATCH_ALL
+int ogb_batch_release(ogb_batch* b) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   batch_unref(b);
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_host_alloc(size_t nbytes, void** out) {
+int ogb_host_alloc(size_t nbytes, void** out) try {
   if (!out) return fail(OGB_ERR_INVALID, "null out");
   OGB_CUDA(cudaHostAlloc(out, std::max<size_t>(nbytes, 1), cudaHostAllocDefault));
   return 0;
-}
-int ogb_host_free(void* p) {
+} OGB_CATCH_ALL
+int ogb_host_free(void* p) try {
   if (p) OGB_CUDA(cudaFreeHost(p));
   return 0;
-}
+} OGB_CATCH_ALL
 
 int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* keys_host, int64_t m, int32_t side_right,
-                          int32_t device, int64_t* out_host) {
+                          int32_t device, int64_t* out_host) try {
   if (!sorted_host || !keys_host || !out_host || n < 0 || m < 0) return fail(OGB_ERR_INVALID, "bad arguments");
   OGB_CUDA(cudaSetDevice(device));
   int64_t *d_t = nullptr, *d_k = nullptr, *d_o = nullptr;
@@ -2463,9 +2478,9 @@ int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* 
   OGB_CUDA(cudaMemcpy(out_host, d_o, (size_t)m * 8, cudaMemcpyDeviceToHost));
   cudaFree(d_t); cudaFree(d_k); cudaFree(d_o);
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out) {
+int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out) try {
   if (!out_ms || !n_out) return fail(OGB_ERR_INVALID, "null argument");
   OGB_CUDA(cudaDeviceSynchronize());
   const int n = (int)std::min<size_t>(g_timeline.size(), (size_t)std::max(capacity, 0));
@@ -2478,9 +2493,9 @@ int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out) {
   g_timeline.clear();
   *n_out = n;
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t device, int64_t* mismatches) {
+int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t device, int64_t* mismatches) try {
   if (!mismatches || n < 0 || !(discount > 0.0 && discount < 1.0)) return fail(OGB_ERR_INVALID, "bad arguments");
   OGB_CUDA(cudaSetDevice(device));
   unsigned long long* d = nullptr;
@@ -2495,9 +2510,9 @@ int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t devic
   cudaFree(d);
   *mismatches = (int64_t)host;
   return 0;
-}
+} OGB_CATCH_ALL
 
-int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t purpose, int64_t n, int32_t device, uint32_t* out_host) {
+int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t purpose, int64_t n, int32_t device, uint32_t* out_host) try {
   if (!out_host || n < 0) return fail(OGB_ERR_INVALID, "bad arguments");
   OGB_CUDA(cudaSetDevice(device));
   uint4* d = nullptr;
@@ -2508,6 +2523,6 @@ int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t 
   OGB_CUDA(cudaMemcpy(out_host, d, (size_t)n * 16, cudaMemcpyDeviceToHost));
   cudaFree(d);
   return 0;
-}
+} OGB_CATCH_ALL
 
 }  // extern "C"
