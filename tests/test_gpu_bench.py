@@ -1,0 +1,36 @@
+"""The bench line the driver reads: contract keys of bench.py's GPU arm (short run, one GPU)."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_gpu_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '20', '--warmup', '3', '--cpu-seconds', '1'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+                'dtype', 'data', 'config', 'roofline', 'cpu_baseline', 'e2e', 'clocks', 'gpu_launches'):
+        assert key in line, key
+    assert line['metric'] == 'relabeled transitions/sec' and line['unit'] == 'transitions/s' and line['n_gpus'] == 1
+    assert line['steps'] == 20 and line['warmup'] == 3 and line['scaling'] == 'weak' and line['data'] == 'synthetic'
+    assert line['config']['key'] == 'c2' and 'workload' in line['config']
+    roof = line['roofline']
+    assert roof['bound'] == 'hbm' and roof['unit'] == 'GB/s' and 0.05 < roof['frac'] < 1.05
+    assert abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-6
+    assert line['gpu_launches'] >= 20                        # at least one kernel of ours per timed step
+    e2e = line['e2e']
+    assert e2e['unit'] == line['unit'] and 0 < e2e['value'] < line['value']       # host buffers: PCIe-bound, below the resident rate
+    assert e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0
+    cpu = line['cpu_baseline']
+    assert cpu['kind'] == 'port' and cpu['cores'] == 1 and cpu['value'] > 0 and cpu['sample']
+    assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
