@@ -154,8 +154,9 @@ int ogb_sampler_destroy(ogb_sampler* s);
 /* GCDataset.sample / HGCDataset.sample (datasets.py:213, :496).  n_batches >= 1 successive sample() calls are
  * produced by one launch and stacked on a leading axis (omitted when n_batches == 1).  `idxs` (host, may be
  * NULL) as in the reference: when given (batch_size * n_batches entries) no index draw is consumed.  `draws` NULL
- * selects the on-device Philox mode; otherwise validation mode (n_batches must be 1).  Asynchronous: returns
- * after enqueueing on the sampler's stream. */
+ * selects the on-device Philox mode; otherwise validation mode (n_batches must be 1).  batch_size == 0 is legal, as
+ * in the reference (every key with zero rows, nothing launched).  Asynchronous: returns after enqueueing on the
+ * sampler's stream. */
 int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, const int64_t* idxs,
                        int32_t evaluation, const ogb_draws* draws, ogb_batch** out);
 

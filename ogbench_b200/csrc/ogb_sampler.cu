@@ -1195,7 +1195,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
                const ogb_draws* draws, ogb_batch** out) {
   using namespace ogb;
   if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
-  if (batch_size < 1 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size and n_batches must be >= 1");
+  if (batch_size < 0 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size must be >= 0 and n_batches >= 1");
   if (draws && n_batches != 1) return fail(OGB_ERR_INVALID, "validation draws need n_batches == 1");
   const ogb_dataset* ds = s->ds;
   const ogb_config& cfg = s->cfg;
@@ -1342,6 +1342,13 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   b->vec_rows = (int32_t*)(base + off_rows);
   if (want_crop) b->crop = (int8_t*)(base + off_crop);
   if (want_init) b->vec_init = (int32_t*)(base + off_init);
+  if (total == 0) {   // an empty batch is legal (np.random.randint(n, size=0) in the reference): every key with zero rows, no launch
+    if (cudaEventCreateWithFlags(&b->ready, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b->ready, s->stream) != cudaSuccess)
+      return bail(fail(OGB_ERR_CUDA, "ready event failed"));
+    if (!draws) s->counter += (uint64_t)n_batches;
+    *out = b;
+    return 0;
+  }
 
   // ---- parameters of the fused index + row-gather kernel ----
   RelabelParams p;
@@ -1976,7 +1983,9 @@ int ogb_sampler_sample(ogb_sampler* s, int64_t batch_size, int32_t n_batches, co
 // get_observations / get_goal_observations (datasets.py:341-357): rows `idxs` of the observations (frame-stacked as
 // the sampler's config says) or of the goal representation.
 int ogb_sampler_gather(ogb_sampler* s, int32_t which, const int64_t* idxs, int64_t n, ogb_batch** out) try {
-  if (!s || !idxs || !out || n < 1) return fail(OGB_ERR_INVALID, "ogb_sampler_gather: bad argument");
+  if (!s || (!idxs && n > 0) || !out || n < 0) return fail(OGB_ERR_INVALID, "ogb_sampler_gather: bad argument");
+  static const int64_t no_rows = 0;
+  if (n == 0) idxs = &no_rows;   // an empty gather is legal (observations[np.zeros(0, int)]); run_sample wants a non-null pointer
   if (which < 0 || which > 1) return fail(OGB_ERR_INVALID, "which must be 0 (observations) or 1 (goal observations)");
   PlanBuilder pb;
   pb.ds = s->ds;

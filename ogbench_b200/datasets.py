@@ -677,6 +677,8 @@ class GCDataset:
                     keep.append(arr)
                     setattr(c_draws, name, arr.ctypes.data)
         out = np.empty(n, dtype=np.int64)
+        if n == 0:      # (the np.random calls above were still made, with size 0, like the reference's)
+            return out
         _native.check(_native.lib().ogb_sampler_sample_goals(
             self._sampler.ptr, idxs.ctypes.data_as(C.c_void_p), n, float(p_curgoal), float(p_trajgoal), int(bool(geom_sample)),
             float(discount), C.byref(c_draws) if c_draws is not None else None, out.ctypes.data_as(C.c_void_p)))
@@ -713,6 +715,8 @@ class HGCDataset(GCDataset):
         arrs = [np.ascontiguousarray(np.asarray(a), dtype=np.int64).reshape(-1) for a in (idxs, final_state_idxs, high_goal_idxs)]
         n = len(arrs[0])
         nxt, steps = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        if n == 0:
+            return nxt, steps
         _native.check(_native.lib().ogb_sampler_compute_high_next_idxs(
             self._sampler.ptr, *[a.ctypes.data_as(C.c_void_p) for a in arrs], n, int(subgoal_steps),
             nxt.ctypes.data_as(C.c_void_p), steps.ctypes.data_as(C.c_void_p)))

@@ -232,6 +232,30 @@ def test_cached_key_layout_across_calls(output):
         assert len(sampler._sampler._layouts) == 4      # (100), (37), (1), (100, evaluation)
 
 
+@pytest.mark.parametrize('output', ['device', 'numpy'])
+def test_empty_batch_like_the_reference(output):
+    """sample(0), sample(idxs=[]) and the helper methods on empty index arrays return every key with zero rows, with the
+    reference's shapes and dtypes (np.random.randint(n, size=0) there; checked against the unmodified reference when the
+    oracle was written -- the oracle reproduces it)."""
+    lengths = ragged(47, 8, 4, 9)
+    fields = toy_fields(47, lengths, (3,), 2, np.float32)
+    config = cfg(subgoal_steps=3)
+    for kind in ('gc', 'hgc'):
+        for rng in ('philox', 'numpy'):
+            sampler = device_sampler(fields, config, kind, rng=rng, output=output)
+            np.random.seed(3)
+            _, want = oracle_with_draws(fields, config, kind, 0)
+            for got in (sampler.sample(0), sampler.sample(5, idxs=np.zeros(0, dtype=np.int64))):
+                got = to_host(got)
+                assert set(got) == set(want)
+                for k in want:
+                    assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, (kind, rng, k)
+            assert np.asarray(sampler.get_observations(np.zeros(0, dtype=np.int64))).shape == (0, 3)
+            assert sampler.sample_goals(np.zeros(0, dtype=np.int64), 0.2, 0.5, 0.3, True).shape == (0,)
+            nonempty = to_host(sampler.sample(4))                   # and the sampler keeps working afterwards
+            assert nonempty['observations'].shape == (4, 3)
+
+
 def test_index_vectors_exposed():
     case = load_case('hgc_state_hiql')
     sampler = device_sampler(case['fields'], case['cfg'], 'hgc')
