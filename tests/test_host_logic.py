@@ -201,3 +201,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
     assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in line['config']
+
+
+def test_fuzz_generator_runs_on_the_oracle_alone():
+    """The random-case generator of the GPU fuzz test yields configurations the oracle accepts (no GPU needed here)."""
+    from tests.fuzz_util import run_case
+
+    master = np.random.default_rng(5)
+    kinds = set()
+    for _ in range(40):
+        case = run_case(np.random.default_rng(int(master.integers(0, 2**31))), oracle_only=True)
+        kinds.add((case['kind'], case['fields']['observations'].ndim > 2))
+    assert {k for k, _ in kinds} == {'gc', 'hgc'}
