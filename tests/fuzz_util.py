@@ -57,11 +57,56 @@ def random_case(r):
     return dict(kind=kind, fields=fields, config=cfg(**over), batch=batch, output=output, dedup=dedup, summary=summary)
 
 
+def run_atc_case(r, oracle_only=False):
+    """ATCDataset.sample(batch, k) in rng='numpy' mode against the oracle (datasets.py:369-464)."""
+    from oracle.replay_oracle import OracleATCSampler
+
+    pixel = r.random() < 0.6
+    lo = int(r.integers(3, 9))
+    lengths = r.integers(lo, lo + int(r.integers(1, 30)), size=int(r.integers(2, 14 if pixel else 80)))
+    if pixel:
+        obs_shape, obs_dtype = [(64, 64, 3), (32, 48, 3), (8, 8, 3), (20, 12, 4)][r.integers(0, 4)], np.uint8
+        fs = [None, 2, 3][r.integers(0, 3)]
+    else:
+        obs_shape, obs_dtype, fs = (int(r.integers(1, 60)),), np.float32, [None, None, 2][r.integers(0, 3)]
+    compact = bool(r.random() < 0.8) or fs is not None
+    fields = toy_fields(int(r.integers(0, 10**6)), lengths, obs_shape, int(r.integers(1, 6)), obs_dtype, compact=compact)
+    config = dict(frame_stack=fs, p_aug=[None, 0.0, 0.5, 1.0][r.integers(0, 4)])
+    if r.random() < 0.5:
+        config['augment_padding'] = int(r.integers(0, 6))
+    k = int(r.integers(1, lo - 1))                                  # every trajectory has anchors for this offset
+    B = int(r.integers(1, 40)) if pixel else int([1, 33, 500][r.integers(0, 3)])
+    output = ['device', 'numpy'][r.integers(0, 2)]
+    summary = f'kind=atc obs={obs_shape} fs={fs} compact={compact} B={B} k={k} output={output} cfg={config}'
+    oracle = OracleATCSampler(fields, config)
+    try:
+        sampler = None
+        if not oracle_only:
+            from tests.gpu_util import device_sampler, to_host
+
+            sampler = device_sampler(fields, config, 'atc', rng='numpy', output=output)
+            assert np.array_equal(sampler.get_valid_atc_idxs(k), oracle.valid_anchors(k)), 'anchor sets differ'
+        for it in range(3):
+            seed = int(r.integers(0, 2**31))
+            np.random.seed(seed)
+            want = oracle.sample(B, k, evaluation=(it == 1))
+            if sampler is None:
+                continue
+            np.random.seed(seed)
+            got = to_host(sampler.sample(B, k, evaluation=(it == 1)))
+            assert_batches_identical(got, want, label=f'atc, call {it}: ')
+    except AssertionError as exc:
+        raise AssertionError(f'{summary}\n   {exc}') from exc
+    return dict(kind='atc', fields=fields, config=config, batch=B, summary=summary)
+
+
 def run_case(r, oracle_only=False):
     """One random case; raises AssertionError (message prefixed by the case summary) on any mismatch."""
     from oracle import philox_np
     from oracle.replay_oracle import DrawsSource, OracleSampler
 
+    if r.random() < 0.12:
+        return run_atc_case(r, oracle_only)
     case = random_case(r)
     kind, fields, config, B = case['kind'], case['fields'], case['config'], case['batch']
     oracle = OracleSampler(fields, config, kind)
