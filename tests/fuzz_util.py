@@ -100,13 +100,56 @@ def run_atc_case(r, oracle_only=False):
     return dict(kind='atc', fields=fields, config=config, batch=B, summary=summary)
 
 
+def run_trl_case(r, oracle_only=False):
+    """TRL branch of GCDataset.sample (datasets.py:198-204, 254-276) in validation mode: the device consumes the draws
+    the oracle made from np.random, midpoint draw included."""
+    from oracle.replay_oracle import OracleSampler
+
+    pixel = r.random() < 0.2
+    lengths = r.integers(4, 4 + int(r.integers(1, 60)), size=int(r.integers(2, 10 if pixel else 60)))
+    if pixel:
+        obs_shape, obs_dtype, fs = [(64, 64, 3), (8, 8, 3)][r.integers(0, 2)], np.uint8, [None, 3][r.integers(0, 2)]
+    else:
+        obs_shape, obs_dtype, fs = (int(r.integers(1, 70)),), [np.float32, np.float64][r.integers(0, 2)], None
+    fields = toy_fields(int(r.integers(0, 10**6)), lengths, obs_shape, int(r.integers(1, 9)), obs_dtype,
+                        oracle_rep_dim=(int(r.integers(1, 6)) if r.random() < 0.3 else None))
+    am = goal_mix(r)
+    config = cfg(agent_name=['trl', 'latent_trl', 'discrete_latent_trl'][r.integers(0, 3)], value_p_curgoal=0.0, value_p_trajgoal=1.0,
+                 value_p_randomgoal=0.0, value_geom_sample=bool(r.integers(0, 2)), actor_p_curgoal=am[0], actor_p_trajgoal=am[1],
+                 actor_p_randomgoal=am[2], actor_geom_sample=bool(r.integers(0, 2)), discount=[0.99, 0.999][r.integers(0, 2)],
+                 gc_negative=bool(r.integers(0, 2)), frame_stack=fs, p_aug=[None, 0.0, 1.0][r.integers(0, 3)])
+    B = int(r.integers(1, 30)) if pixel else int([1, 33, 700][r.integers(0, 3)])
+    output = ['device', 'numpy'][r.integers(0, 2)]
+    summary = f'kind=trl obs={obs_shape} fs={fs} B={B} output={output} cfg={config}'
+    oracle = OracleSampler(fields, config, 'gc')
+    try:
+        sampler = None
+        if not oracle_only:
+            from tests.gpu_util import device_sampler, to_host
+
+            sampler = device_sampler(fields, config, 'gc', output=output)
+        for it in range(2):
+            np.random.seed(int(r.integers(0, 2**31)))
+            want = oracle.sample(B, evaluation=(it == 1))
+            if sampler is None:
+                continue
+            got = to_host(sampler.sample(B, evaluation=(it == 1), draws=oracle.last_draws))
+            assert_batches_identical(got, want, label=f'trl, call {it}: ')
+    except AssertionError as exc:
+        raise AssertionError(f'{summary}\n   {exc}') from exc
+    return dict(kind='trl', fields=fields, config=config, batch=B, summary=summary)
+
+
 def run_case(r, oracle_only=False):
     """One random case; raises AssertionError (message prefixed by the case summary) on any mismatch."""
     from oracle import philox_np
     from oracle.replay_oracle import DrawsSource, OracleSampler
 
-    if r.random() < 0.12:
+    which = r.random()
+    if which < 0.12:
         return run_atc_case(r, oracle_only)
+    if which < 0.22:
+        return run_trl_case(r, oracle_only)
     case = random_case(r)
     kind, fields, config, B = case['kind'], case['fields'], case['config'], case['batch']
     oracle = OracleSampler(fields, config, kind)

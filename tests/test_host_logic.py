@@ -212,4 +212,4 @@ def test_fuzz_generator_runs_on_the_oracle_alone():
     for _ in range(60):
         case = run_case(np.random.default_rng(int(master.integers(0, 2**31))), oracle_only=True)
         kinds.add((case['kind'], case['fields']['observations'].ndim > 2))
-    assert {k for k, _ in kinds} == {'gc', 'hgc', 'atc'}
+    assert {k for k, _ in kinds} == {'gc', 'hgc', 'atc', 'trl'}
