@@ -273,19 +273,43 @@ class ReplayBuffer(Dataset):
 
 
 class _PinnedPool:
-    """Reusable page-locked host blocks for output='numpy'."""
+    """Reusable page-locked host blocks for output='numpy'.
+
+    Block sizes are rounded up to one of eight steps per power of two (at most 12.5 % slack; a 545 MB batch pins 576 MB,
+    not 1 GiB), returned blocks are kept for the next call of the same size class, and the pool gives page-locked
+    memory back to the system once more than `max_idle_bytes` of it sits unused.
+    """
+
+    max_idle_bytes = 4 << 30
 
     def __init__(self):
         self.free: Dict[int, list] = {}
+        self.idle_bytes = 0
+
+    @staticmethod
+    def bucket_of(nbytes: int) -> int:
+        bits = (max(nbytes, 1) - 1).bit_length()
+        if bits <= 12:
+            return 4096
+        step = 1 << (bits - 4)
+        return -(-nbytes // step) * step
 
     def take(self, nbytes: int) -> '_PinnedBlock':
-        bucket = 1 << max(12, (nbytes - 1).bit_length())
+        bucket = self.bucket_of(nbytes)
         stack = self.free.setdefault(bucket, [])
         if stack:
+            self.idle_bytes -= bucket
             return _PinnedBlock(self, bucket, stack.pop())
         out = C.c_void_p()
         _native.check(_native.lib().ogb_host_alloc(bucket, C.byref(out)))
         return _PinnedBlock(self, bucket, out.value)
+
+    def give_back(self, bucket: int, ptr: int):
+        if self.idle_bytes + bucket > self.max_idle_bytes:
+            _native.lib().ogb_host_free(C.c_void_p(ptr))
+            return
+        self.free.setdefault(bucket, []).append(ptr)
+        self.idle_bytes += bucket
 
 
 class _PinnedBlock:
@@ -294,8 +318,8 @@ class _PinnedBlock:
 
     def __del__(self):
         try:
-            self.pool.free[self.bucket].append(self.ptr)
-        except Exception:
+            self.pool.give_back(self.bucket, self.ptr)
+        except Exception:  # interpreter shutdown
             pass
 
 

@@ -213,3 +213,13 @@ def test_fuzz_generator_runs_on_the_oracle_alone():
         case = run_case(np.random.default_rng(int(master.integers(0, 2**31))), oracle_only=True)
         kinds.add((case['kind'], case['fields']['observations'].ndim > 2))
     assert {k for k, _ in kinds} == {'gc', 'hgc', 'atc', 'trl'}
+
+
+def test_pinned_pool_size_classes():
+    """Host blocks of output='numpy' are rounded up by at most 12.5 % (eight size classes per power of two)."""
+    from ogbench_b200.datasets import _PinnedPool
+
+    for n in (1, 4096, 4097, 5000, 65536, 65537, 545_259_520, (1 << 30) + 1):
+        b = _PinnedPool.bucket_of(n)
+        assert b >= n and b >= 4096 and (b <= 4096 or b <= n * 1.125 + 1), (n, b)
+        assert _PinnedPool.bucket_of(b) == b               # a size class maps to itself: returned blocks are found again
