@@ -144,7 +144,7 @@ def run_reference_arm(args):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, device_index, period=0.02):
+    def __init__(self, device_index, period=0.002):
         super().__init__(daemon=True)
         self.period = period
         self.samples = []
