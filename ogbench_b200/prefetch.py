@@ -23,9 +23,20 @@ reference's call order, which that mode exists to reproduce.
 
 from __future__ import annotations
 
+import atexit
 import queue
 import threading
+import weakref
 from typing import Any, Dict, Optional
+
+_LIVE: 'weakref.WeakSet[Prefetcher]' = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    # a worker must not be inside the CUDA library while the interpreter (and the driver) shuts down
+    for p in list(_LIVE):
+        p.close()
 
 
 class Prefetcher:
@@ -45,6 +56,7 @@ class Prefetcher:
         self._closing = threading.Event()
         self._thread: Optional[threading.Thread] = threading.Thread(target=self._work, daemon=True)
         self.drawn = 0          # batches handed to the consumer
+        _LIVE.add(self)
         self._thread.start()
 
     def _work(self):
