@@ -10,8 +10,10 @@ thread while the current one is being sampled, so the swap every `dataset_replac
 
 from __future__ import annotations
 
+import atexit
 import glob
 import threading
+import weakref
 from typing import Any, Callable, List, Optional
 
 import numpy as np
@@ -150,6 +152,16 @@ def list_shards(dataset_dir: str) -> List[str]:
     return shards
 
 
+_LIVE_CYCLERS: 'weakref.WeakSet[ShardCycler]' = weakref.WeakSet()
+
+
+@atexit.register
+def _join_prefetch_threads():
+    # an upload must not be in flight inside the CUDA library while the interpreter shuts down
+    for c in list(_LIVE_CYCLERS):
+        c.close()
+
+
 class ShardCycler:
     """Cycle through dataset shards like impls/main.py:185-199, without the reload stall.
 
@@ -175,6 +187,7 @@ class ShardCycler:
         self._next_index: Optional[int] = None
         self._thread: Optional[threading.Thread] = None
         self._error: Optional[BaseException] = None
+        _LIVE_CYCLERS.add(self)
         self._start_prefetch()
 
     def _start_prefetch(self):
