@@ -204,13 +204,18 @@ class ReplayBuffer(Dataset):
     @classmethod
     def create_from_initial_dataset(cls, init_dataset, size, **kwargs):
         """Create a replay buffer from the initial dataset (datasets.py:108-125)."""
-        init = dict(init_dataset)
+        init = {k: np.asarray(v) for k, v in dict(init_dataset).items()}
         n = get_size(init)
-        fields = {k: _ZeroField((size, *np.asarray(v).shape[1:]), np.asarray(v).dtype) for k, v in init.items()}
-        rb = cls(fields, **kwargs)
-        rb._fill(init, n)
+
+        def create_buffer(init_buffer):
+            buffer = np.zeros((size, *init_buffer.shape[1:]), dtype=init_buffer.dtype)
+            buffer[:len(init_buffer)] = init_buffer
+            return buffer
+
+        rb = cls({k: create_buffer(v) for k, v in init.items()}, **kwargs)
         rb.size = rb.pointer = n
-        rb._sync_size()
+        rb.native(rb._device)            # one bulk upload per field (not a write per row); active rows = n
+        rb._dict = {k: _ZeroField(v.shape, v.dtype) for k, v in rb._dict.items()}   # the host copies are not kept
         return rb
 
     def __init__(self, fields, rng='philox', output='device', device=0):
@@ -246,10 +251,6 @@ class ReplayBuffer(Dataset):
             keep.append(arr)
             ptrs[i] = arr.ctypes.data
         _native.check(_native.lib().ogb_sampler_write_row(sampler.ptr, int(row), ptrs, len(self._names)))
-
-    def _fill(self, init, n):
-        for r in range(n):
-            self._write(r, {k: np.asarray(v)[r] for k, v in init.items()})
 
     def add_transition(self, transition):
         """Add a transition to the replay buffer (datasets.py:134-142)."""
