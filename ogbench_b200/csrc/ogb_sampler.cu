@@ -106,6 +106,25 @@ int fail_from_exception() {
                                          __FILE__, __LINE__);                                            \
   } while (0)
 
+// The calling thread's current device is the caller's business: entry points switch to the dataset's device for their
+// own calls and put the previous one back on the way out (a process that drives several GPUs from one thread --
+// or a garbage-collected batch of another device's sampler -- must not find its device changed underfoot).
+struct DeviceGuard {
+  int previous = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    status = cudaGetDevice(&previous);
+    if (status != cudaSuccess) { previous = -1; status = cudaSetDevice(device); return; }
+    if (previous == device) previous = -1;          // nothing to switch, nothing to restore
+    else status = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (previous >= 0) cudaSetDevice(previous);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define OGB_TRY(expr)        \
   do {                       \
     int rc_ = (expr);        \
@@ -462,7 +481,7 @@ void block_give(ogb_sampler* s, uint8_t* block, size_t bytes, std::vector<cudaEv
 
 void dataset_unref(ogb_dataset* ds) {
   if (ds->refs.fetch_sub(1) != 1) return;
-  cudaSetDevice(ds->device);
+  DeviceGuard device_guard(ds->device);
   for (auto& f : ds->fields) if (f.dptr && !f.in_record) cudaFree(f.dptr);
   if (ds->record_base) cudaFree(ds->record_base);
   if (ds->d_valid_table) cudaFree(ds->d_valid_table);
@@ -473,7 +492,7 @@ void dataset_unref(ogb_dataset* ds) {
 
 void sampler_unref(ogb_sampler* s) {
   if (s->refs.fetch_sub(1) != 1) return;
-  cudaSetDevice(s->ds->device);
+  DeviceGuard device_guard(s->ds->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
   if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
@@ -498,7 +517,7 @@ void sampler_unref(ogb_sampler* s) {
 void batch_unref(ogb_batch* b) {
   if (b->refs.fetch_sub(1) != 1) return;
   ogb_sampler* s = b->sampler;
-  cudaSetDevice(s->ds->device);
+  DeviceGuard device_guard(s->ds->device);
   // The block goes back to the sampler's cache together with the events after which it may be rewritten: the
   // batch's own `ready` event, plus one event per consumer stream that took the batch through the DLPack protocol.
   std::vector<cudaEvent_t> free_after;
@@ -789,7 +808,8 @@ int ogb_device_count(int* out) try {
 
 int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device, ogb_dataset** out) try {
   if (!fields || n_fields <= 0 || !out) return fail(OGB_ERR_INVALID, "ogb_dataset_create: bad arguments");
-  OGB_CUDA(cudaSetDevice(device));
+  DeviceGuard device_guard(device);
+  OGB_CUDA(device_guard.status);
   ogb_dataset* ds = new ogb_dataset();
   ds->device = device;
   cudaDeviceGetAttribute(&ds->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -1010,7 +1030,8 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
   if (!ds || !cfg || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_create: null argument");
   if (kind < OGB_KIND_GC || kind > OGB_KIND_ATC) return fail(OGB_ERR_INVALID, "unknown sampler kind %d", kind);
   if (stream_id >= (1u << 24)) return fail(OGB_ERR_INVALID, "stream_id must be < 2^24");
-  OGB_CUDA(cudaSetDevice(ds->device));
+  DeviceGuard device_guard(ds->device);
+  OGB_CUDA(device_guard.status);
   if (kind == OGB_KIND_ATC) {
     if (ds->terminals_field < 0) return fail(OGB_ERR_INVALID, "KeyError: 'terminals'");
     if (cfg->frame_stack > 0 && ds->next_obs_field >= 0)
@@ -1086,6 +1107,8 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
 
 int ogb_sampler_set_stream(ogb_sampler* s, void* cuda_stream) try {
   if (!s) return fail(OGB_ERR_INVALID, "null sampler");
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks may still be in flight on the old stream
   if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
@@ -1131,7 +1154,8 @@ int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_
   ogb_dataset* ds = s->ds;
   if (row < 0 || row >= ds->size) return fail(OGB_ERR_INDEX, "row %lld out of range", (long long)row);
   if (n_fields != (int32_t)ds->fields.size()) return fail(OGB_ERR_INVALID, "expected %zu field pointers", ds->fields.size());
-  OGB_CUDA(cudaSetDevice(ds->device));
+  DeviceGuard device_guard(ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   if (s->aux_stream) {  // index kernels of big launches read tiny fields on the auxiliary stream
     cudaEvent_t ev = s->chunk_events[s->next_event];
@@ -1240,7 +1264,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     if (aug_mode && !draws->has_aug_coin) return fail(OGB_ERR_INVALID, "validation mode: the augmentation coin is missing");
     if (aug_mode && draws->aug_coin < p_aug_eff && !draws->crop) return fail(OGB_ERR_INVALID, "validation mode: crop draws are missing");
   }
-  OGB_CUDA(cudaSetDevice(ds->device));
+  DeviceGuard device_guard(ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
 
   const std::vector<KeyPlan>& plan = *spec.plan;
@@ -2105,7 +2130,8 @@ int ogb_sampler_sample_goals(ogb_sampler* s, const int64_t* idxs, int64_t n, dou
     for (int64_t r = 0; r < n; ++r)
       if (draws->rand_pos[r] < 0 || draws->rand_pos[r] >= n_choices) return fail(OGB_ERR_INDEX, "rand_pos out of range");
   }
-  OGB_CUDA(cudaSetDevice(ds->device));
+  DeviceGuard device_guard(ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   GoalsParams q;
   memset(&q, 0, sizeof(q));
@@ -2173,7 +2199,8 @@ int ogb_sampler_compute_high_next_idxs(ogb_sampler* s, const int64_t* idxs, cons
                                        int64_t n, int64_t subgoal_steps, int64_t* out_next, int64_t* out_steps) try {
   if (!s || !idxs || !final_state_idxs || !goal_idxs || !out_next || !out_steps || n < 1)
     return fail(OGB_ERR_INVALID, "ogb_sampler_compute_high_next_idxs: bad argument");
-  OGB_CUDA(cudaSetDevice(s->ds->device));
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   DeviceScratch tmp;
   int64_t *d_i = nullptr, *d_f = nullptr, *d_g = nullptr, *d_n = nullptr, *d_s = nullptr;
@@ -2218,6 +2245,8 @@ int atc_anchors(ogb_sampler* s, int64_t k, const std::vector<int32_t>** host, co
 int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
   if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
+  DeviceGuard device_guard(s->ds->device);           // a new offset uploads its anchor table
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   const std::vector<int32_t>* host;
   OGB_TRY(atc_anchors(s, k, &host, nullptr));
@@ -2226,6 +2255,8 @@ int ogb_sampler_num_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) try {
 } OGB_CATCH_ALL
 int ogb_sampler_copy_atc_anchors(ogb_sampler* s, int64_t k, int64_t* out) try {
   if (!s || !out) return fail(OGB_ERR_INVALID, "null argument");
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
   const std::vector<int32_t>* host;
   OGB_TRY(atc_anchors(s, k, &host, nullptr));
@@ -2241,6 +2272,8 @@ int ogb_sampler_sample_atc(ogb_sampler* s, int64_t batch_size, int32_t n_batches
   if (k < 0) return fail(OGB_ERR_INVALID, "k must be >= 0");
   const std::vector<int32_t>* host;
   const int32_t* dev;
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
   {
     std::lock_guard<std::mutex> lock(s->mu);
     OGB_TRY(atc_anchors(s, k, &host, &dev));
@@ -2323,7 +2356,8 @@ int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) try {
   if (!b) return fail(OGB_ERR_INVALID, "null batch");
   cudaStream_t c = (cudaStream_t)consumer_stream;
   if (c == b->sampler->stream) { b->main_stream_consumer = true; return 0; }
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
   OGB_CUDA(cudaStreamWaitEvent(c, b->ready, 0));
   std::lock_guard<std::mutex> lock(b->mu);
   if (std::find(b->consumers.begin(), b->consumers.end(), c) == b->consumers.end()) b->consumers.push_back(c);
@@ -2333,7 +2367,8 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
   if (!b || !dst) return fail(OGB_ERR_INVALID, "null argument");
   if (nbytes < b->keys_bytes) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, b->keys_bytes);
   ogb_sampler* s = b->sampler;
-  OGB_CUDA(cudaSetDevice(s->ds->device));
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
   if (b->chunk_done.size() > 1) {
     // pipelined: chunk c's rows of every key travel as soon as chunk c's kernels are done, on a stream of their own,
     // while the kernels of chunk c+1 are still running
@@ -2363,7 +2398,8 @@ int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes
   if (!b || !dst || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad argument");
   const size_t need = (size_t)b->total_rows * b->keys[(size_t)i].row_bytes;
   if (nbytes < need) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, need);
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
   OGB_CUDA(cudaMemcpyAsync(dst, b->block + b->offsets[(size_t)i], need, cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   return 0;
@@ -2373,7 +2409,8 @@ int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) try {
   if (!b || !n_bad) return fail(OGB_ERR_INVALID, "null argument");
   if (!b->sampler->canary) return fail(OGB_ERR_INVALID, "the sampler was not put into canary mode before this batch was drawn");
   std::vector<uint8_t> host(b->keys_bytes);
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
   OGB_CUDA(cudaMemcpyAsync(host.data(), b->block, host.size(), cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   std::vector<uint8_t> owned(host.size(), 0);
@@ -2391,7 +2428,8 @@ int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host) try {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
   if (slot < 0 || slot >= b->n_slots) return fail(OGB_ERR_INVALID, "bad slot");
   std::vector<int32_t> tmp((size_t)b->total_rows);
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
   OGB_CUDA(cudaMemcpyAsync(tmp.data(), b->vec_rows + (size_t)slot * b->total_rows, tmp.size() * 4, cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   for (size_t i = 0; i < tmp.size(); ++i) dst_host[i] = tmp[i];
@@ -2401,7 +2439,8 @@ int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host) try {
   if (!b || !dst_host) return fail(OGB_ERR_INVALID, "null argument");
   if (!b->crop) return fail(OGB_ERR_INVALID, "this batch has no image keys, hence no crop shifts");
   std::vector<int8_t> tmp((size_t)b->total_rows * 2);
-  OGB_CUDA(cudaSetDevice(b->sampler->ds->device));
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
   OGB_CUDA(cudaMemcpyAsync(tmp.data(), b->crop, tmp.size(), cudaMemcpyDeviceToHost, b->sampler->stream));
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   const int pad = b->sampler->cfg.crop_padding;
@@ -2475,7 +2514,8 @@ int ogb_host_free(void* p) try {
 int ogb_searchsorted_warp(const int64_t* sorted_host, int64_t n, const int64_t* keys_host, int64_t m, int32_t side_right,
                           int32_t device, int64_t* out_host) try {
   if (!sorted_host || !keys_host || !out_host || n < 0 || m < 0) return fail(OGB_ERR_INVALID, "bad arguments");
-  OGB_CUDA(cudaSetDevice(device));
+  DeviceGuard device_guard(device);
+  OGB_CUDA(device_guard.status);
   int64_t *d_t = nullptr, *d_k = nullptr, *d_o = nullptr;
   OGB_CUDA(cudaMalloc((void**)&d_t, std::max<int64_t>(n, 1) * 8));
   OGB_CUDA(cudaMalloc((void**)&d_k, std::max<int64_t>(m, 1) * 8));
@@ -2506,7 +2546,8 @@ int ogb_debug_timeline(double* out_ms, int32_t capacity, int32_t* n_out) try {
 
 int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t device, int64_t* mismatches) try {
   if (!mismatches || n < 0 || !(discount > 0.0 && discount < 1.0)) return fail(OGB_ERR_INVALID, "bad arguments");
-  OGB_CUDA(cudaSetDevice(device));
+  DeviceGuard device_guard(device);
+  OGB_CUDA(device_guard.status);
   unsigned long long* d = nullptr;
   OGB_CUDA(cudaMalloc((void**)&d, 8));
   OGB_CUDA(cudaMemset(d, 0, 8));
@@ -2523,7 +2564,8 @@ int ogb_geometric_check(double discount, uint64_t seed, int64_t n, int32_t devic
 
 int ogb_philox_fill(uint64_t seed, uint32_t stream_id, uint64_t batch, uint32_t purpose, int64_t n, int32_t device, uint32_t* out_host) try {
   if (!out_host || n < 0) return fail(OGB_ERR_INVALID, "bad arguments");
-  OGB_CUDA(cudaSetDevice(device));
+  DeviceGuard device_guard(device);
+  OGB_CUDA(device_guard.status);
   uint4* d = nullptr;
   OGB_CUDA(cudaMalloc((void**)&d, std::max<int64_t>(n, 1) * 16));
   const ogb::RngKey key = ogb::make_rng_key(seed, stream_id);

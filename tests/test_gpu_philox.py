@@ -422,3 +422,31 @@ def test_prefetcher_returns_the_direct_call_sequence(output):
             assert set(want) == set(got)
             for k in want:
                 assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), (step, k)
+
+
+def test_current_device_is_left_alone():
+    """The library switches to the dataset's device inside its entry points and restores the caller's current device
+    (needs two GPUs: the sampler lives on cuda:0 while the calling thread's current device is cuda:1)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    fields = toy_fields(3, ragged(3, 40, 5, 60), (9,), 3, np.float32)
+    config = cfg()
+    torch.cuda.set_device(1)
+    here = device_sampler(fields, config, 'gc', seed=11, device=0)
+    assert torch.cuda.current_device() == 1
+    got = to_host(here.sample(256))
+    assert torch.cuda.current_device() == 1
+    torch.cuda.set_device(0)
+    there = device_sampler(fields, config, 'gc', seed=11, device=0)
+    want = to_host(there.sample(256))
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
+    del here, there, got, want
+    import gc
+
+    torch.cuda.set_device(1)
+    gc.collect()                                      # batches and samplers of cuda:0 are released from a cuda:1 thread
+    assert torch.cuda.current_device() == 1
+    torch.cuda.set_device(0)
