@@ -6,7 +6,8 @@
  * point cites the reference interface it stands in for.  Plain pointers and sizes only, no torch types.
  * All functions return 0 on success and a negative ogb_status on failure; ogb_last_error() gives the message
  * (thread-local).  No C++ exception crosses this boundary: an internal one (e.g. host memory exhausted) comes back
- * as a status code.  There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * as a status code.  Entry points switch to the dataset's CUDA device for their own work and restore the calling
+ * thread's current device before returning.  There is no CPU fallback: without a CUDA device every compute entry point fails with
  * OGB_ERR_CUDA.
  */
 #ifndef OGB_SAMPLER_H_
