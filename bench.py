@@ -6,10 +6,17 @@
     python bench.py --impl reference ...      # the CPU implementation of the same path on the host cores
 
 A "step" is one launch of the hot path producing `batches_per_launch` successive GCDataset.sample(batch) calls
-(config.batches_per_launch; 1 reproduces the reference's one-call-per-step usage and is launch-latency bound).
+(config.batches_per_launch; 1 reproduces the reference's one-call-per-step usage and is launch-latency bound), made
+through the public call `GCDataset.sample_many(L, B)`.  K steps are a few milliseconds of device time, so the K-step
+loop is repeated R times back to back inside one timed region of >= 250 ms (`repeats`, `timed_region_ms`);
+`ms_per_step` is the region divided by K * R.
+
+The headline (top-level keys) is C2 = BASELINE.json configs[1]; the same line carries every config of BASELINE.json
+under `configs` (c1..c5, each with value / roofline / e2e / cpu_baseline), C5 as one trajectory-aligned shard per GPU.
 `value` = transitions all ranks produced / max-over-ranks device time with the dataset resident in HBM;
 `e2e` = the same through the public Python API with host buffers (transition indices uploaded from pinned host
-memory every step, the whole batch copied back into pinned host memory, both inside the timed region);
+memory every step, the whole batch copied back into pinned host memory, both inside the timed region), next to the
+raw pinned D2H copy rate of the same box measured in the same run (`link_gbs`);
 `roofline` = algorithmic bytes / average launch duration of the dominant kernel vs the measured
 HBM copy bandwidth; `cpu_baseline` = the numpy oracle port timed on this box's host cores in the same run.
 """
@@ -32,20 +39,25 @@ import numpy as np  # noqa: E402
 METRIC = 'relabeled transitions/sec'
 UNIT = 'transitions/s'
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+HEADLINE = 'c2'
+ALL_CONFIGS = ['c1', 'c2', 'c3', 'c4', 'c5']
+MIN_REGION_MS = 250.0
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--config', default='c2', help='workload key (c1..c5, c3b/c4b/c5b), SURVEY.md 8(d); c2 is the headline config')
+    ap.add_argument('--config', default=None,
+                    help='one workload key (c1..c5, c3b/c4b/c5b), SURVEY.md 8(d); default: the c2 headline plus c1..c5 under "configs"')
     ap.add_argument('--batches-per-launch', type=int, default=None)
     ap.add_argument('--e2e-batches', type=int, default=None, help='batches per e2e step')
-    ap.add_argument('--cpu-seconds', type=float, default=10.0, help='budget of the cpu_baseline leg')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0, help='budget of the headline cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--min-region-ms', type=float, default=MIN_REGION_MS)
     return ap.parse_args()
 
 
@@ -57,6 +69,27 @@ def hbm_peak():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+
+
+def default_batches_per_launch(w):
+    # ~1M transitions per launch for vector workloads, 16 batches for the pixel workload: ~1.1 GB of output per launch
+    # in both cases (>> 126 MB L2)
+    return 16 if w.obs_dtype == 'uint8' else max(1, (1 << 20) // w.batch)
+
+
+def config_dict(key, L):
+    """The workload description both arms print (a pure function of the workload key and batches_per_launch)."""
+    from ogbench_b200 import synthetic
+
+    w = synthetic.WORKLOADS[key]
+    return {
+        'workload': w.name, 'key': w.key, 'rows_resident_per_gpu': w.rows, 'batch': w.batch, 'batches_per_launch': L,
+        'transitions_per_step_per_gpu': w.batch * L,
+        'placement': 'trajectory-aligned shard per GPU' if key.startswith('c5') else 'replica per GPU',
+        'l2': 'no explicit flush: outputs rotate through three blocks of one launch each (together larger than the 126 MB L2 for '
+              'every config, each block larger than L2 except c1), inputs are random rows of the resident dataset (per-config sizes '
+              'in notes; c1 and c2 are at or below L2 size, as the real datasets of these shapes are)',
+    }
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -72,7 +105,8 @@ def _cpu_fields(w):
 
 
 def _cpu_worker(args):
-    key, seconds, seed = args
+    """One host process: W warm-up steps, then K timed steps of `calls` sample(batch) calls each."""
+    key, steps, warmup, budget_s, seed = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     from ogbench_b200 import synthetic
     from oracle.replay_oracle import OracleSampler
@@ -81,56 +115,66 @@ def _cpu_worker(args):
     fields, _ = _cpu_fields(w)
     sampler = OracleSampler(fields, w.config, w.kind)
     np.random.seed(seed)
-    for _ in range(3):
+    for _ in range(2):
         sampler.sample(w.batch)
-    n, t0 = 0, time.perf_counter()
-    while True:
+    t0 = time.perf_counter()
+    n_cal = 0
+    while time.perf_counter() - t0 < 0.2 or n_cal < 2:     # calibrate: calls per step so that the run fits the budget
         sampler.sample(w.batch)
-        n += 1
-        dt = time.perf_counter() - t0
-        if dt >= seconds:
-            return n, dt
+        n_cal += 1
+    t_call = (time.perf_counter() - t0) / n_cal
+    calls = max(1, int(budget_s / ((steps + warmup) * t_call)))
+    for _ in range(warmup * calls):
+        sampler.sample(w.batch)
+    t0 = time.perf_counter()
+    for _ in range(steps * calls):
+        sampler.sample(w.batch)
+    return steps * calls, time.perf_counter() - t0, calls
 
 
-def cpu_baseline(key, seconds, workers):
+def cpu_baseline(key, workers, steps, warmup, budget_s):
     """transitions/s of the oracle port with `workers` independent processes (1 = the reference's own threading)."""
     from ogbench_b200 import synthetic
 
     w = synthetic.WORKLOADS[key]
+    jobs = [(key, steps, warmup, budget_s, i) for i in range(workers)]
     if workers == 1:
-        results = [_cpu_worker((key, seconds, 0))]
+        results = [_cpu_worker(jobs[0])]
     else:
         import multiprocessing as mp
 
         with mp.get_context('spawn').Pool(workers) as pool:
-            results = pool.map(_cpu_worker, [(key, seconds, i) for i in range(workers)])
-    rate = sum(n * w.batch / dt for n, dt in results)
-    calls = sum(n for n, _ in results)
+            results = pool.map(_cpu_worker, jobs)
+    rate = sum(n * w.batch / dt for n, dt, _ in results)
+    calls = sum(n for n, _, _ in results)
     _, episodes = _cpu_fields(w)
-    sample = (f'{calls} calls of sample({w.batch}) over {max(dt for _, dt in results):.1f} s on {workers} process(es), '
-              f'numpy {np.__version__}, dataset {episodes}x{w.steps} rows')
-    return rate, sample
+    slowest = max(dt for _, dt, _ in results)
+    sample = (f'{steps} steps of {results[0][2]} sample({w.batch}) calls per process = {calls} calls over {slowest:.1f} s on '
+              f'{workers} process(es), numpy {np.__version__}, dataset {episodes}x{w.steps} rows')
+    return rate, sample, 1e3 * slowest / steps
 
 
 def run_reference_arm(args):
-    from ogbench_b200 import synthetic
-
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    w = synthetic.WORKLOADS[args.config]
+    from ogbench_b200 import synthetic
+
+    key = args.config or HEADLINE
+    w = synthetic.WORKLOADS[key]
+    L = args.batches_per_launch or default_batches_per_launch(w)
     workers = os.cpu_count() or 1
-    # steps*warmup are honoured as a time budget: each "step" is a bounded slice of the same workload
-    seconds = min(60.0, max(5.0, 0.05 * (args.steps + args.warmup)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     t0 = time.perf_counter()
-    rate, sample = cpu_baseline(args.config, seconds, workers)
+    rate, sample, ms_per_step = cpu_baseline(key, workers, steps, warmup, budget_s=30.0)
     wall = time.perf_counter() - t0
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * w.batch * workers / rate, 'higher_is_better': True, 'scaling': 'weak',
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'u8' if w.obs_dtype == 'uint8' else 'f32', 'data': 'synthetic',
-        'config': {'workload': w.name, 'batch': w.batch, 'rows': w.rows, 'note': 'reference numpy algorithm (oracle port; the '
-                   'reference itself is Python and is not installed on the GPU box), one process per host core'},
+        'config': config_dict(key, L),
+        'notes': 'reference numpy algorithm (oracle port; the reference itself is Python+JAX and is not installed on the GPU '
+                 'box), one process per host core, each step a bounded number of sample(batch) calls per process',
         'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': workers, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': wall,
@@ -202,46 +246,62 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
-L2_BYTES = 126e6
+def committed_traffic(key, kernel_name, kernel_ms, per_step):
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json),
+    scaled to this run's launch size.  Refused (None + reason) when the capture is of another kernel or when the kernel it
+    recorded ran more than 10 % slower or faster than this run's -- ncu serialises launches on a cold cache, which moves a
+    launch by a few percent; a bigger gap means the kernel has changed since the capture."""
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(tpath):
+        return None, 'profiles/traffic.json is absent'
+    try:
+        entry = json.load(open(tpath)).get(key)
+        if not entry:
+            return None, f'no capture for {key}'
+        if entry.get('kernel', '').find(kernel_name) < 0:
+            return None, f"capture is of {entry.get('kernel')!r}, the run's dominant kernel is {kernel_name!r}"
+        scale = per_step / float(entry.get('transitions_per_launch', per_step))
+        ncu_ms = float(entry['duration_us_under_ncu']) * 1e-3 * scale
+        if abs(ncu_ms - kernel_ms) > 0.10 * kernel_ms:
+            return None, f'stale capture: {ncu_ms:.4f} ms under ncu vs {kernel_ms:.4f} ms in this run'
+        return float(entry['dram_bytes_per_launch']) * scale, f"{entry.get('source', 'ncu capture')}, {ncu_ms:.4f} ms under ncu"
+    except Exception as exc:  # a malformed file must not take the bench down
+        return None, f'unreadable: {exc}'
 
 
-def l2_note(out_bytes, resident_bytes):
-    """How the timed loop relates to the 126 MB L2: outputs rotate through three blocks, inputs are random rows of the
-    resident dataset."""
-    out = (f'each step writes {out_bytes / 1e6:.0f} MB into one of three rotating output blocks '
-           f'({"each larger than" if out_bytes > L2_BYTES else "together " + ("larger" if 3 * out_bytes > L2_BYTES else "smaller") + " than"} the 126 MB L2)')
-    src = (f'and gathers random rows of a {resident_bytes / 1e6:.0f} MB resident dataset '
-           f'({"larger than L2" if resident_bytes > L2_BYTES else "smaller than L2: it stays cache-resident, as the real dataset of this shape would"})')
-    return out + ' ' + src
+def link_probe(torch, device, nbytes, reps=8):
+    """Raw pinned device->host copy rate of this rank's GPU for a block of the e2e step's size (GB/s)."""
+    src = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    return reps * nbytes / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
 
 
-def default_batches_per_launch(w):
-    # ~1M transitions per launch for vector workloads, 16 batches for the pixel workload: ~1.1 GB of output per launch
-    # in both cases (>> 126 MB L2)
-    return 16 if w.obs_dtype == 'uint8' else max(1, (1 << 20) // w.batch)
-
-
-def run_gpu_arm(args):
+def measure_config(key, args, ctx, headline):
+    """All measurements of one workload on this rank; collective calls inside (every rank runs the same sequence)."""
     import ctypes as C
 
-    import torch
-    import torch.distributed as dist
+    torch, dist_util, lib, _native = ctx['torch'], ctx['dist_util'], ctx['lib'], ctx['_native']
+    from ogbench_b200 import Dataset, GCDataset, HGCDataset, synthetic
 
-    from ogbench_b200 import Dataset, GCDataset, HGCDataset, _native, dist_util, synthetic
-
-    rank, world, local = dist_util.env_rank()
-    if world > 1:   # NCCL prints its version / debug lines to stdout: keep stdout for the one JSON line
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'        # (an explicit INFO/TRACE request from the caller is left alone)
-    torch.cuda.set_device(local)
-    numa = dist_util.bind_to_gpu_numa(local) if world > 1 and not os.environ.get('OGB_NO_NUMA_BIND') else None
-    dist_util.init('nccl', device=torch.device('cuda', local))
-    w = synthetic.WORKLOADS[args.config]
+    rank, world, local = ctx['rank'], ctx['world'], ctx['local']
+    dev = f'cuda:{local}'
+    w = synthetic.WORKLOADS[key]
     L = args.batches_per_launch or default_batches_per_launch(w)
 
     # each rank holds a replica (c1-c4) or its own trajectory-aligned shard (c5), generated directly in HBM
-    fields = synthetic.device_fields(w, device=local, seed=w.seed + (rank if args.config.startswith('c5') else 0))
+    # OGB_BENCH_EPISODES=n (measurement switch, reported in `notes`): a dataset of n episodes of the same row shape, e.g. one
+    # that fits L2, to tell what the DRAM side of the gathers costs
+    episodes = int(os.environ.get('OGB_BENCH_EPISODES', '0')) or w.episodes
+    fields = synthetic.device_fields(w, device=local, episodes=episodes, seed=w.seed + (rank if key.startswith('c5') else 0))
     dataset = Dataset.create(**fields)
     cls = GCDataset if w.kind == 'gc' else HGCDataset
     sampler = cls(dataset, w.config, device=local, seed=1234, stream_id=rank)
@@ -249,7 +309,6 @@ def run_gpu_arm(args):
     torch.cuda.empty_cache()
     stream = torch.cuda.Stream(device=local)
     sampler._sampler.set_stream(stream.cuda_stream)
-    lib = _native.lib()
     _native.check(lib.ogb_sampler_set_profile(sampler._sampler.ptr, 1))   # CUDA events around the dominant kernel of each launch
 
     def barrier():
@@ -257,12 +316,12 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(local)
 
     def launch():
-        handle = sampler._sampler.sample_native(w.batch, n_batches=L)
+        batch = sampler.sample_many(L, w.batch)                  # the public call: dict of DeviceArray, [L, B, ...] per key
+        handle = next(iter(batch.values()))._batch
         n = C.c_int32()
         lib.ogb_batch_launches(handle.ptr, C.byref(n))
         return handle, n.value
 
-    # ---- device-resident throughput ----
     launches = 0
     dominant_ms = []
     dominant_name = C.c_char_p()
@@ -287,29 +346,39 @@ def run_gpu_arm(args):
                 harvest(pending.pop(0), keep)
         return pending
 
-    tail = run(max(args.warmup, 3) + 2, False)   # same hand-over pattern as the timed loop: every recycled block exists
+    def timed(n_steps, keep):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            tail = run(n_steps, keep)
+            ev1.record(stream)
+        barrier()
+        for h in tail:
+            harvest(h, keep)
+        del tail
+        return ev0.elapsed_time(ev1)
+
+    warmup = max(args.warmup, 3)
+    tail = run(warmup + 2, False)   # same hand-over pattern as the timed loop: every recycled block exists
     del tail
+    barrier()
+    # how many times the K-step loop must repeat for a region of >= min_region_ms (same R on every rank)
+    probe_ms = dist_util.reduce_scalar(timed(args.steps, False), 'max', device=dev)
+    repeats = max(1, int(np.ceil(args.min_region_ms / max(probe_ms, 1e-3))))
+    n_steps = args.steps * repeats
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        tail = run(args.steps, True)
-        ev1.record(stream)
-    barrier()
+    elapsed_ms = timed(n_steps, True)
     clocks.stop_flag.set()
     clocks.join()
-    for h in tail:
-        harvest(h, True)
-    del tail
-    elapsed_ms = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean(dominant_ms)) if dominant_ms else elapsed_ms / args.steps
+    kernel_ms = float(np.mean(dominant_ms)) if dominant_ms else elapsed_ms / n_steps
     kernel_name = (dominant_name.value or b'').decode()
-    elapsed_ms = dist_util.reduce_scalar(elapsed_ms, 'max', device=f'cuda:{local}')   # slowest rank
+    elapsed_ms = dist_util.reduce_scalar(elapsed_ms, 'max', device=dev)   # slowest rank
     per_step = w.batch * L
-    value = dist_util.reduce_scalar(args.steps * per_step, 'sum', device=f'cuda:{local}') / (elapsed_ms * 1e-3)
+    value = dist_util.reduce_scalar(n_steps * per_step, 'sum', device=dev) / (elapsed_ms * 1e-3)
+    resident = dataset.native(local).resident_bytes()
 
     # ---- end to end through the public API with host buffers ----
     e2e = None
@@ -317,7 +386,7 @@ def run_gpu_arm(args):
         Le = args.e2e_batches or max(1, min(L, (64 << 20) // (w.bytes_per_transition * w.batch // 2 + 1)))
         host_sampler = cls(dataset, w.config, device=local, seed=4321, stream_id=rank, output='numpy')
         rows = Le * w.batch
-        n_valid = w.episodes * (w.steps - 1)
+        n_valid = episodes * (w.steps - 1)
         pinned = C.c_void_p()
         _native.check(lib.ogb_host_alloc(rows * 8 * 4, C.byref(pinned)))
         pool = np.frombuffer((C.c_ubyte * (rows * 8 * 4)).from_address(pinned.value), dtype=np.int64).reshape(4, rows)
@@ -325,10 +394,9 @@ def run_gpu_arm(args):
         pos = rng.integers(0, n_valid, size=(4, rows))
         pool[:] = pos + pos // (w.steps - 1)  # valid_idxs[j] = j + j // (T-1) for fixed-length compact trajectories
         steps_e = max(3, min(args.steps, 50))
-        d2h = 0
         for i in range(3):
             out = host_sampler.sample_many(Le, w.batch, idxs=pool[i % 4])
-        d2h = sum(v.nbytes for k, v in out.items() if True)
+        d2h = sum(v.nbytes for v in out.values())
         del out
         barrier()
         t0 = time.perf_counter()
@@ -337,55 +405,102 @@ def run_gpu_arm(args):
             del out
         torch.cuda.synchronize(local)
         dt = time.perf_counter() - t0
-        dt = dist_util.reduce_scalar(dt, 'max', device=f'cuda:{local}')
-        e2e = {'value': world * steps_e * rows / dt, 'unit': UNIT, 'numa_bound': numa is not None, 'h2d_bytes_per_step': rows * 8, 'd2h_bytes_per_step': int(d2h),
-               'steps': steps_e, 'batches_per_step': Le, 'api': "GCDataset(..., output='numpy').sample_many(L, B, idxs=host)"}
+        dt = dist_util.reduce_scalar(dt, 'max', device=dev)
+        barrier()
+        link = link_probe(torch, torch.device('cuda', local), int(d2h))      # every rank copies at the same time, like the e2e leg
+        link_min = -dist_util.reduce_scalar(-link, 'max', device=dev)
+        link_sum = dist_util.reduce_scalar(link, 'sum', device=dev)
+        e2e_value = world * steps_e * rows / dt
+        e2e = {'value': e2e_value, 'unit': UNIT, 'numa_bound': ctx['numa'] is not None, 'h2d_bytes_per_step': rows * 8,
+               'd2h_bytes_per_step': int(d2h), 'steps': steps_e, 'batches_per_step': Le,
+               'link_gbs': link_sum, 'link_gbs_slowest_rank': link_min,
+               'frac_of_link': e2e_value * (d2h / rows) / 1e9 / link_sum,
+               'link_note': 'raw pinned cudaMemcpyAsync D2H of one e2e block per rank, all ranks copying at once, summed over ranks',
+               'api': "GCDataset(..., output='numpy').sample_many(L, B, idxs=host)"}
         lib.ogb_host_free(pinned)
+        del host_sampler
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    del sampler, dataset
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
 
     peak, peak_src = hbm_peak()
     achieved = w.bytes_per_transition * per_step / (kernel_ms * 1e-3) / 1e9
-    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json),
-    # scaled to this run's launch size when the capture used another batches_per_launch
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        try:
-            entry = json.load(open(tpath)).get(args.config)
-            if entry and entry.get('kernel', '').find(kernel_name) >= 0:
-                traffic = float(entry['dram_bytes_per_launch']) * per_step / float(entry.get('transitions_per_launch', per_step))
-        except Exception:
-            traffic = None
-    line = {
-        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u8' if w.obs_dtype == 'uint8' else 'f32', 'data': 'synthetic',
-        'config': {
-            'workload': w.name, 'key': w.key, 'rows_resident_per_gpu': w.rows, 'batch': w.batch, 'batches_per_launch': L,
-            'transitions_per_step_per_gpu': per_step, 'rng': 'on-device Philox4x32-10',
-            'placement': 'trajectory-aligned shard per GPU' if args.config.startswith('c5') else 'replica per GPU',
-            'l2': l2_note(w.bytes_per_transition * per_step // 2, dataset.native(local).resident_bytes()),
-        },
+    traffic, traffic_note = committed_traffic(key, kernel_name, kernel_ms, per_step)
+    out_bytes = w.bytes_per_transition * per_step // 2
+    result = {
+        'value': value, 'ms_per_step': elapsed_ms / n_steps, 'batches_per_launch': L, 'repeats': repeats,
+        'timed_region_ms': elapsed_ms, 'steps_timed': n_steps,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'kernel': kernel_name, 'kernel_ms': kernel_ms, 'bytes_per_transition': w.bytes_per_transition,
-                     'bytes_per_launch': w.bytes_per_transition * per_step, 'peak_source': peak_src,
-                     'step_frac': w.bytes_per_transition * per_step / (elapsed_ms / args.steps * 1e-3) / 1e9 / peak,
+                     'traffic_source': traffic_note, 'kernel': kernel_name, 'kernel_ms': kernel_ms,
+                     'bytes_per_transition': w.bytes_per_transition, 'bytes_per_launch': w.bytes_per_transition * per_step,
+                     'peak_source': peak_src,
+                     'step_frac': w.bytes_per_transition * per_step / (elapsed_ms / n_steps * 1e-3) / 1e9 / peak,
                      'note': 'achieved = algorithmic bytes of one launch / device time of the dominant kernel (CUDA events on its '
                              'stream); step_frac = the same bytes / whole step time (index kernel and launch gaps included)'},
         'clocks': clocks.summary(),
         'gpu_launches': launches,
+        'notes': f'each step writes {out_bytes / 1e6:.0f} MB into one of three rotating output blocks and gathers random rows of a '
+                 f'{resident / 1e6:.0f} MB resident dataset (L2 is 126 MB)'
+                 + (f'; OGB_BENCH_EPISODES={episodes}: NOT the BASELINE shape' if episodes != w.episodes else ''),
     }
     if e2e is not None:
-        line['e2e'] = e2e
-    if world == 1 and not args.no_cpu_baseline:
-        rate, sample = cpu_baseline(args.config, args.cpu_seconds, 1)
-        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample,
-                                'host_cores_available': os.cpu_count()}
-    print(json.dumps(line), flush=True)
+        result['e2e'] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        budget = args.cpu_seconds if headline else min(args.cpu_seconds, 4.0)
+        rate, sample, _ = cpu_baseline(key, 1, 4, 1, budget_s=budget)
+        result['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample,
+                                  'host_cores_available': os.cpu_count()}
+    return result
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from ogbench_b200 import _native, dist_util, synthetic
+
+    rank, world, local = dist_util.env_rank()
+    if world > 1:   # NCCL prints its version / debug lines to stdout: keep stdout for the one JSON line
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'        # (an explicit INFO/TRACE request from the caller is left alone)
+    torch.cuda.set_device(local)
+    numa = dist_util.bind_to_gpu_numa(local) if world > 1 and not os.environ.get('OGB_NO_NUMA_BIND') else None
+    dist_util.init('nccl', device=torch.device('cuda', local))
+    ctx = {'torch': torch, 'dist_util': dist_util, 'lib': _native.lib(), '_native': _native, 'rank': rank, 'world': world,
+           'local': local, 'numa': numa}
+
+    head_key = args.config or HEADLINE
+    head = measure_config(head_key, args, ctx, headline=True)
+    others = {}
+    if args.config is None:
+        for key in ALL_CONFIGS:
+            others[key] = head if key == head_key else measure_config(key, args, ctx, headline=False)
+
+    if rank == 0:
+        w = synthetic.WORKLOADS[head_key]
+        line = {
+            'metric': METRIC, 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u8' if w.obs_dtype == 'uint8' else 'f32', 'data': 'synthetic',
+            'config': config_dict(head_key, head['batches_per_launch']),
+            'repeats': head['repeats'], 'timed_region_ms': head['timed_region_ms'], 'steps_timed': head['steps_timed'],
+            'rng': 'on-device Philox4x32-10', 'api': 'GCDataset.sample_many(batches_per_launch, batch) -> dict of device arrays',
+            'notes': head['notes'],
+            'roofline': head['roofline'], 'clocks': head['clocks'], 'gpu_launches': head['gpu_launches'],
+        }
+        for k in ('e2e', 'cpu_baseline'):
+            if k in head:
+                line[k] = head[k]
+        if others:
+            line['configs'] = {k: dict(v, workload=synthetic.WORKLOADS[k].name, batch=synthetic.WORKLOADS[k].batch,
+                                       dtype='u8' if synthetic.WORKLOADS[k].obs_dtype == 'uint8' else 'f32',
+                                       placement=config_dict(k, v['batches_per_launch'])['placement'])
+                               for k, v in others.items()}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

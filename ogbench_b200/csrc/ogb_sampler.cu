@@ -46,6 +46,8 @@ struct AbSwitches {
   int stage_bytes;       // OGB_STAGE_BYTES=n   per-warp stage budget instead of 4096 / 6144
   int ws;                // OGB_WS=0|1          warp-specialised fused kernel off / on (-1: ogb_sampler_set_debug decides)
   bool timeline;         // OGB_TIMELINE        record an event per phase for ogb_debug_timeline
+  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (308 built in; 216, 316, 220: one CTA per SM)
+  bool no_shadow;        // OGB_NO_SHADOW       no shadow copy of the next row's observation inside the records
 };
 
 const AbSwitches& ab() {
@@ -68,6 +70,8 @@ const AbSwitches& ab() {
     a.stage_bytes = number("OGB_STAGE_BYTES", 0);
     a.ws = number("OGB_WS", -1);
     a.timeline = flag("OGB_TIMELINE");
+    a.gather_shape = number("OGB_GATHER_SHAPE", 0);
+    a.no_shadow = flag("OGB_NO_SHADOW");
     return a;
   }();
   return sw;
@@ -208,6 +212,17 @@ int upload_vector(const std::vector<T>& host, T** dptr, cudaStream_t stream = 0)
   return 0;
 }
 
+// shadow[r] = observations[min(r + 1, n_rows - 1)] inside the record table (datasets.py:82), rows [row_begin, row_end)
+__global__ void shadow_next_kernel(uint8_t* record_base, size_t stride, uint32_t obs_off, uint32_t shadow_off, uint32_t row_bytes,
+                                   int64_t n_rows, int64_t row_begin, int64_t row_end) {
+  const int64_t n = (row_end - row_begin) * row_bytes;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row_begin + e / row_bytes, c = e % row_bytes;
+    const int64_t src = r + 1 < n_rows ? r + 1 : n_rows - 1;
+    record_base[(size_t)r * stride + shadow_off + c] = record_base[(size_t)src * stride + obs_off + c];
+  }
+}
+
 __global__ void repad_rows_kernel(const uint8_t* __restrict__ dense, uint8_t* __restrict__ padded, int64_t n_rows,
                                   uint32_t row_bytes, uint32_t stride, int vec_log2) {
   const uint32_t epr = row_bytes >> vec_log2;
@@ -295,7 +310,14 @@ struct ogb_dataset {
   int device = 0;
   int64_t size = 0;         // rows allocated
   int64_t active_rows = 0;  // rows that hold data (== size except for a ReplayBuffer that is still filling up)
-  std::vector<Field> fields;
+  std::vector<Field> fields;    // the caller's fields, then (hidden, index >= n_public) the shadow field if there is one
+  size_t n_public = 0;
+  // Shadow copy of the NEXT row's observation inside every record (row r holds observations[min(r + 1, size - 1)],
+  // datasets.py:82), kept for datasets whose observation row is <= 16 bytes and fits the record's padding: the
+  // transition's next_observations then comes out of the record that is loaded anyway instead of costing a scattered
+  // sector of its own (point-maze: 4 -> 3 sectors per transition).  -1: none.
+  int shadow_next_field = -1;
+  size_t record_used = 0;       // bytes of a record the fields occupy (before padding)
   int obs_field = -1, terminals_field = -1, valids_field = -1, next_obs_field = -1, oracle_field = -1;
   // valid rows
   int valid_mode = 0;  // 0 none, 1 table, 2 gaps
@@ -657,12 +679,17 @@ struct PlanBuilder {
     push(std::move(k));
   }
   void base_keys() {  // datasets.py:78-83 (+ :229-231)
-    for (size_t i = 0; i < ds->fields.size(); ++i) {
+    for (size_t i = 0; i < ds->n_public; ++i) {
       const std::string& nm = ds->fields[i].name;
       if ((int)i == ds->obs_field) obs_key("observations", ogb::SLOT_IDX, true);
       else field_key(nm.c_str(), (int)i, ogb::SLOT_IDX, nm == "next_observations");
     }
-    if (ds->next_obs_field < 0) obs_key("next_observations", ogb::SLOT_NEXT, true);
+    if (ds->next_obs_field < 0) {
+      // observations[min(idx + 1, size - 1)] (datasets.py:82): from the record's shadow copy when there is one
+      // (never with frame stacking, whose next_observations is the un-clamped idx + 1 through the stacker, :231)
+      if (ds->shadow_next_field >= 0 && cfg->frame_stack <= 0) field_key("next_observations", ds->shadow_next_field, ogb::SLOT_IDX, true);
+      else obs_key("next_observations", ogb::SLOT_NEXT, true);
+    }
   }
 };
 
@@ -813,13 +840,6 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   ogb_dataset* ds = new ogb_dataset();
   ds->device = device;
   cudaDeviceGetAttribute(&ds->sm_count, cudaDevAttrMultiProcessorCount, device);
-  {  // keep freed batch blocks cached in the stream-ordered pool
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t thresh = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
-    }
-  }
   int rc = 0;
   auto bail = [&](int code) { dataset_unref(ds); return code; };
   int64_t size = 0;
@@ -898,6 +918,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
       // goal row (a prefix of the record) never straddles a line (measured on the 156-byte C2 record: stride 256 is
       // 8 % faster than 160 or 192 and 3 % faster than separate arrays)
       const int env_align = ab().record_align;
+      ds->record_used = cursor;
       ds->record_stride = cursor <= 32 ? 32 : cursor <= 64 ? 64 : round_up(cursor, env_align >= 32 ? (size_t)env_align : 128);
       const size_t bytes = (size_t)size * ds->record_stride;
       cudaError_t e = cudaMalloc((void**)&ds->record_base, bytes);
@@ -948,7 +969,26 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
       if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "repad of field '%s': %s", in.name, cudaGetErrorString(e)));
     }
   }
+  ds->n_public = ds->fields.size();
   ds->obs_field = ds->find("observations");
+  if (ds->obs_field >= 0 && ds->find("next_observations") < 0 && !ab().no_shadow) {
+    const Field obs = ds->fields[(size_t)ds->obs_field];
+    size_t a = 16;
+    while (obs.row_bytes % a != 0) a >>= 1;
+    const size_t off = round_up(ds->record_used, a);
+    if (obs.in_record && obs.row_bytes <= 16 && off + obs.row_bytes <= ds->record_stride) {
+      Field sh = obs;
+      sh.name = "\x01next_observations";      // not a name a caller can pass
+      sh.rec_off = off;
+      sh.dptr = ds->record_base + off;
+      ds->shadow_next_field = (int)ds->fields.size();
+      ds->fields.push_back(sh);
+      shadow_next_kernel<<<ds->sm_count * 8, 256>>>(ds->record_base, ds->record_stride, (uint32_t)obs.rec_off, (uint32_t)off,
+                                                     (uint32_t)obs.row_bytes, size, 0, size);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return bail(fail(OGB_ERR_CUDA, "shadow fill: %s", cudaGetErrorString(e)));
+    }
+  }
   ds->terminals_field = ds->find("terminals");
   ds->valids_field = ds->find("valids");
   ds->next_obs_field = ds->find("next_observations");
@@ -1153,7 +1193,7 @@ int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_
   if (!s || !field_rows) return fail(OGB_ERR_INVALID, "null argument");
   ogb_dataset* ds = s->ds;
   if (row < 0 || row >= ds->size) return fail(OGB_ERR_INDEX, "row %lld out of range", (long long)row);
-  if (n_fields != (int32_t)ds->fields.size()) return fail(OGB_ERR_INVALID, "expected %zu field pointers", ds->fields.size());
+  if (n_fields != (int32_t)ds->n_public) return fail(OGB_ERR_INVALID, "expected %zu field pointers", ds->n_public);
   DeviceGuard device_guard(ds->device);
   OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
@@ -1163,10 +1203,21 @@ int ogb_sampler_write_row(ogb_sampler* s, int64_t row, const void* const* field_
     OGB_CUDA(cudaEventRecord(ev, s->aux_stream));
     OGB_CUDA(cudaStreamWaitEvent(s->stream, ev, 0));
   }
-  for (size_t i = 0; i < ds->fields.size(); ++i) {
+  for (size_t i = 0; i < ds->n_public; ++i) {
     if (!field_rows[i]) continue;
     const Field& f = ds->fields[i];
     OGB_CUDA(cudaMemcpyAsync(f.dptr + (size_t)row * f.stride, field_rows[i], f.row_bytes, cudaMemcpyHostToDevice, s->stream));
+  }
+  if (ds->shadow_next_field >= 0 && field_rows[ds->obs_field]) {
+    // keep the shadow coherent: row r-1 shadows row r, and the last row shadows itself (stream-ordered behind the copy)
+    const Field& sh = ds->fields[(size_t)ds->shadow_next_field];
+    const Field& obs = ds->fields[(size_t)ds->obs_field];
+    const int64_t begin = row > 0 ? row - 1 : row, end = row == ds->size - 1 ? row + 1 : row;
+    if (end > begin) {
+      shadow_next_kernel<<<1, 32, 0, s->stream>>>(ds->record_base, ds->record_stride, (uint32_t)obs.rec_off, (uint32_t)sh.rec_off,
+                                                  (uint32_t)obs.row_bytes, ds->size, begin, end);
+      if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "shadow update launch failed");
+    }
   }
   return 0;
 } OGB_CATCH_ALL
@@ -1237,6 +1288,13 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       for (int64_t r = 0; r < total; ++r)
         if (idxs[r] < 0 || idxs[r] > last)
           return fail(OGB_ERR_INDEX, "index %lld is out of bounds for axis 0 with size %lld", (long long)idxs[r], (long long)ds->size);
+  }
+  if (idxs && spec.trl) {
+    // datasets.py:255-256: `assert (idxs != final_state_idxs).all()` -- a given index that is a trajectory's final state
+    // (a terminal row) has no midpoint span, and its idx + 1 belongs to the next trajectory (or lies past the table)
+    for (int64_t r = 0; r < total; ++r)
+      if (idxs[r] >= 0 && idxs[r] < ds->size && !ds->terminals_host.empty() && ds->terminals_host[(size_t)idxs[r]])
+        return fail(OGB_ERR_ASSERT, "assert (idxs != final_state_idxs).all() (datasets.py:256): index %lld is a final state", (long long)idxs[r]);
   }
   const int64_t n_choices = spec.n_choices >= 0 ? spec.n_choices : (ds->valid_mode == 0 ? ds->active_rows : ds->n_valid);
   if (n_choices < 1) return fail(OGB_ERR_INVALID, "nothing to sample from: the dataset holds no rows yet");
@@ -1672,64 +1730,103 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     return 0;
   };
 
-  // asynchronous row gather (cp.async ring per warp), all element widths in one launch
+  // asynchronous row gather (cp.async ring per warp), all element widths in one launch.  The jobs of a launch are
+  // unrolled into the item list of one 32-row tile (relabel_rows.cuh, ItemDesc / OutDesc); a job list that needs more
+  // items or outputs than a launch holds is split over several launches.
   for (size_t q = 0; q < span_jobs.size();) {
     AsyncGatherParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.vec_rows = b->vec_rows;
     ap.total_rows = total;
-    size_t max_pitch = 0;
     const size_t q0 = q;
-    for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) max_pitch = std::max(max_pitch, span_jobs[t].bytes);
-    // rows per item: the largest power of two whose rows fit the stage budget, so that the items of a 32-row tile are
-    // equal (an uneven split, e.g. 28 + 4 rows, makes the short item hold a pipeline slot for little data)
     const int env_stage = ab().stage_bytes;
+    auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
+    // rows per item: the largest power of two whose rows fit the stage budget, so that the items of a 32-row tile are
+    // equal (an uneven split, e.g. 28 + 4 rows, makes the short item hold a pipeline slot for little data).
     // budget: 4 KB stages (2 CTAs per SM) for rows up to 256 bytes, 6 KB (16-row items, 1 CTA per SM) beyond -- C3's
     // 384/288-byte spans run 15 % faster with 16-row items than with 8-row ones
-    const size_t budget = std::max<size_t>(env_stage ? (size_t)env_stage : (max_pitch > 256 ? 6144 : 4096), max_pitch);
-    auto rows_for = [&](size_t pitch) { size_t r = 32; while (r > 1 && r * pitch > budget) r >>= 1; return r; };
-    size_t stage = 0;
-    for (size_t t = q0; t < span_jobs.size() && t < q0 + kMaxRowJobs; ++t) stage = std::max(stage, rows_for(span_jobs[t].bytes) * span_jobs[t].bytes);
-    ap.stage_bytes = (int)round_up(stage, 128);
-    auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((((uint64_t)1 << 32) + d - 1) / d); };
-    int n_outs = 0;
-    for (; q < span_jobs.size() && ap.n_jobs < kMaxRowJobs && n_outs + (int)span_jobs[q].outs.size() <= kMaxRowOuts; ++q) {
-      const SpanJob& sj = span_jobs[q];
-      AsyncJob& job = ap.jobs[ap.n_jobs++];
-      job.src = sj.src;
-      job.stride = (uint32_t)sj.stride;
-      job.cpr = (uint32_t)(sj.bytes / 16);
-      job.spitch = job.cpr * 16u;
-      job.cpr_magic = magic(job.cpr);
-      job.chunk_dr = (uint8_t)(32 / job.cpr);
-      job.chunk_dch = (uint8_t)(32 % job.cpr);
-      job.chunk_step = (uint32_t)job.chunk_dr * job.spitch + (uint32_t)job.chunk_dch * 16u;
-      job.rows_per_item = (uint16_t)rows_for(job.spitch);   // >= 4 rows: items start on 16-byte boundaries of the dense output
-      job.slot = (uint8_t)sj.slot;
-      job.out_begin = (uint8_t)n_outs;
-      job.n_out = (uint8_t)sj.outs.size();
-      for (const auto& po : sj.outs) {
-        const Field& f = ds->fields[(size_t)plan[po.first].field];
-        AsyncOut& out = ap.outs[n_outs++];
-        out.dst = base + b->offsets[po.first];
-        out.soff = (uint32_t)po.second;
-        out.row_bytes = (uint32_t)f.row_bytes;
-        out.gap = job.spitch - (uint32_t)f.row_bytes;
-        if (f.row_bytes % 16 == 0 && out.gap == 0) {
-          out.drain = DRAIN_DENSE16;
-        } else if (f.row_bytes % 4 == 0 && po.second % 4 == 0) {
-          out.drain = DRAIN_WORDS;
-          out.epr = (uint32_t)(f.row_bytes / 4);
-        } else {
-          out.drain = DRAIN_ELEMS;
-          out.vec_log2 = (uint8_t)((f.row_bytes % 2 == 0 && po.second % 2 == 0) ? 1 : 0);
-          out.epr = (uint32_t)(f.row_bytes >> out.vec_log2);
-        }
-        out.epr_magic = magic(out.epr);
+    size_t q1 = std::min(span_jobs.size(), q0 + (size_t)kMaxRowJobs), budget = 0;
+    for (;; --q1) {   // the largest prefix of the remaining jobs whose items and outputs fit one launch
+      size_t max_pitch = 0, n_items = 0, n_outs = 0;
+      for (size_t t = q0; t < q1; ++t) max_pitch = std::max(max_pitch, span_jobs[t].bytes);
+      budget = std::max<size_t>(env_stage ? (size_t)env_stage : (max_pitch > 256 ? 6144 : 4096), max_pitch);
+      for (size_t t = q0; t < q1; ++t) {
+        size_t r = 32;
+        while (r > 1 && r * span_jobs[t].bytes > budget) r >>= 1;
+        n_items += 32 / r;
+        n_outs += (32 / r) * span_jobs[t].outs.size();
+      }
+      if ((n_items <= (size_t)kMaxItems && n_outs <= (size_t)kMaxItemOuts) || q1 == q0 + 1) {
+        if (n_items > (size_t)kMaxItems || n_outs > (size_t)kMaxItemOuts)
+          return bail(fail(OGB_ERR_UNSUPPORTED, "a %zu-byte row span with %zu keys does not fit one gather launch", span_jobs[q0].bytes, span_jobs[q0].outs.size()));
+        break;
       }
     }
-    const size_t smem = (size_t)kAsyncWarps * kAsyncStages * ap.stage_bytes;
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(220 * 1024) / smem));
+    auto rows_for = [&](size_t pitch) { size_t r = 32; while (r > 1 && r * pitch > budget) r >>= 1; return r; };
+    size_t stage = 0;
+    for (size_t t = q0; t < q1; ++t) stage = std::max(stage, rows_for(span_jobs[t].bytes) * span_jobs[t].bytes);
+    ap.stage_bytes = (int)round_up(stage, 128);
+    // (stages, warps per CTA): 3 x 8 built in; the alternatives are compiled for the GCDataset fused launch and the
+    // un-fused gather only (OGB_GATHER_SHAPE, measurement switch)
+    int shape = ab().gather_shape;
+    if (shape != 216 && shape != 316 && shape != 220) shape = 308;
+    if (shape != 308 && fuse && q0 == 0 && (p.kind != OGB_KIND_GC || draws != nullptr)) shape = 308;
+    const int n_stages = shape / 100, n_warps = shape % 100;
+    ap.ring_bytes = n_stages * ap.stage_bytes;
+    for (; q < q1; ++q) {
+      const SpanJob& sj = span_jobs[q];
+      const uint32_t cpr = (uint32_t)(sj.bytes / 16), pitch = cpr * 16u;
+      const uint32_t rpi = (uint32_t)rows_for(pitch);
+      for (uint32_t sub = 0; sub < 32; sub += rpi) {
+        ItemDesc& it = ap.items[ap.n_items++];
+        it.src16 = reinterpret_cast<const uint4*>(sj.src);
+        it.stride16 = (uint32_t)(sj.stride / 16);
+        it.cpr = cpr;
+        it.cpr_magic = magic(cpr);
+        it.dr = 32 / cpr;
+        it.dch = 32 % cpr;
+        it.slot = (uint32_t)sj.slot;
+        it.sub = sub;
+        it.rows = rpi;
+        it.flags = sub == 0 ? 1u : 0u;
+        it.out_begin_n = (uint32_t)ap.n_outs | ((uint32_t)sj.outs.size() << 16);
+        for (const auto& po : sj.outs) {
+          const Field& f = ds->fields[(size_t)plan[po.first].field];
+          OutDesc& out = ap.outs[ap.n_outs++];
+          out.dst = base + b->offsets[po.first] + (size_t)sub * f.row_bytes;
+          out.tile_bytes = (uint32_t)(32 * f.row_bytes);
+          out.soff = (uint32_t)po.second;
+          out.gap = pitch - (uint32_t)f.row_bytes;
+          uint32_t kind, vec_log2 = 0;
+          if (f.row_bytes % 16 == 0 && out.gap == 0) {
+            kind = DRAIN_DENSE16;
+            out.epr = (uint32_t)f.row_bytes;
+          } else if (f.row_bytes % 4 == 0 && po.second % 4 == 0) {
+            // items start on 16-byte boundaries of the dense output unless an item holds fewer than four odd-sized rows
+            kind = ((size_t)sub * f.row_bytes) % 16 == 0 ? DRAIN_WORDS : DRAIN_WORDS_UNALIGNED;
+            out.epr = (uint32_t)(f.row_bytes / 4);
+          } else {
+            kind = DRAIN_ELEMS;
+            vec_log2 = (f.row_bytes % 2 == 0 && po.second % 2 == 0) ? 1 : 0;
+            out.epr = (uint32_t)(f.row_bytes >> vec_log2);
+          }
+          out.epr_magic = magic(out.epr);
+          out.kind = kind | (vec_log2 << 8) | (pitch << 16);
+        }
+      }
+    }
+    // index-vector prefetch of the un-fused kernel: every pair's first item names the slot (and tile) of the pair after it
+    for (int k = 0; k < ap.n_items; ++k) {
+      if (!(ap.items[k].flags & 1u)) continue;
+      int nk = k + 1;
+      while (nk < ap.n_items && !(ap.items[nk].flags & 1u)) ++nk;
+      const bool wraps = nk == ap.n_items;
+      ap.items[k].flags |= (ap.items[wraps ? 0 : nk].slot << 8) | (wraps ? 0x10000u : 0u);
+    }
+    ap.ring_offset = (int)round_up((size_t)ap.n_items * sizeof(ItemDesc) + (size_t)ap.n_outs * sizeof(OutDesc), 128);
+    const size_t smem = (size_t)ap.ring_offset + (size_t)n_warps * ap.ring_bytes;
+    if (smem > (size_t)225 * 1024) return bail(fail(OGB_ERR_UNSUPPORTED, "gather shape %d needs %zu bytes of shared memory", shape, smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(n_warps <= 8 ? 8 : 1, (size_t)(220 * 1024) / smem));
     if (fuse && q0 == 0) {
       // index algebra + the first (normally the only) group of row jobs in ONE launch
       FusedParams* fp = new FusedParams();
@@ -1745,14 +1842,14 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       const int ws_env = ab().ws;
       const int n_slots_fl = flavour == FLAVOUR_GC ? GC_TRL_NUM_SLOTS : (flavour == FLAVOUR_HGC ? HGC_NUM_SLOTS : 2);
       const size_t ws_smem = smem + (size_t)kAsyncWarps * ((size_t)kQueueDepth * n_slots_fl * 128 + 16 * kQueueDepth);
-      const bool ws = (ws_env >= 0 ? ws_env != 0 : s->prefer_ws) && ws_smem <= 113 * 1024;
+      const bool ws = (ws_env >= 0 ? ws_env != 0 : s->prefer_ws) && ws_smem <= 113 * 1024 && shape == 308;
       fused_name = ws ? "relabel_gather_ws_kernel" : "relabel_gather_kernel";
       fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
         f.relabel.row_end = f.gather.row_end = end;
         const int64_t n_warp_tiles = (end - begin + 31) / 32;
-        const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * ctas_per_sm);
+        const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * ctas_per_sm);
         const void* fn = nullptr;
 #define OGB_PICK_FUSED(KERNEL, INJ)                                                      \
         fn = flavour == FLAVOUR_GC ? (const void*)KERNEL<INJ, FLAVOUR_GC>                   \
@@ -1763,8 +1860,11 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         else if (inject) { OGB_PICK_FUSED(relabel_gather_kernel, true); }
         else { OGB_PICK_FUSED(relabel_gather_kernel, false); }
 #undef OGB_PICK_FUSED
+        if (shape == 216) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 16>;
+        else if (shape == 316) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 3, 16>;
+        else if (shape == 220) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 20>;
         const size_t smem_bytes = ws ? ws_smem : smem;
-        const unsigned threads = ws ? (kAsyncWarps + kIndexWarps) * 32 : kAsyncWarps * 32;
+        const unsigned threads = ws ? (kAsyncWarps + kIndexWarps) * 32 : (unsigned)n_warps * 32;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess)
           return fail(OGB_ERR_CUDA, "cudaFuncSetAttribute(relabel_gather_kernel) failed");
         void* args[] = {(void*)&f};
@@ -1775,13 +1875,19 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       };
       continue;
     }
-    OGB_CUDA(cudaFuncSetAttribute(gather_rows_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const void* gather_fn = shape == 216 ? (const void*)gather_rows_async_kernel<2, 16>
+                          : shape == 316 ? (const void*)gather_rows_async_kernel<3, 16>
+                          : shape == 220 ? (const void*)gather_rows_async_kernel<2, 20>
+                                         : (const void*)gather_rows_async_kernel<kAsyncStages, kAsyncWarps>;
+    OGB_CUDA(cudaFuncSetAttribute(gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
       ap.row_begin = begin;
       ap.row_end = end;
       const int64_t n_warp_tiles = (end - begin + 31) / 32;
-      const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + kAsyncWarps - 1) / kAsyncWarps, (int64_t)ds->sm_count * ctas_per_sm);
-      gather_rows_async_kernel<<<grid, kAsyncWarps * 32, smem, st>>>(ap);
+      const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * ctas_per_sm);
+      void* args[] = {(void*)&ap};
+      if (cudaLaunchKernel(gather_fn, dim3(grid), dim3((unsigned)n_warps * 32), args, smem, st) != cudaSuccess)
+        return fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       if (cudaGetLastError() != cudaSuccess) return fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed");
       b->launches++;
       return 0;
@@ -2384,7 +2490,10 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
       }
       begin = end;
     }
+    int32_t chunk_flag = 0;   // the deferred index check covers chunked launches too (every chunk's kernels are done by now)
+    if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&chunk_flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
     OGB_CUDA(cudaStreamSynchronize(s->copy_stream));
+    if (chunk_flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
     return 0;
   }
   OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->stream));

@@ -338,8 +338,29 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     else i = valid_row<kSmemTables>(p, seg, pos);
   }
   put_slot(p, sr, SLOT_IDX, g, i);
-  const int32_t nxt = p.stacked_next ? i + p.next_offset                                           // :231 / :408
-                                     : (i + p.next_offset < p.n_rows_ds ? i + p.next_offset : p.n_rows_ds - 1);  // :82
+  // Grouped tiny fields of the transition's own record (observations, actions, terminals, valids of a point-maze row,
+  // plus the shadow copy of the next row's observation): fetched NOW, so the load flies under the goal algebra below
+  // (its first use was the hottest stall of C1's launch, 14 % of the samples, when it was issued after the goals).
+  uint4 grp_a[kMaxTinyGroups], grp_b[kMaxTinyGroups];
+#pragma unroll
+  for (int u = 0; u < kMaxTinyGroups; ++u) {
+    grp_a[u] = make_uint4(0, 0, 0, 0);
+    grp_b[u] = make_uint4(0, 0, 0, 0);
+    if (u < p.n_tiny_groups && p.tiny_groups[u].slot == SLOT_IDX) {
+      const TinyGroup& grp = p.tiny_groups[u];
+      const uint4* sp = reinterpret_cast<const uint4*>(grp.src + (size_t)(uint32_t)i * grp.stride);
+      grp_a[u] = __ldg(sp);
+      if (grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
+    }
+  }
+  // :82 clamps idx + 1 to size - 1; with frame stacking (:231) and for ATC (:408) the reference does not clamp, and a
+  // row past the table is an IndexError there: here the gather stays inside the table and the error is reported through
+  // the deferred index flag when the caller enabled it
+  int32_t nxt = i + p.next_offset;
+  if (nxt >= p.n_rows_ds) {
+    nxt = p.n_rows_ds - 1;
+    if (p.stacked_next && p.idx_error != nullptr) *p.idx_error = 1;
+  }
   put_slot(p, sr, SLOT_NEXT, g, nxt);
 
   if (kFlavour != FLAVOUR_PLAIN) {
@@ -421,29 +442,27 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     }
   }
 
-  // grouped tiny fields: one record load per group, all groups' loads issued before any store.  (Unrolling the field
-  // and job loops completely, so that the descriptors sit at fixed constant-bank offsets, was measured: the code
-  // growth costs more than the saved LDCs, 0.052 vs 0.047 ms on C1 and 0.223 vs 0.203 ms on C2's fused kernel.)
+  // grouped tiny fields: one record load per group (the groups of the transition's own row were fetched above), all
+  // loads issued before any store.  (Unrolling the field and job loops completely, so that the descriptors sit at fixed
+  // constant-bank offsets, was measured: the code growth costs more than the saved LDCs, 0.052 vs 0.047 ms on C1 and
+  // 0.223 vs 0.203 ms on C2's fused kernel.)
   {
-    uint4 ga[kMaxTinyGroups], gb[kMaxTinyGroups];
 #pragma unroll
     for (int u = 0; u < kMaxTinyGroups; ++u) {
-      ga[u] = make_uint4(0, 0, 0, 0);
-      gb[u] = make_uint4(0, 0, 0, 0);
-      if (u < p.n_tiny_groups) {
+      if (u < p.n_tiny_groups && p.tiny_groups[u].slot != SLOT_IDX) {
         const TinyGroup& grp = p.tiny_groups[u];
         const uint4* sp = reinterpret_cast<const uint4*>(grp.src + (size_t)(uint32_t)pick_slot<kSlots>(sr, grp.slot) * grp.stride);
-        ga[u] = __ldg(sp);
-        if (grp.n_vec > 1) gb[u] = __ldg(sp + 1);
+        grp_a[u] = __ldg(sp);
+        if (grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
       }
     }
 #pragma unroll 1
     for (int f = 0; f < p.n_tiny_fields; ++f) {
       const TinyField& fld = p.tiny_fields[f];
-      uint4 a = ga[0], b = gb[0];
+      uint4 a = grp_a[0], b = grp_b[0];
 #pragma unroll
       for (int u = 1; u < kMaxTinyGroups; ++u)
-        if (fld.group == u) { a = ga[u]; b = gb[u]; }
+        if (fld.group == u) { a = grp_a[u]; b = grp_b[u]; }
       uint32_t* dp = reinterpret_cast<uint32_t*>(fld.dst) + (size_t)g * fld.n_words;
       const uint32_t w0 = select_word(a, b, fld.word);
       if (fld.n_words == 1) {
@@ -529,7 +548,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
 // kSmemTables: a persistent grid (a few CTAs per SM) whose CTAs first copy the segment table into shared memory
 // (dynamic: 16 B * n_seg_table + 4 B * n_seg_bucket) and then walk the rows with a grid stride.
 template <bool kInject, int kFlavour, bool kSmemTables>
-__global__ void __launch_bounds__(kRelabelThreads) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
+__global__ void __launch_bounds__(kRelabelThreads, 4) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
   extern __shared__ __align__(16) uint8_t smem_tables[];
   SegView seg{p.seg_bucket, p.seg_table};
   if (kSmemTables) {
@@ -684,49 +703,62 @@ constexpr int kAsyncStages = 3;
 constexpr int kAsyncWarps = 8;
 constexpr int kAsyncMaxStride = 4096;
 
-enum : int { DRAIN_WORDS = 0, DRAIN_DENSE16 = 1, DRAIN_ELEMS = 2 };
-
-// One output array of a job: a sub-field of the staged span, written densely (datasets.py:78-83: every field of the
-// dataset is gathered at the same rows, so one staged record feeds several keys).
-struct AsyncOut {
-  uint8_t* dst;
-  uint32_t soff;          // byte offset of the sub-field inside a staged row
-  uint32_t row_bytes;
-  uint32_t epr;           // output elements per row: 4-byte words (DRAIN_WORDS) or 1 << vec_log2 bytes (DRAIN_ELEMS)
-  uint32_t epr_magic;     // ceil(2^32 / epr), or 0 when epr == 1
-  uint32_t gap;           // spitch - row_bytes: bytes between the end of this sub-field in one staged row and its start in the next
-  uint8_t drain;          // DRAIN_*
-  uint8_t vec_log2;       // DRAIN_ELEMS only
-  uint16_t pad_;
-};
-
-// One load job: the span [src, src + 16 * cpr) of every source row named by index vector `slot`
-struct AsyncJob {
-  const uint8_t* src;     // field base, or record table base + span offset; 16-byte aligned
-  uint32_t stride;        // source row stride, multiple of 16
-  uint32_t spitch;        // row pitch inside a stage = 16 * cpr
-  uint32_t cpr;           // 16-byte chunks copied per row
+// The work of one 32-row warp tile is a fixed list of pipeline ITEMS -- (load job, sub-range of rows that fits one
+// stage) -- and every item feeds one or more dense OUTPUTS (datasets.py:78-83: every field of the dataset is gathered
+// at the same rows, so one staged record feeds several keys).  The list is the same for every tile of a launch, so the
+// host lays it out once, with everything that can be derived ahead of time already derived, and every CTA keeps a copy
+// in shared memory: an item costs the warp three 16-byte shared loads to set up, an output two (the first version
+// walked job/output descriptors in the constant bank and re-derived cursors, ring addresses and alignment per item:
+// 47 % of the executed instructions of C2's fused launch were that bookkeeping, profiles/r2_c2_sass_before.txt).
+struct __align__(16) ItemDesc {
+  // ---- words 0-3 ----
+  const uint4* src16;     // span base: field base, or record table base + span offset; 16-byte aligned
+  uint32_t stride16;      // source row stride in 16-byte units
+  uint32_t cpr;           // 16-byte chunks copied per row (the row pitch inside a stage is exactly cpr chunks)
+  // ---- words 4-7 ----
   uint32_t cpr_magic;     // ceil(2^32 / cpr), or 0 when cpr == 1: e / cpr == umulhi(e, magic) for e * cpr < 2^32
-  uint32_t chunk_step;    // advance of a lane's stage offset per issue iteration: (32 / cpr) * spitch + (32 % cpr) * 16
-  uint16_t rows_per_item; // rows of one stage
-  uint8_t slot;
-  uint8_t chunk_dr;       // 32 / cpr
-  uint8_t chunk_dch;      // 32 % cpr
-  uint8_t out_begin;      // first of this job's outputs in AsyncGatherParams::outs
-  uint8_t n_out;
-  uint8_t pad_;
+  uint32_t dr;            // 32 / cpr   } advance of a lane's (row, chunk) position per issue iteration
+  uint32_t dch;           // 32 % cpr   }
+  uint32_t slot;          // which index vector names the source rows
+  // ---- words 8-11 (all the drain needs) ----
+  uint32_t sub;           // first row of the item inside the tile
+  uint32_t rows;          // rows of the item in a full tile
+  uint32_t flags;         // bit 0: first item of its (tile, job) pair; bits 8-15: slot of the NEXT pair; bit 16: that pair
+                          // belongs to the next tile (index-vector prefetch of the un-fused kernel)
+  uint32_t out_begin_n;   // first output | number of outputs << 16
 };
+static_assert(sizeof(ItemDesc) == 48, "ItemDesc is read as three 16-byte words");
 
-constexpr int kMaxRowOuts = 48;
+enum : int { DRAIN_WORDS = 0, DRAIN_DENSE16 = 1, DRAIN_ELEMS = 2, DRAIN_WORDS_UNALIGNED = 3 };
+
+struct __align__(16) OutDesc {
+  // ---- words 0-3 ----
+  uint8_t* dst;           // key base + sub * row_bytes: output of the item's first row in tile 0
+  uint32_t tile_bytes;    // 32 * row_bytes: advance per tile
+  uint32_t soff;          // byte offset of the sub-field inside a staged row
+  // ---- words 4-7 ----
+  uint32_t epr;           // output elements per row: 4-byte words (DRAIN_WORDS*), 1 << vec_log2 bytes (DRAIN_ELEMS), bytes (DENSE16)
+  uint32_t epr_magic;     // ceil(2^32 / epr), or 0 when epr == 1
+  uint32_t gap;           // stage pitch - row_bytes: bytes between the end of this sub-field in one staged row and its start in the next
+  uint32_t kind;          // DRAIN_* | vec_log2 << 8 | stage pitch << 16 (DRAIN_ELEMS only)
+};
+static_assert(sizeof(OutDesc) == 32, "OutDesc is read as two 16-byte words");
+
+constexpr int kMaxItems = 64;      // per launch; the host splits the job list over several launches beyond that
+constexpr int kMaxItemOuts = 96;
 
 struct AsyncGatherParams {
   const int32_t* vec_rows;
   int64_t total_rows;
   int64_t row_begin, row_end;  // row_begin is a multiple of 32
-  int32_t n_jobs;
+  int32_t n_items;             // items of one tile
+  int32_t n_outs;              // outputs of all items
   int32_t stage_bytes;
-  AsyncJob jobs[kMaxRowJobs];
-  AsyncOut outs[kMaxRowOuts];
+  int32_t ring_bytes;          // kAsyncStages * stage_bytes
+  int32_t ring_offset;         // the per-warp rings start this far into dynamic shared memory (after the tables)
+  int32_t pad_;
+  ItemDesc items[kMaxItems];
+  OutDesc outs[kMaxItemOuts];
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
@@ -800,10 +832,9 @@ __device__ __forceinline__ void drain_dense16(const uint32_t sbase, uint8_t* __r
   for (uint32_t i = lane; i < n16; i += 32) store_out(reinterpret_cast<uint4*>(dbase) + i, lds128(sbase + (i << 4)));
 }
 
-struct ItemCursor {
-  int32_t wt;   // warp tile (32 batch rows); a launch holds < 2^31 rows, so tiles fit 32 bits comfortably
-  int32_t j;    // job
-  int32_t sub;  // first row of the sub-range within the warp tile
+struct TileCursor {
+  int32_t tile; // warp tile (32 batch rows); a launch holds < 2^31 rows, so tiles fit 32 bits comfortably
+  int32_t k;    // item of the tile (index into the item table)
   int32_t n;    // rows of this tile (32 except for the ragged last tile)
 };
 
@@ -844,52 +875,61 @@ __device__ __forceinline__ void queue_mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, int32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
-template <int kMode, bool kInject, int kFlavour>
-__device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& p, const RelabelParams& rp, uint8_t* smem_ring,
+// every CTA copies the launch's item / output tables from the constant bank into shared memory once
+__device__ __forceinline__ void stage_tables(const AsyncGatherParams& p, uint8_t* smem_dyn) {
+  uint4* items_s = reinterpret_cast<uint4*>(smem_dyn);
+  const int n_item_vecs = p.n_items * (int)(sizeof(ItemDesc) / 16);
+  for (int i = threadIdx.x; i < n_item_vecs; i += blockDim.x) items_s[i] = reinterpret_cast<const uint4*>(p.items)[i];
+  uint4* outs_s = items_s + n_item_vecs;
+  const int n_out_vecs = p.n_outs * (int)(sizeof(OutDesc) / 16);
+  for (int i = threadIdx.x; i < n_out_vecs; i += blockDim.x) outs_s[i] = reinterpret_cast<const uint4*>(p.outs)[i];
+}
+
+template <int kMode, bool kInject, int kFlavour, int kStages = kAsyncStages, int kWarps = kAsyncWarps>
+__device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& p, const RelabelParams& rp, uint8_t* smem_dyn,
                                                        const QueueView qv) {
-  constexpr bool kFused = kMode != MODE_VECTORS;
   constexpr int kSlots = FlavourSlots<kFlavour>::value;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int32_t n_warps_global = (int32_t)gridDim.x * kAsyncWarps;
-  const int32_t n_warp_tiles = (int32_t)((p.row_end + 31) >> 5);
-  const int32_t last_n = (int32_t)(p.row_end - ((int64_t)(n_warp_tiles - 1) << 5));      // rows of the last tile
-  const int32_t first_tile = (int32_t)(p.row_begin >> 5) + (int32_t)blockIdx.x * kAsyncWarps + warp;
-  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;
-  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(smem_ring) + (uint32_t)warp * (uint32_t)kAsyncStages * stage_bytes;
-  const int32_t n_jobs = p.n_jobs;
+  const int32_t n_warps_global = (int32_t)gridDim.x * kWarps;
+  const int32_t n_tiles = (int32_t)((p.row_end + 31) >> 5);
+  const int32_t last_n = (int32_t)(p.row_end - ((int64_t)(n_tiles - 1) << 5));      // rows of the last tile
+  const int32_t first_tile = (int32_t)(p.row_begin >> 5) + (int32_t)blockIdx.x * kWarps + warp;
+  const int32_t n_items = p.n_items;
+  const uint4* items_s = reinterpret_cast<const uint4*>(smem_dyn);
+  const uint4* outs_s = items_s + n_items * (int)(sizeof(ItemDesc) / 16);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(smem_dyn) + (uint32_t)p.ring_offset + (uint32_t)warp * (uint32_t)p.ring_bytes;
 
-  auto tile_rows = [&](int32_t wt) -> int32_t { return wt == n_warp_tiles - 1 ? last_n : 32; };
-  auto advance = [&](ItemCursor& c) {
-    c.sub += p.jobs[c.j].rows_per_item;
-    if (c.sub >= c.n) {
-      c.sub = 0;
-      if (++c.j == n_jobs) { c.j = 0; c.wt += n_warps_global; c.n = tile_rows(c.wt); }
+  auto advance = [&](TileCursor& c) {
+    if (++c.k == n_items) {
+      c.k = 0;
+      c.tile += n_warps_global;
+      c.n = c.tile == n_tiles - 1 ? last_n : 32;
     }
   };
-  // lane l keeps the source row of batch row (wt*32 + l) for the (tile, job) pair being issued
-  int32_t sr[kMaxSlots];                 // kFused: rows of every slot for the tile being issued
+  // lane l keeps the source row of batch row (tile*32 + l) for the (tile, job) pair being issued
+  int32_t sr[kMaxSlots];                 // fused: rows of every slot for the tile being issued
 #pragma unroll
   for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
   int32_t issue_rows = 0;
-  // !kFused: the vector of the pair after the current one is fetched one pair ahead, so its latency hides behind a job
-  auto load_rows = [&](int32_t wt, int j) -> int32_t {
-    if (wt >= n_warp_tiles) return 0;
-    const int n = tile_rows(wt);
-    return __ldg(p.vec_rows + (int64_t)p.jobs[j].slot * p.total_rows + ((int64_t)wt << 5) + min(lane, n - 1));
+  // un-fused: the vector of the pair after the current one is fetched one pair ahead, so its latency hides behind a job
+  auto load_rows = [&](int32_t tile, uint32_t slot) -> int32_t {
+    if (tile >= n_tiles) return 0;
+    const int n = tile == n_tiles - 1 ? last_n : 32;
+    return __ldg(p.vec_rows + (int64_t)slot * p.total_rows + ((int64_t)tile << 5) + min(lane, n - 1));
   };
   int32_t pref_rows = 0;
-  if (!kFused) pref_rows = load_rows(first_tile, 0);
+  if (kMode == MODE_VECTORS) pref_rows = load_rows(first_tile, items_s[1].w);
   uint32_t queue_k = 0;                  // MODE_QUEUE: ordinal of the next tile this warp takes from its queue
-
-  auto issue = [&](const ItemCursor& c, const uint32_t stage_u32) {
-    if (c.wt < n_warp_tiles) {
-      const AsyncJob& job = p.jobs[c.j];
-      if (c.sub == 0) {                                        // entering the next (tile, job) pair
+  auto issue = [&](const TileCursor& c, const uint32_t stage_u32) {
+    if (c.tile < n_tiles) {
+      const uint4* it = items_s + c.k * (int)(sizeof(ItemDesc) / 16);
+      const uint4 d0 = it[0], d1 = it[1], d2 = it[2];
+      if (d2.z & 1u) {                                           // entering the next (tile, job) pair
         if (kMode == MODE_FUSED) {
-          if (c.j == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, SegView{rp.seg_bucket, rp.seg_table}, ((int64_t)c.wt << 5) + lane, sr);
-          issue_rows = pick_slot<kSlots>(sr, job.slot);
+          if (c.k == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, SegView{rp.seg_bucket, rp.seg_table}, ((int64_t)c.tile << 5) + lane, sr);
+          issue_rows = pick_slot<kSlots>(sr, (int)d1.w);
         } else if (kMode == MODE_QUEUE) {
-          if (c.j == 0) {                                      // take this tile's rows from the index warps
+          if (c.k == 0) {                                        // take this tile's rows from the index warps
             const uint32_t qs = queue_k % kQueueDepth;
             queue_mbar_wait(qv.full + 8u * qs, (queue_k / kQueueDepth) & 1u);
 #pragma unroll
@@ -898,95 +938,100 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
             if (lane == 0) queue_mbar_arrive(qv.empty + 8u * qs);
             ++queue_k;
           }
-          issue_rows = pick_slot<kSlots>(sr, job.slot);
+          issue_rows = pick_slot<kSlots>(sr, (int)d1.w);
         } else {
           issue_rows = pref_rows;
-          const int nj = c.j + 1 < n_jobs ? c.j + 1 : 0;
-          pref_rows = load_rows(nj ? c.wt : c.wt + n_warps_global, nj);
+          pref_rows = load_rows((d2.z & 0x10000u) ? c.tile + n_warps_global : c.tile, (d2.z >> 8) & 0xffu);
         }
       }
-      const int rows = min((int)job.rows_per_item, c.n - c.sub);
-      const uint32_t cpr = job.cpr, spitch = job.spitch;
+      const uint32_t cpr = d0.w, stride16 = d0.z, dr = d1.y, dch = d1.z;
+      const int rows = min((int)d2.y, c.n - (int)d2.x);          // <= 0: the ragged last tile ends before this item
       const int n_chunks = rows * (int)cpr;
-      // lane -> (row r, chunk ch) of the item; both advance incrementally, no division inside the loop.
-      // Source addresses are formed in 16-byte units (32-bit), so a field must stay below 64 GB (host-checked).
-      uint32_t r = fast_div((uint32_t)lane, job.cpr_magic);
+      // lane -> (row r, chunk ch) of the item; both advance incrementally, no division inside the loop.  Chunk e of an
+      // item lands at stage offset 16 * e (the stage pitch is exactly cpr chunks).  Source addresses are formed in
+      // 16-byte units (32-bit), so a field must stay below 64 GB (host-checked).
+      uint32_t r = fast_div((uint32_t)lane, d1.x);
       uint32_t ch = (uint32_t)lane - r * cpr;
-      uint32_t soff = stage_u32 + r * spitch + (ch << 4);
-      const uint32_t stride16 = job.stride >> 4;
-      const uint32_t dr = job.chunk_dr, dch = job.chunk_dch, step = job.chunk_step;
-      const uint4* __restrict__ src16 = reinterpret_cast<const uint4*>(job.src);
-      r += (uint32_t)c.sub;
-      if (dch == 0) {                                          // chunks per row divide 32: a lane stays on its chunk column
-        src16 += ch;
+      r += d2.x;
+      uint32_t soff = stage_u32 + ((uint32_t)lane << 4);
+      const uint4* __restrict__ src16 = reinterpret_cast<const uint4*>(((uint64_t)d0.y << 32) | (uint64_t)d0.x);
+      if (dch == 0) {                                            // chunks per row divide 32: a lane stays on its chunk column
 #pragma unroll 2
         for (int e = lane; e - lane < n_chunks; e += 32) {
           const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, issue_rows, (int)r);
-          if (e < n_chunks) cp_async16(soff, src16 + src_row * stride16);
-          r += dr; soff += step;
+          if (e < n_chunks) cp_async16(soff, src16 + (src_row * stride16 + ch));
+          r += dr; soff += 512u;
         }
       } else {
 #pragma unroll 2
         for (int e = lane; e - lane < n_chunks; e += 32) {
           const uint32_t src_row = (uint32_t)__shfl_sync(0xffffffffu, issue_rows, (int)r);
           if (e < n_chunks) cp_async16(soff, src16 + (src_row * stride16 + ch));
-          r += dr; ch += dch; soff += step;
-          if (ch >= cpr) { ch -= cpr; ++r; }     // the stage pitch is exactly cpr chunks: soff needs no correction
+          r += dr; ch += dch; soff += 512u;
+          if (ch >= cpr) { ch -= cpr; ++r; }
         }
       }
     }
     cp_async_commit();
   };
 
-  auto drain = [&](const ItemCursor& c, const uint32_t sbase) {
-    const AsyncJob& job = p.jobs[c.j];
-    const int rows = min((int)job.rows_per_item, c.n - c.sub);
-    const uint32_t first_row = (uint32_t)((c.wt << 5) + c.sub);
+  auto drain = [&](const TileCursor& c, const uint32_t sbase) {
+    const uint4 d2 = items_s[c.k * (int)(sizeof(ItemDesc) / 16) + 2];
+    const int rows = min((int)d2.y, c.n - (int)d2.x);
+    if (rows <= 0) return;
+    const uint4* od = outs_s + (d2.w & 0xffffu) * (uint32_t)(sizeof(OutDesc) / 16);
 #pragma unroll 1
-    for (int o = job.out_begin; o < job.out_begin + job.n_out; ++o) {
-      const AsyncOut& out = p.outs[o];
-      uint8_t* dbase = out.dst + (size_t)first_row * out.row_bytes;
-      const uint32_t s0 = sbase + out.soff;
-      if (out.drain == DRAIN_WORDS) {
-        if ((reinterpret_cast<uintptr_t>(dbase) & 15) == 0) drain_words(s0, dbase, (uint32_t)rows * out.epr, out.epr_magic, out.gap, lane);
-        else drain_words_unaligned(s0, dbase, (uint32_t)rows * out.epr, out.epr_magic, out.gap, lane);
-      } else if (out.drain == DRAIN_DENSE16) {
-        drain_dense16(s0, dbase, (uint32_t)rows * out.row_bytes, lane);
+    for (uint32_t o = d2.w >> 16; o != 0; --o, od += sizeof(OutDesc) / 16) {
+      const uint4 o0 = od[0], o1 = od[1];
+      uint8_t* dbase = reinterpret_cast<uint8_t*>(((uint64_t)o0.y << 32) | (uint64_t)o0.x) + (uint64_t)(uint32_t)c.tile * o0.z;
+      const uint32_t s0 = sbase + o0.w;
+      const uint32_t kind = o1.w & 0xffu;
+      if (kind == DRAIN_WORDS) {
+        drain_words(s0, dbase, (uint32_t)rows * o1.x, o1.y, o1.z, lane);
+      } else if (kind == DRAIN_DENSE16) {
+        drain_dense16(s0, dbase, (uint32_t)rows * o1.x, lane);
+      } else if (kind == DRAIN_WORDS_UNALIGNED) {
+        drain_words_unaligned(s0, dbase, (uint32_t)rows * o1.x, o1.y, o1.z, lane);
       } else {
-        const uint8_t* sgen = smem_ring + (size_t)(s0 - (uint32_t)__cvta_generic_to_shared(smem_ring));
-        const uint32_t n_elem = (uint32_t)rows * out.epr;
-        if (out.vec_log2 == 1) drain_flat<uint16_t>(sgen, dbase, n_elem, job.spitch, out.epr, out.epr_magic, lane);
-        else drain_flat<uint8_t>(sgen, dbase, n_elem, job.spitch, out.epr, out.epr_magic, lane);
+        const uint8_t* sgen = smem_dyn + (size_t)(s0 - (uint32_t)__cvta_generic_to_shared(smem_dyn));
+        const uint32_t n_elem = (uint32_t)rows * o1.x, pitch = o1.w >> 16;
+        if (((o1.w >> 8) & 0xffu) == 1u) drain_flat<uint16_t>(sgen, dbase, n_elem, pitch, o1.x, o1.y, lane);
+        else drain_flat<uint8_t>(sgen, dbase, n_elem, pitch, o1.x, o1.y, lane);
       }
     }
   };
 
-  ItemCursor head{first_tile, 0, 0, 32};  // next item to issue
-  if (first_tile < n_warp_tiles) head.n = tile_rows(first_tile);
-  ItemCursor tail = head;                  // next item to drain
-  const uint32_t ring_end = ring_u32 + (uint32_t)kAsyncStages * stage_bytes;
-  uint32_t head_stage = ring_u32, tail_stage = ring_u32;   // shared-memory addresses of the stages
+  TileCursor head{first_tile, 0, first_tile == n_tiles - 1 ? last_n : 32};  // next item to issue
+  TileCursor tail = head;                                                    // next item to drain
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes, ring_bytes = (uint32_t)p.ring_bytes;
+  uint32_t head_off = 0, tail_off = 0;                                       // stage offsets inside this warp's ring
 #pragma unroll 1
-  for (int t = 0; tail.wt < n_warp_tiles; ++t) {
-    issue(head, head_stage);             // one cp.async group per iteration (empty once the head has run off the end)
-    if (head.wt < n_warp_tiles) advance(head);
-    head_stage += stage_bytes;
-    if (head_stage == ring_end) head_stage = ring_u32;
-    if (t >= kAsyncStages - 1) {
-      cp_async_wait<kAsyncStages - 1>();   // everything but the newest kAsyncStages-1 groups has landed
+  for (int t = 0; tail.tile < n_tiles; ++t) {
+    issue(head, ring_u32 + head_off);    // one cp.async group per iteration (empty once the head has run off the end)
+    if (head.tile < n_tiles) advance(head);
+    head_off += stage_bytes;
+    if (head_off == ring_bytes) head_off = 0;
+    if (t >= kStages - 1) {
+      cp_async_wait<kStages - 1>();        // everything but the newest kStages-1 groups has landed
       __syncwarp();                        // ... for every lane of this warp
-      drain(tail, tail_stage);
+      drain(tail, ring_u32 + tail_off);
       __syncwarp();                        // the stage may be overwritten by the next issue
       advance(tail);
-      tail_stage += stage_bytes;
-      if (tail_stage == ring_end) tail_stage = ring_u32;
+      tail_off += stage_bytes;
+      if (tail_off == ring_bytes) tail_off = 0;
     }
   }
 }
 
-__global__ void __launch_bounds__(kAsyncWarps * 32) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
-  extern __shared__ __align__(128) uint8_t smem_ring[];
-  gather_rows_async_body<MODE_VECTORS, false, FLAVOUR_PLAIN>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_ring, QueueView{0, 0, 0});
+// resident CTAs per SM a (stages, warps) shape is compiled for: the register cap follows from it
+constexpr int gather_min_blocks(int warps) { return warps <= 8 ? 2 : 1; }
+
+template <int kStages = kAsyncStages, int kWarps = kAsyncWarps>
+__global__ void __launch_bounds__(kWarps * 32, gather_min_blocks(kWarps)) gather_rows_async_kernel(const __grid_constant__ AsyncGatherParams p) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  stage_tables(p, smem_dyn);
+  __syncthreads();
+  gather_rows_async_body<MODE_VECTORS, false, FLAVOUR_PLAIN, kStages, kWarps>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_dyn, QueueView{0, 0, 0});
 }
 
 struct FusedParams {
@@ -995,21 +1040,24 @@ struct FusedParams {
 };
 
 // sample() in one launch: index algebra + row gathers (datasets.py:213-294 / :496-643 for vector observations)
-template <bool kInject, int kFlavour>
-__global__ void __launch_bounds__(kAsyncWarps * 32) relabel_gather_kernel(const __grid_constant__ FusedParams p) {
-  extern __shared__ __align__(128) uint8_t smem_ring[];
-  gather_rows_async_body<MODE_FUSED, kInject, kFlavour>(p.gather, p.relabel, smem_ring, QueueView{0, 0, 0});
+template <bool kInject, int kFlavour, int kStages = kAsyncStages, int kWarps = kAsyncWarps>
+__global__ void __launch_bounds__(kWarps * 32, gather_min_blocks(kWarps)) relabel_gather_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  stage_tables(p.gather, smem_dyn);
+  __syncthreads();
+  gather_rows_async_body<MODE_FUSED, kInject, kFlavour, kStages, kWarps>(p.gather, p.relabel, smem_dyn, QueueView{0, 0, 0});
 }
 
 // sample() in one launch, warp-specialised: warps [0, kAsyncWarps) gather, warps [kAsyncWarps, +kIndexWarps) run the
-// index algebra ahead of them.  Dynamic shared memory: the rings, then the row queues, then the mbarriers.
+// index algebra ahead of them.  Dynamic shared memory: the tables, the rings, then the row queues, then the mbarriers.
 template <bool kInject, int kFlavour>
 __global__ void __launch_bounds__((kAsyncWarps + kIndexWarps) * 32) relabel_gather_ws_kernel(const __grid_constant__ FusedParams p) {
   constexpr int kSlots = FlavourSlots<kFlavour>::value;
-  extern __shared__ __align__(128) uint8_t smem_ring[];
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t ring_bytes = (uint32_t)kAsyncWarps * kAsyncStages * (uint32_t)p.gather.stage_bytes;
-  const uint32_t queue_u32 = (uint32_t)__cvta_generic_to_shared(smem_ring) + ring_bytes;
+  stage_tables(p.gather, smem_dyn);
+  const uint32_t rings_end = (uint32_t)p.gather.ring_offset + (uint32_t)kAsyncWarps * (uint32_t)p.gather.ring_bytes;
+  const uint32_t queue_u32 = (uint32_t)__cvta_generic_to_shared(smem_dyn) + rings_end;
   constexpr uint32_t kQueueBytesPerWarp = kQueueDepth * kSlots * 32 * 4;
   const uint32_t bars_u32 = queue_u32 + (uint32_t)kAsyncWarps * kQueueBytesPerWarp;
   auto view_of = [&](int w) { return QueueView{queue_u32 + (uint32_t)w * kQueueBytesPerWarp, bars_u32 + (uint32_t)w * (16u * kQueueDepth),
@@ -1019,7 +1067,7 @@ __global__ void __launch_bounds__((kAsyncWarps + kIndexWarps) * 32) relabel_gath
   __syncthreads();
 
   if (warp < kAsyncWarps) {
-    gather_rows_async_body<MODE_QUEUE, kInject, kFlavour>(p.gather, p.relabel, smem_ring, view_of(warp));
+    gather_rows_async_body<MODE_QUEUE, kInject, kFlavour>(p.gather, p.relabel, smem_dyn, view_of(warp));
     return;
   }
   // ---- index warps ----

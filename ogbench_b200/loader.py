@@ -165,12 +165,14 @@ def _join_prefetch_threads():
 class ShardCycler:
     """Cycle through dataset shards like impls/main.py:185-199, without the reload stall.
 
-        cycler = ShardCycler(list_shards(path), make_sampler=lambda p: load_gc_dataset(p, config), replace_interval=1000)
+        cycler = ShardCycler(list_shards(path), make_sampler=lambda p: load_gc_dataset(p, config, seed=FLAGS.seed),
+                             replace_interval=1000)
         for i in range(1, train_steps + 1):
             train_dataset = cycler.at_step(i)          # swaps to the next shard when i % replace_interval == 0
             batch = train_dataset.sample(batch_size)
 
-    Random goals stay shard-local, exactly as in the reference (only the loaded shard is sampled).
+    Random goals stay shard-local, exactly as in the reference (only the loaded shard is sampled).  The sampler's
+    RNG position (its Philox batch counter) is carried from shard to shard, so revisiting a shard draws new batches.
     """
 
     def __init__(self, shard_paths: List[str], make_sampler: Callable[[str], Any], replace_interval: int, prefetch: bool = True):
@@ -216,13 +218,22 @@ class ShardCycler:
                 if self._error is not None:
                     raise self._error
                 assert self._next_index == self.index
-                self.current, self._next = self._next, None
+                previous, self.current, self._next = self.current, self._next, None
                 self.prefetched_swaps += int(ready_early)
             else:
-                self.current = self.make_sampler(self.paths[self.index])
+                previous, self.current = self.current, self.make_sampler(self.paths[self.index])
+            self._carry_rng(previous, self.current)
             self.swaps += 1
             self._start_prefetch()
         return self.current
+
+    @staticmethod
+    def _carry_rng(previous, current):
+        """The reference keeps consuming ONE np.random stream across shard swaps (impls/main.py:185-202), so a revisited
+        shard never replays its batches.  A fresh sampler starts at Philox counter 0: hand it the position the previous
+        shard's sampler had reached (same seed / stream_id, the counter keeps advancing over the whole run)."""
+        if hasattr(previous, 'state_dict') and hasattr(current, 'load_state_dict'):
+            current.load_state_dict(previous.state_dict())
 
     def close(self):
         if self._thread is not None:

@@ -34,3 +34,27 @@ def test_bench_gpu_arm_prints_the_contract_line():
     cpu = line['cpu_baseline']
     assert cpu['kind'] == 'port' and cpu['cores'] == 1 and cpu['value'] > 0 and cpu['sample']
     assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
+    # the timed region is stretched to >= 250 ms by repeating the K-step loop, and says so
+    assert line['repeats'] >= 1 and line['timed_region_ms'] >= 200 and line['steps_timed'] == line['steps'] * line['repeats']
+    assert line['clocks']['samples'] >= 20
+    assert 0 < e2e['frac_of_link'] < 1.1 and e2e['link_gbs'] > 1
+    # every BASELINE.json config rides in the same line
+    assert set(line['configs']) == {'c1', 'c2', 'c3', 'c4', 'c5'}
+    for key, c in line['configs'].items():
+        assert c['value'] > 0 and 0.05 < c['roofline']['frac'] < 1.05 and c['roofline']['kernel'], key
+        assert c['e2e']['value'] > 0 and c['cpu_baseline']['value'] > 0, key
+    assert line['configs']['c2']['value'] == line['value']
+
+
+def test_bench_reference_arm_prints_the_same_config():
+    common = ['--steps', '3', '--warmup', '1']
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', *common], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    line = json.loads([ln for ln in ref.stdout.splitlines() if ln.strip()][-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['steps'] == 3 and line['warmup'] == 1
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    ours = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--config', 'c2', '--no-cpu-baseline', '--no-e2e', *common],
+                          capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert ours.returncode == 0, ours.stderr[-2000:]
+    assert json.loads(ours.stdout.splitlines()[-1])['config'] == line['config']          # the driver's same_config check

@@ -109,16 +109,39 @@ def test_host_draw_schedule_matches_reference_order():
             assert np.array_equal(got, want), name
 
 
-def test_cpulist_parser_and_l2_note():
+def test_cpulist_parser_and_bench_config_dict():
     import bench
     from ogbench_b200 import dist_util
 
     assert dist_util._parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
     assert dist_util._parse_cpulist('') == []
-    small = bench.l2_note(59e6, 32e6)
-    assert 'smaller than L2' in small and 'together larger' in small
-    big = bench.l2_note(537e6, 256e6)
-    assert 'each larger than' in big and 'larger than L2' in big
+    # both arms of bench.py print this dict: a pure function of the workload key and batches_per_launch
+    c2 = bench.config_dict('c2', 1024)
+    assert c2 == bench.config_dict('c2', 1024) and c2['key'] == 'c2' and c2['transitions_per_step_per_gpu'] == 1 << 20
+    assert c2['placement'] == 'replica per GPU' and 'shard' in bench.config_dict('c5', 256)['placement']
+    assert 'L2' in c2['l2']
+
+
+def test_bench_refuses_stale_traffic_capture(tmp_path, monkeypatch):
+    """roofline.traffic comes from the committed ncu capture only while that capture still describes the kernel that ran."""
+    import json
+
+    import bench
+
+    (tmp_path / 'profiles').mkdir()
+    entry = {'kernel': 'void relabel_gather_kernel<0, 0>(FusedParams)', 'dram_bytes_per_launch': 1e9, 'duration_us_under_ncu': 190.0,
+             'transitions_per_launch': 1 << 20}
+    (tmp_path / 'profiles' / 'traffic.json').write_text(json.dumps({'c2': entry}))
+    monkeypatch.setattr(bench, 'ROOT', str(tmp_path))
+    ok, note = bench.committed_traffic('c2', 'relabel_gather_kernel', 0.185, 1 << 20)
+    assert ok == 1e9 and 'under ncu' in note
+    half, _ = bench.committed_traffic('c2', 'relabel_gather_kernel', 0.0925, 1 << 19)      # scaled to the launch size
+    assert half == 5e8
+    stale, why = bench.committed_traffic('c2', 'relabel_gather_kernel', 0.150, 1 << 20)     # the kernel got 21 % faster since
+    assert stale is None and 'stale' in why
+    other, why = bench.committed_traffic('c2', 'gather_rows_async_kernel', 0.185, 1 << 20)
+    assert other is None and 'capture is of' in why
+    assert bench.committed_traffic('c9', 'x', 1.0, 1)[0] is None
 
 
 def test_workload_catalogue_is_consistent():

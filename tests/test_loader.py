@@ -118,3 +118,50 @@ def test_shard_cycler_on_device(tmp_path):
             assert ((ids >= 1000 * shard) & (ids < 1000 * shard + 180)).all(), (i, key)
     cyc.close()
     assert cyc.swaps == 3
+
+
+@pytest.mark.gpu
+def test_shard_cycler_revisits_draw_new_batches(tmp_path):
+    """The reference keeps one np.random stream across shard swaps, so a revisited shard never replays its batches: the
+    cycler carries the Philox counter from sampler to sampler (and no two steps of a run share a counter)."""
+    from tests.golden.make_golden import cfg
+
+    for s in range(2):
+        rng = np.random.default_rng(10 + s)
+        n_ep, T = 5, 40
+        term = np.zeros(n_ep * T, dtype=bool)
+        term[T - 1::T] = True
+        np.savez(str(tmp_path / f'shard{s}.npz'), observations=rng.standard_normal((n_ep * T, 3)).astype(np.float32),
+                 actions=rng.uniform(-1, 1, (n_ep * T, 2)).astype(np.float32), terminals=term)
+    config = cfg()
+    cyc = loader.ShardCycler(loader.list_shards(str(tmp_path)), lambda p: loader.load_gc_dataset(p, config, seed=3), replace_interval=4)
+    visits, counters = {}, []
+    for i in range(1, 17):                       # shards 0,1,0,1 in blocks of four steps (the first block has three)
+        sampler = cyc.at_step(i)
+        counters.append(sampler.state_dict()['counter'])
+        batch = sampler.sample(32)
+        visits.setdefault(cyc.index, []).append(np.asarray(batch['observations']).copy())
+    cyc.close()
+    assert counters == list(range(16))           # one global batch counter for the whole run
+    first, second = visits[0][:3], visits[0][3:6]
+    assert not any(np.array_equal(a, b) for a in first for b in second)
+
+
+def test_shard_cycler_carries_sampler_state():
+    class Fake:
+        def __init__(self, path):
+            self.path, self.counter = path, 0
+
+        def state_dict(self):
+            return {'counter': self.counter}
+
+        def load_state_dict(self, state):
+            self.counter = state['counter']
+
+    cyc = loader.ShardCycler(['a', 'b'], Fake, replace_interval=3, prefetch=False)
+    seen = []
+    for i in range(1, 10):
+        s = cyc.at_step(i)
+        seen.append((s.path, s.counter))
+        s.counter += 1
+    assert seen == [('a', 0), ('a', 1), ('b', 2), ('b', 3), ('b', 4), ('a', 5), ('a', 6), ('a', 7), ('b', 8)]
