@@ -77,6 +77,10 @@ typedef struct {
   int32_t dedup_keys;            /* 1: keys that the reference fills with equal values share one buffer */
   int32_t trl;                   /* config['agent_name'] in (trl, latent_trl, discrete_latent_trl), datasets.py:254-276:
                                     1 = with the valid_idxs override of :198-204, 2 = without it (lost at :211), 0 = off */
+  int32_t jax_compat;            /* 1: the scalar keys are written as float32 (masks, rewards) / int32 (offsets, steps) --
+                                    what `jit` makes of the reference's float64 / int64 numpy arrays with x64 off
+                                    (impls/main.py:204-207) -- so that jax.dlpack.from_dlpack needs no cast */
+  int32_t pad_;
 } ogb_config;
 
 /* Validation mode: the reference's own random draws, in its call order.  Host pointers,
@@ -196,11 +200,15 @@ int ogb_batch_sync(ogb_batch* b);                                 /* host-wait f
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream);/* make a consumer stream wait (DLPack protocol) */
 int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return */
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes); /* one key, D2H, synchronous */
+int ogb_batch_copy_slice_to_host(ogb_batch* b, int32_t i, int64_t batch_index, void* dst, size_t nbytes); /* one batch of one key */
 int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host); /* debug: needs set_debug(1) */
 int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad);           /* debug: needs set_debug(2); bytes written outside every key */
 int ogb_batch_crop_shifts(ogb_batch* b, int64_t* dst_host);       /* debug: [rows,2] applied (cy,cx), -1 if none */
 /* DLPack export of key i (DLManagedTensor*, legacy v0 ABI); the deleter drops one reference on the batch. */
 int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out_dl_managed_tensor);
+/* ... of ONE batch of a multi-batch launch, as [batch, ...]: the i-th `sample(batch_size)` of impls/main.py:202 when the
+ * K calls were drawn ahead in one launch (GCDataset(..., lookahead=K)). */
+int ogb_batch_dlpack_slice(ogb_batch* b, int32_t i, int64_t batch_index, void** out_dl_managed_tensor);
 int ogb_batch_mark_escaped(ogb_batch* b);                         /* a raw device pointer was handed out (e.g. __cuda_array_interface__):
                                                                      the block is recycled only after a device-wide sync */
 int ogb_batch_retain(ogb_batch* b);

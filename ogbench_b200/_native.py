@@ -44,6 +44,7 @@ class Config(C.Structure):
         ('neg_reward_lut', C.POINTER(C.c_double)), ('pow_lut', C.POINTER(C.c_double)),
         ('dedup_keys', C.c_int32),
         ('trl', C.c_int32),
+        ('jax_compat', C.c_int32), ('pad_', C.c_int32),
     ]
 
 
@@ -112,10 +113,12 @@ SIGNATURES = [
     ('ogb_batch_wait_on_stream', C.c_int, [_P, _P]),
     ('ogb_batch_copy_to_host', C.c_int, [_P, _P, C.c_size_t]),
     ('ogb_batch_copy_key_to_host', C.c_int, [_P, C.c_int32, _P, C.c_size_t]),
+    ('ogb_batch_copy_slice_to_host', C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_size_t]),
     ('ogb_batch_check_gaps', C.c_int, [_P, _P]),
     ('ogb_batch_index_vector', C.c_int, [_P, C.c_int32, _P]),
     ('ogb_batch_crop_shifts', C.c_int, [_P, _P]),
     ('ogb_batch_dlpack', C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    ('ogb_batch_dlpack_slice', C.c_int, [_P, C.c_int32, C.c_int64, C.POINTER(_P)]),
     ('ogb_batch_mark_escaped', C.c_int, [_P]),
     ('ogb_batch_retain', C.c_int, [_P]),
     ('ogb_batch_release', C.c_int, [_P]),

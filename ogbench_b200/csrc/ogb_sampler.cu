@@ -46,7 +46,7 @@ struct AbSwitches {
   int stage_bytes;       // OGB_STAGE_BYTES=n   per-warp stage budget instead of 4096 / 6144
   int ws;                // OGB_WS=0|1          warp-specialised fused kernel off / on (-1: ogb_sampler_set_debug decides)
   bool timeline;         // OGB_TIMELINE        record an event per phase for ogb_debug_timeline
-  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (308 built in; 216, 316, 220: one CTA per SM)
+  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (308 built in; 208; 216, 316, 220: one CTA per SM)
   bool no_shadow;        // OGB_NO_SHADOW       no shadow copy of the next row's observation inside the records
 };
 
@@ -673,9 +673,9 @@ struct PlanBuilder {
     k.name = name;
     k.route = ROUTE_SCALAR;
     k.scalar = sc;
-    k.dtype = dtype;
+    k.dtype = cfg->jax_compat ? (dtype == OGB_F64 ? OGB_F32 : OGB_I32) : dtype;   // what jit narrows them to with x64 off
     k.ndim_tail = 0;
-    k.row_bytes = 8;
+    k.row_bytes = cfg->jax_compat ? 4 : 8;
     push(std::move(k));
   }
   void base_keys() {  // datasets.py:78-83 (+ :229-231)
@@ -1500,6 +1500,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   p.batch_magic = batch_size > 1 && batch_size < ((int64_t)1 << 32) ? (uint64_t)(~(uint64_t)0 / (uint64_t)batch_size) + 1 : 0;
   p.total_rows = total;
   p.n_slots = spec.n_slots;
+  p.narrow = cfg.jax_compat ? 1 : 0;
   p.vec_rows = b->vec_rows;
   p.vec_init = b->vec_init;
   p.crop_out = b->crop;
@@ -1769,7 +1770,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     // (stages, warps per CTA): 3 x 8 built in; the alternatives are compiled for the GCDataset fused launch and the
     // un-fused gather only (OGB_GATHER_SHAPE, measurement switch)
     int shape = ab().gather_shape;
-    if (shape != 216 && shape != 316 && shape != 220) shape = 308;
+    if (shape != 208 && shape != 216 && shape != 316 && shape != 220) shape = 308;
     if (shape != 308 && fuse && q0 == 0 && (p.kind != OGB_KIND_GC || draws != nullptr)) shape = 308;
     const int n_stages = shape / 100, n_warps = shape % 100;
     ap.ring_bytes = n_stages * ap.stage_bytes;
@@ -1860,7 +1861,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         else if (inject) { OGB_PICK_FUSED(relabel_gather_kernel, true); }
         else { OGB_PICK_FUSED(relabel_gather_kernel, false); }
 #undef OGB_PICK_FUSED
-        if (shape == 216) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 16>;
+        if (shape == 208) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 8>;
+        else if (shape == 216) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 16>;
         else if (shape == 316) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 3, 16>;
         else if (shape == 220) fn = (const void*)relabel_gather_kernel<false, FLAVOUR_GC, 2, 20>;
         const size_t smem_bytes = ws ? ws_smem : smem;
@@ -1875,7 +1877,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       };
       continue;
     }
-    const void* gather_fn = shape == 216 ? (const void*)gather_rows_async_kernel<2, 16>
+    const void* gather_fn = shape == 208 ? (const void*)gather_rows_async_kernel<2, 8>
+                          : shape == 216 ? (const void*)gather_rows_async_kernel<2, 16>
                           : shape == 316 ? (const void*)gather_rows_async_kernel<3, 16>
                           : shape == 220 ? (const void*)gather_rows_async_kernel<2, 20>
                                          : (const void*)gather_rows_async_kernel<kAsyncStages, kAsyncWarps>;
@@ -2513,6 +2516,18 @@ int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes
   OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
   return 0;
 } OGB_CATCH_ALL
+// one batch of a multi-batch launch (see ogb_batch_dlpack_slice), D2H, synchronous
+int ogb_batch_copy_slice_to_host(ogb_batch* b, int32_t i, int64_t batch_index, void* dst, size_t nbytes) try {
+  if (!b || !dst || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad argument");
+  if (batch_index < 0 || batch_index >= b->n_batches) return fail(OGB_ERR_INDEX, "batch %lld of %d", (long long)batch_index, b->n_batches);
+  const size_t need = (size_t)b->batch * b->keys[(size_t)i].row_bytes;
+  if (nbytes < need) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, need);
+  DeviceGuard device_guard(b->sampler->ds->device);
+  OGB_CUDA(device_guard.status);
+  OGB_CUDA(cudaMemcpyAsync(dst, b->block + b->offsets[(size_t)i] + (size_t)batch_index * need, need, cudaMemcpyDeviceToHost, b->sampler->stream));
+  OGB_CUDA(cudaStreamSynchronize(b->sampler->stream));
+  return 0;
+} OGB_CATCH_ALL
 // debug (ogb_sampler_set_debug(s, 2)): bytes of the key area that belong to no key must still hold the 0xA5 fill
 int ogb_batch_check_gaps(ogb_batch* b, int64_t* n_bad) try {
   if (!b || !n_bad) return fail(OGB_ERR_INVALID, "null argument");
@@ -2591,6 +2606,24 @@ int ogb_batch_dlpack(ogb_batch* b, int32_t i, void** out) try {
   t->manager_ctx = b;
   t->deleter = dl_deleter;
   b->refs.fetch_add(1);
+  *out = t;
+  return 0;
+} OGB_CATCH_ALL
+// One batch of a multi-batch launch as a tensor of its own ([batch, ...], the leading axis dropped): what a look-ahead
+// sampler hands out for the i-th of K batches it drew in one launch.  Same ownership as ogb_batch_dlpack.
+int ogb_batch_dlpack_slice(ogb_batch* b, int32_t i, int64_t batch_index, void** out) try {
+  if (!b || !out || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad key index");
+  if (batch_index < 0 || batch_index >= b->n_batches) return fail(OGB_ERR_INDEX, "batch %lld of %d", (long long)batch_index, b->n_batches);
+  void* whole = nullptr;
+  OGB_TRY(ogb_batch_dlpack(b, i, &whole));
+  DLManagedTensor_* t = (DLManagedTensor_*)whole;
+  const KeyPlan& k = b->keys[(size_t)i];
+  const bool has_axis = b->n_batches > 1 || b->keep_axis;
+  if (has_axis) {
+    for (int d = 1; d < t->dl_tensor.ndim; ++d) t->dl_tensor.shape[d - 1] = t->dl_tensor.shape[d];
+    t->dl_tensor.ndim -= 1;
+  }
+  t->dl_tensor.data = (uint8_t*)t->dl_tensor.data + (size_t)batch_index * (size_t)b->batch * k.row_bytes;
   *out = t;
   return 0;
 } OGB_CATCH_ALL

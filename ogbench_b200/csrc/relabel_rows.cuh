@@ -155,8 +155,8 @@ struct RelabelParams {
   int64_t total_rows;          // batch * n_batches (also the stride of the [slot][row] index vectors)
   int64_t row_begin, row_end;  // rows this launch handles
   int32_t n_slots;
-  int32_t pad0_;
-  // ---- scalar outputs (float64 / int64 like the reference) ----
+  int32_t narrow;              // jax_compat: the scalar outputs below are float32 / int32 arrays
+  // ---- scalar outputs (float64 / int64 like the reference; float32 / int32 when `narrow`) ----
   double* masks;
   double* rewards;
   int64_t* hv_offsets;
@@ -180,6 +180,15 @@ struct RelabelParams {
   TinyGroup tiny_groups[kMaxTinyGroups];
   TinyField tiny_fields[kMaxTinyFields];
 };
+
+// scalar keys: float64 / int64 as the reference returns them, or -- jax_compat -- the float32 / int32 that `jit` narrows
+// them to with x64 off ((float)double rounds to nearest even like numpy's astype; the integers are far below 2^31)
+__device__ __forceinline__ void put_f64(const RelabelParams& p, double* base, const int64_t g, const double v) {
+  if (p.narrow) reinterpret_cast<float*>(base)[g] = (float)v; else base[g] = v;
+}
+__device__ __forceinline__ void put_i64(const RelabelParams& p, int64_t* base, const int64_t g, const int64_t v) {
+  if (p.narrow) reinterpret_cast<int32_t*>(base)[g] = (int32_t)v; else base[g] = v;
+}
 
 // word `i` (0..7) of the eight words held in two uint4
 __device__ __forceinline__ uint32_t select_word(const uint4& a, const uint4& b, const uint32_t i) {
@@ -379,8 +388,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     const int32_t ag = kInject ? pick_goal_injected<kSmemTables>(p, seg, 2, i, fin, g)                   // :240-246 / :585-591
                                : pick_goal_philox<kSmemTables>(p, seg, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
     const double succ = (i == vg) ? 1.0 : 0.0;                         // :250-252 / :579-582
-    p.masks[g] = 1.0 - succ;
-    p.rewards[g] = succ - neg;
+    put_f64(p, p.masks, g, 1.0 - succ);
+    put_f64(p, p.rewards, g, succ - neg);
     if (kFlavour == FLAVOUR_GC) {
       put_slot(p, sr, GC_VALUE_GOAL, g, vg);
       put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
@@ -395,8 +404,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
         }
         put_slot(p, sr, GC_TRL_MID, g, mid);
         put_slot(p, sr, GC_TRL_PLUS1, g, i + 1);
-        p.trl_offsets[g] = (int64_t)vg - i;
-        p.trl_mid_offsets[g] = (int64_t)mid - i;
+        put_i64(p, p.trl_offsets, g, (int64_t)vg - i);
+        put_i64(p, p.trl_mid_offsets, g, (int64_t)mid - i);
       }
     } else {
       const int32_t hv = vg;
@@ -406,13 +415,13 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
       put_slot(p, sr, HGC_HV_GOAL, g, hv);
       put_slot(p, sr, HGC_HV_NEXT, g, hv_next);
       put_slot(p, sr, HGC_LV_NEXT, g, lv_next);
-      p.hv_offsets[g] = (int64_t)hv - (int64_t)i;                                   // :531
-      p.hv_steps[g] = hv_s;
-      p.lv_steps[g] = lv_s;
+      put_i64(p, p.hv_offsets, g, (int64_t)hv - (int64_t)i);                                   // :531
+      put_i64(p, p.hv_steps, g, hv_s);
+      put_i64(p, p.lv_steps, g, lv_s);
       const double hv_succ = hv_s < p.k_val ? 1.0 : 0.0;                            // :533
       const double lv_succ = lv_s < p.k_lo ? 1.0 : 0.0;                             // :552
-      p.hv_masks[g] = 1.0 - hv_succ;
-      p.hv_rewards[g] = p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ);
+      put_f64(p, p.hv_masks, g, 1.0 - hv_succ);
+      put_f64(p, p.hv_rewards, g, p.gc_negative ? __ldg(p.neg_lut + hv_s) : __dmul_rn(__ldg(p.pow_lut + hv_s), hv_succ));
       double lv_mask = 1.0 - lv_succ;
       double lv_rew = p.gc_negative ? __ldg(p.neg_lut + lv_s) : __dmul_rn(__ldg(p.pow_lut + lv_s), lv_succ);
       if (p.has_low_goal) {                                                         // :563-576
@@ -428,8 +437,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
         lv_mask = 1.0 - s;
         lv_rew = s - neg;
       }
-      p.lv_masks[g] = lv_mask;
-      p.lv_rewards[g] = lv_rew;
+      put_f64(p, p.lv_masks, g, lv_mask);
+      put_f64(p, p.lv_rewards, g, lv_rew);
       const int32_t ha = ag;
       int32_t ha_next, la_next, unused;
       subgoal_step(i, fin, ha, p.k_act, ha_next, unused);                           // :595-600

@@ -331,7 +331,7 @@ class _Sampler:
     """Thin owner of an ogb_sampler handle; builds the C config from the reference's config mapping."""
 
     def __init__(self, dataset: Dataset, config, kind: int, device: int = 0, seed: int = 0, stream_id: int = 0,
-                 dedup: bool = True, output: str = 'device', crop_padding: int = 3):
+                 dedup: bool = True, output: str = 'device', crop_padding: int = 3, jax_compat: bool = False):
         assert output in ('device', 'numpy')
         self.dataset = dataset
         self.kind = kind
@@ -340,6 +340,7 @@ class _Sampler:
         self._keepalive = []
         cfg = _native.Config()
         cfg.dedup_keys = int(dedup)
+        cfg.jax_compat = int(bool(jax_compat))
         cfg.crop_padding = crop_padding  # 3 in GCDataset.augment (datasets.py:331); ATC: config['augment_padding'] (:440)
         if kind == _native.KIND_ATC:
             p_aug = config['p_aug']
@@ -589,6 +590,33 @@ def _crop_array(arr, crop_froms, padding, device, output):
     return next(iter(sampler.wrap(BatchHandle(out, device, None)).values()))
 
 
+class _Lookahead:
+    """K successive sample(batch) calls drawn in ONE launch and handed out one at a time (GCDataset(..., lookahead=K)).
+
+    The Philox draws of a launch of K batches are those of K single launches (counter = batch index), so the sequence of
+    batches is exactly the one direct sample() calls return (tests/test_gpu_lookahead.py)."""
+
+    __slots__ = ('counter0', 'n', 'pos', 'batch', 'evaluation', 'handle', 'keys', 'host')
+
+    def __init__(self, counter0, n, batch, evaluation, many):
+        self.counter0, self.n, self.pos, self.batch, self.evaluation = counter0, n, 0, batch, evaluation
+        first = next(iter(many.values()))
+        if isinstance(first, DeviceArray):
+            self.handle, self.host = first._batch, None
+            # (name, key index, dtype, shape of one batch, device address of batch 0, bytes per batch)
+            self.keys = [(k, v._index, v.dtype, v.shape[1:], v.ptr, v.nbytes // n) for k, v in many.items()]
+        else:
+            self.handle, self.keys, self.host = None, None, many
+
+    def take(self):
+        i = self.pos
+        self.pos = i + 1
+        if self.host is not None:
+            return {k: v[i] for k, v in self.host.items()}       # views into the pinned block of the whole launch
+        handle = self.handle
+        return {k: DeviceArray(handle, idx, k, dtype, shape, ptr + i * step, step, i) for k, idx, dtype, shape, ptr, step in self.keys}
+
+
 class GCDataset:
     """Dataset class for goal-conditioned RL, device-resident (reference: datasets.py:149-366).
 
@@ -600,12 +628,22 @@ class GCDataset:
     (seed, stream_id, batch counter).  rng='numpy': the global np.random stream is consumed with exactly the
     reference's calls and the device computes the batch from those draws -- bit-identical to the reference for the
     same np.random.seed.
+
+    lookahead=K (rng='philox'): the unchanged training loop of impls/main.py:202 -- one `sample(batch_size)` per step --
+    gets the amortised rate of K-batch launches: the first call draws K batches in one launch and every call pops the
+    next one; the sequence of batches is the one K = 0 returns.  Calls with `idxs`, `draws`, `sample_many`,
+    `sample_goals` and `load_state_dict` settle the look-ahead first (the batch counter is put back to the number of
+    batches actually handed out), so mixing them in keeps the sequence too.
+
+    jax_compat=True: masks / rewards come out as float32 and offsets / steps as int32 -- what `jit` makes of the
+    reference's float64 / int64 arrays with JAX's default x64-off -- so `jax.dlpack.from_dlpack` needs no cast.
     """
 
     _KIND = _native.KIND_GC
 
     def __init__(self, dataset: Dataset, config: Any, preprocess_frame_stack: bool = True, *, device: int = 0,
-                 seed: int = 0, stream_id: int = 0, rng: str = 'philox', output: str = 'device', dedup: bool = True):
+                 seed: int = 0, stream_id: int = 0, rng: str = 'philox', output: str = 'device', dedup: bool = True,
+                 lookahead: int = 0, jax_compat: bool = False):
         if not isinstance(dataset, Dataset):
             dataset = Dataset.create(freeze=False, **dataset)
         assert rng in ('philox', 'numpy')
@@ -614,6 +652,8 @@ class GCDataset:
         self.preprocess_frame_stack = preprocess_frame_stack
         self.rng = rng
         self.size = dataset.size
+        self.lookahead = int(lookahead)
+        self._ahead = None
         # datasets.py:191-196 (checked before touching the device, like the reference's __post_init__)
         assert np.isclose(config['value_p_curgoal'] + config['value_p_trajgoal'] + config['value_p_randomgoal'], 1.0)
         assert np.isclose(config['actor_p_curgoal'] + config['actor_p_trajgoal'] + config['actor_p_randomgoal'], 1.0)
@@ -624,9 +664,10 @@ class GCDataset:
             if config['value_p_curgoal'] != 0.0 or config['value_p_randomgoal'] != 0.0:
                 raise NotImplementedError('TRL sampling needs value_p_curgoal == value_p_randomgoal == 0 (datasets.py:257)')
         self._sampler = _Sampler(dataset, config, self._KIND, device=device, seed=seed, stream_id=stream_id,
-                                 dedup=dedup, output=output)
+                                 dedup=dedup, output=output, jax_compat=jax_compat)
         self.terminal_locs, self.initial_locs = self._sampler.bounds()
         self._n_choices = self._sampler.num_choices()  # len(valid_idxs); every non-terminal row for TRL (:198-204)
+        self._trl_rows = None
 
     # ---- the reference's draw order, host side (rng='numpy') ----
     def _goal_sets(self):
@@ -634,20 +675,38 @@ class GCDataset:
         return [(cfg['value_geom_sample'], cfg['discount'], cfg['value_p_curgoal']),
                 (cfg['actor_geom_sample'], cfg['discount'], cfg['actor_p_curgoal'])]
 
-    def _host_draws(self, batch_size, idxs, evaluation) -> _HostDraws:
+    def _trl_valid_rows(self):
+        """valid_idxs of the TRL agents: every row that is not a terminal row (datasets.py:198-204)."""
+        if self._trl_rows is None:
+            keep = np.ones(self.size, dtype=bool)
+            keep[self.terminal_locs] = False
+            (self._trl_rows,) = np.nonzero(keep)
+        return self._trl_rows
+
+    def _host_draws(self, batch_size, idxs, evaluation):
+        """The reference's np.random calls of one sample(), in its order; returns (draws, idxs)."""
         d = _HostDraws()
         if idxs is None:
             d.idx_pos = np.random.randint(self._n_choices, size=batch_size)      # datasets.py:226 -> :68/:70
         for geom, discount, p_cur in self._goal_sets():
             d.goal(self._n_choices, batch_size, geom, discount, p_cur)
         if self._trl:
-            # :259 randint(idxs, value_goal_idxs) needs the goal rows themselves, which only exist on the device
-            raise NotImplementedError("rng='numpy' is not available for TRL samplers; pass recorded draws instead")
+            # :259 draws randint(idxs, value_goal_idxs): the goal rows come from the device (phase one: the value goals of
+            # these very draws), the midpoint draw is made here, and the launch then replays everything (phase two)
+            rows = np.ascontiguousarray(idxs, dtype=np.int64) if idxs is not None else self._trl_valid_rows()[d.idx_pos]
+            cfg = self.config
+            goals = self._goals_native(rows, cfg['value_p_curgoal'], cfg['value_p_trajgoal'], cfg['value_geom_sample'],
+                                       cfg['discount'], d.goals[0])
+            final = self.terminal_locs[np.searchsorted(self.terminal_locs, rows)]
+            assert (rows != final).all()                                         # :256
+            assert (rows != goals).all()                                         # :257
+            d.trl_midpoints = np.random.randint(rows, goals)                     # :259
+            d.idx_pos, idxs = None, rows
         if self.config['p_aug'] is not None and not evaluation:                  # :278-279 / :621-622
             d.aug_coin = np.random.rand()
             if d.aug_coin < self.config['p_aug']:
                 d.crop = np.random.randint(0, 2 * 3 + 1, (batch_size, 2))        # :333
-        return d
+        return d, idxs
 
     def sample(self, batch_size, idxs=None, evaluation=False, *, draws=None):
         """Sample a batch of transitions with goals (datasets.py:213-294).
@@ -657,13 +716,34 @@ class GCDataset:
         """
         if idxs is not None:
             batch_size = len(idxs)
+        elif draws is None and self.lookahead > 1 and self.rng == 'philox':
+            return self._sample_ahead(int(batch_size), bool(evaluation))
+        self._settle()
         if draws is None and self.rng == 'numpy':
-            draws = self._host_draws(batch_size, idxs, evaluation)
+            draws, idxs = self._host_draws(batch_size, idxs, evaluation)
         return self._sampler.sample(batch_size, idxs, evaluation, draws)
+
+    # ---- look-ahead: K batches per launch behind the reference's one-call-per-step loop (impls/main.py:202) ----
+    def _sample_ahead(self, batch_size, evaluation):
+        la = self._ahead
+        if la is None or la.pos == la.n or la.batch != batch_size or la.evaluation != evaluation:
+            self._settle()
+            counter0 = self._sampler.counter
+            many = self._sampler.sample(batch_size, None, evaluation, None, n_batches=self.lookahead, keep_axis=True)
+            la = self._ahead = _Lookahead(counter0, self.lookahead, batch_size, evaluation, many)
+        return la.take()
+
+    def _settle(self):
+        """Drop the batches drawn ahead but not handed out: the batch counter goes back to the number of batches the caller
+        has actually received, so whatever is drawn next continues the sequence direct calls would have produced."""
+        la, self._ahead = self._ahead, None
+        if la is not None and la.pos < la.n:
+            self._sampler.counter = la.counter0 + la.pos
 
     def sample_many(self, num_batches, batch_size, evaluation=False, idxs=None):
         """`num_batches` successive sample(batch_size) calls in one launch; every key gains a leading axis of that length.
         `idxs` (optional, num_batches * batch_size rows) plays the role of sample()'s `idxs`."""
+        self._settle()
         return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches, keep_axis=True)
 
     # ---- reference helpers that other scripts call (impls/pretrain_atc.py:195, pretrain_vae.py:162) ----
@@ -685,24 +765,31 @@ class GCDataset:
 
         rng='numpy' makes the reference's own np.random calls (randint, geometric or rand, rand, rand) and the device
         computes the goals from them; rng='philox' draws on the device."""
+        self._settle()
         idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64).reshape(-1)
-        n = len(idxs)
         if discount is None:
             discount = self.config['discount']
-        c_draws, keep = None, []
+        goal_draws = None
         if self.rng == 'numpy':
             d = _HostDraws()
-            d.goal(self._n_choices, n, geom_sample, discount, p_curgoal)
-            g = d.goals[0]
+            d.goal(self._n_choices, len(idxs), geom_sample, discount, p_curgoal)
+            goal_draws = d.goals[0]
+        return self._goals_native(idxs, p_curgoal, p_trajgoal, geom_sample, discount, goal_draws)
+
+    def _goals_native(self, idxs, p_curgoal, p_trajgoal, geom_sample, discount, goal_draws):
+        """Goal rows for `idxs` from the given draws (None: drawn on the device), as int64 on the host."""
+        n = len(idxs)
+        c_draws, keep = None, []
+        if goal_draws is not None:
             c_draws = _native.GoalDraws()
             for name, dtype in (('rand_pos', np.int64), ('offset', np.int64), ('dist', np.float64), ('u_traj', np.float64), ('u_cur', np.float64)):
-                arr = getattr(g, name)
+                arr = getattr(goal_draws, name)
                 if arr is not None:
                     arr = np.ascontiguousarray(arr, dtype=dtype)
                     keep.append(arr)
                     setattr(c_draws, name, arr.ctypes.data)
         out = np.empty(n, dtype=np.int64)
-        if n == 0:      # (the np.random calls above were still made, with size 0, like the reference's)
+        if n == 0:      # (the np.random calls were still made, with size 0, like the reference's)
             return out
         _native.check(_native.lib().ogb_sampler_sample_goals(
             self._sampler.ptr, idxs.ctypes.data_as(C.c_void_p), n, float(p_curgoal), float(p_trajgoal), int(bool(geom_sample)),
@@ -721,9 +808,12 @@ class GCDataset:
 
     # ---- checkpointable sampler state: one integer ----
     def state_dict(self):
-        return {'counter': self._sampler.counter}
+        """The number of batches handed out so far (batches drawn ahead and not yet handed out do not count)."""
+        la = self._ahead
+        return {'counter': la.counter0 + la.pos if la is not None else self._sampler.counter}
 
     def load_state_dict(self, state):
+        self._ahead = None
         self._sampler.counter = state['counter']
 
 

@@ -69,9 +69,9 @@ class BatchHandle:
 class DeviceArray:
     """One key of a batch, resident in HBM."""
 
-    __slots__ = ('_batch', '_index', 'shape', 'dtype', 'ptr', 'nbytes', 'name')
+    __slots__ = ('_batch', '_index', 'shape', 'dtype', 'ptr', 'nbytes', 'name', '_slice')
 
-    def __init__(self, batch: BatchHandle, index: int, name: str, dtype, shape, ptr: int, nbytes: int):
+    def __init__(self, batch: BatchHandle, index: int, name: str, dtype, shape, ptr: int, nbytes: int, batch_index: int = -1):
         self._batch = batch
         self._index = index
         self.shape = shape
@@ -79,6 +79,7 @@ class DeviceArray:
         self.ptr = ptr
         self.nbytes = nbytes
         self.name = name
+        self._slice = batch_index      # >= 0: this array is ONE batch of a multi-batch launch (look-ahead sampling)
 
     # ---- array-ish surface ----
     @property
@@ -105,7 +106,10 @@ class DeviceArray:
             handle = {None: 1, 1: 1, 2: 2}.get(stream, stream)  # legacy default / per-thread default / explicit handle
             _native.check(lib.ogb_batch_wait_on_stream(self._batch.ptr, C.c_void_p(handle)))
         out = C.c_void_p()
-        _native.check(lib.ogb_batch_dlpack(self._batch.ptr, self._index, C.byref(out)))
+        if self._slice >= 0:
+            _native.check(lib.ogb_batch_dlpack_slice(self._batch.ptr, self._index, self._slice, C.byref(out)))
+        else:
+            _native.check(lib.ogb_batch_dlpack(self._batch.ptr, self._index, C.byref(out)))
         return _PyCapsule_New(out, b'dltensor', C.cast(_capsule_destructor, C.c_void_p))
 
     @property
@@ -117,8 +121,12 @@ class DeviceArray:
     def numpy(self) -> np.ndarray:
         """Synchronous device->host copy of this key."""
         out = np.empty(self.shape, dtype=self.dtype)
-        _native.check(_native.lib().ogb_batch_copy_key_to_host(self._batch.ptr, self._index, out.ctypes.data_as(C.c_void_p),
-                                                               out.nbytes))
+        if self._slice >= 0:
+            _native.check(_native.lib().ogb_batch_copy_slice_to_host(self._batch.ptr, self._index, self._slice,
+                                                                     out.ctypes.data_as(C.c_void_p), out.nbytes))
+        else:
+            _native.check(_native.lib().ogb_batch_copy_key_to_host(self._batch.ptr, self._index, out.ctypes.data_as(C.c_void_p),
+                                                                   out.nbytes))
         return out
 
     def __array__(self, dtype=None, copy=None):

@@ -16,6 +16,15 @@ for key in [a for a in sys.argv[1:] if not a.startswith('--')] or ['c2']:
         for _ in range(N): b = s.sample(w.batch)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / N
         print(f'{key} output={output}: {dt*1e6:.1f} us per sample({w.batch}) through the public API ({len(b)} keys)')
+        for K in (64, 1024):                       # the same unchanged loop with batches drawn K at a time behind sample()
+            la = cls(ds, w.config, output=output, lookahead=K)
+            n_la = 4 * K if output == 'device' else K + 8
+            for _ in range(K + 2): b = la.sample(w.batch)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(n_la): b = la.sample(w.batch)
+            torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n_la
+            print(f'{key} output={output} lookahead={K}: {dt*1e6:.2f} us per sample({w.batch}) amortised over {n_la} calls')
+            del la, b
         from ogbench_b200 import Prefetcher
         with Prefetcher(s, w.batch) as batches:
             next(batches); waited = 0.0

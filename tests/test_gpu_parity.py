@@ -20,10 +20,11 @@ def test_validation_mode_matches_golden(name):
     assert_batches_identical(to_host(got), case['out'], label=name + ':')
 
 
-@pytest.mark.parametrize('name', [n for n in CASES if not n.startswith('trl_')])
+@pytest.mark.parametrize('name', list(CASES))
 def test_numpy_rng_mode_matches_golden(name):
     """rng='numpy': same np.random.seed as the reference run -> same batch, with no recording in between.
-    (TRL draws a midpoint between idx and the goal row, which only exists on the device: recorded draws only.)"""
+    (TRL agents included: their midpoint draw randint(idxs, value_goal_idxs), datasets.py:259, is made on the host
+    between two device phases.)"""
     case = load_case(name)
     sampler = device_sampler(case['fields'], case['cfg'], case['kind'], rng='numpy', output='numpy')
     np.random.seed(case['meta']['seed'])
