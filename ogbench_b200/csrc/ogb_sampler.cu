@@ -46,8 +46,10 @@ struct AbSwitches {
   int stage_bytes;       // OGB_STAGE_BYTES=n   per-warp stage budget instead of 4096 / 6144
   int ws;                // OGB_WS=0|1          warp-specialised fused kernel off / on (-1: ogb_sampler_set_debug decides)
   bool timeline;         // OGB_TIMELINE        record an event per phase for ogb_debug_timeline
-  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (308 built in; 208; 216, 316, 220: one CTA per SM)
+  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (default: 216 for the fused GCDataset launch, 308 otherwise; also 208, 316, 220)
   bool no_shadow;        // OGB_NO_SHADOW       no shadow copy of the next row's observation inside the records
+  int index_grid;        // OGB_INDEX_GRID=n    index kernel grid capped at n CTAs per SM instead of 16
+  bool no_point;         // OGB_NO_POINT        point-maze records go through the generic tiny-field walk of the index kernel
 };
 
 const AbSwitches& ab() {
@@ -72,6 +74,8 @@ const AbSwitches& ab() {
     a.timeline = flag("OGB_TIMELINE");
     a.gather_shape = number("OGB_GATHER_SHAPE", 0);
     a.no_shadow = flag("OGB_NO_SHADOW");
+    a.index_grid = number("OGB_INDEX_GRID", 0);
+    a.no_point = flag("OGB_NO_POINT");
     return a;
   }();
   return sw;
@@ -1679,6 +1683,17 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   }
   const bool any_async = !span_jobs.empty();
   fuse = fuse && any_async;
+  // The point-maze record (relabel_row<..., kPoint>): one group of the transition's own 32-byte record holding
+  // observations f32[2] | actions f32[2] | terminals | valids | shadow next observation, and the two 8-byte goal rows;
+  // nothing else to gather.  The index kernel then runs with these copies compiled in.
+  bool point_record = !ab().no_point && spec.kind == OGB_KIND_GC && !spec.trl && !any_async && lsu_keys.empty() && !any_frames &&
+                      p.n_tiny_groups == 1 && p.n_tiny_fields == 5 && p.n_tiny == 2 && p.n_tiny_fast == 2 &&
+                      p.tiny_groups[0].slot == SLOT_IDX && p.tiny_groups[0].n_vec == 2 &&
+                      p.tiny[0].slot == GC_VALUE_GOAL && p.tiny[0].row_bytes == 8 && p.tiny[1].slot == GC_ACTOR_GOAL && p.tiny[1].row_bytes == 8;
+  if (point_record) {
+    static const int kWord[5] = {0, 2, 4, 5, 6}, kCount[5] = {2, 2, 1, 1, 2};
+    for (int f = 0; f < 5; ++f) point_record = point_record && p.tiny_fields[f].word == kWord[f] && p.tiny_fields[f].n_words == kCount[f];
+  }
   // the index vectors only go to memory when a later launch (or the debug interface) reads them
   p.write_vecs = ((!fuse && any_async) || span_jobs.size() > (size_t)kMaxRowJobs || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
 
@@ -1712,7 +1727,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     else if (smem_tables) { OGB_PICK_INDEX_KERNEL(false, true); }
     else { OGB_PICK_INDEX_KERNEL(false, false); }
 #undef OGB_PICK_INDEX_KERNEL
-    int64_t grid_cap = (int64_t)ds->sm_count * 16;
+    if (point_record && !smem_tables)
+      fn = inject ? (const void*)relabel_index_kernel<true, FLAVOUR_GC, false, true> : (const void*)relabel_index_kernel<false, FLAVOUR_GC, false, true>;
+    int64_t grid_cap = (int64_t)ds->sm_count * (ab().index_grid > 0 ? ab().index_grid : 16);
     size_t smem = 0;
     if (smem_tables) {
       smem = table_bytes;
@@ -1769,9 +1786,14 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     ap.stage_bytes = (int)round_up(stage, 128);
     // (stages, warps per CTA): 3 x 8 built in; the alternatives are compiled for the GCDataset fused launch and the
     // un-fused gather only (OGB_GATHER_SHAPE, measurement switch)
+    // Measured on B200 (profiles/r2_ab_shapes.txt): the fused GCDataset launch runs 4 % (C2) / 2 % (C5) faster as ONE CTA of
+    // 16 warps with two stages per warp (128 KB of shared memory, the rest of the SM's 228 KB stays L1 for the index
+    // algebra's table lookups) than as two CTAs of 8 warps with three stages; the un-fused gather (C3, 6 KB stages) is
+    // 3-6 % faster with three stages.  So: fused GC Philox launches 2 x 16, everything else 3 x 8.
     int shape = ab().gather_shape;
-    if (shape != 208 && shape != 216 && shape != 316 && shape != 220) shape = 308;
-    if (shape != 308 && fuse && q0 == 0 && (p.kind != OGB_KIND_GC || draws != nullptr)) shape = 308;
+    const bool fused_gc = fuse && q0 == 0 && p.kind == OGB_KIND_GC && draws == nullptr;
+    if (shape != 308 && shape != 208 && shape != 216 && shape != 316 && shape != 220) shape = fused_gc ? 216 : 308;
+    if (shape != 308 && fuse && q0 == 0 && !fused_gc) shape = 308;
     const int n_stages = shape / 100, n_warps = shape % 100;
     ap.ring_bytes = n_stages * ap.stage_bytes;
     for (; q < q1; ++q) {
@@ -1827,7 +1849,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     ap.ring_offset = (int)round_up((size_t)ap.n_items * sizeof(ItemDesc) + (size_t)ap.n_outs * sizeof(OutDesc), 128);
     const size_t smem = (size_t)ap.ring_offset + (size_t)n_warps * ap.ring_bytes;
     if (smem > (size_t)225 * 1024) return bail(fail(OGB_ERR_UNSUPPORTED, "gather shape %d needs %zu bytes of shared memory", shape, smem));
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(n_warps <= 8 ? 8 : 1, (size_t)(220 * 1024) / smem));
+    // persistent grid: exactly the CTAs that are resident at once (shared memory bounds them here; the fused kernels are
+    // compiled for gather_min_blocks(warps) CTAs per SM, so registers allow at least that many)
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(n_warps <= 8 ? 2 : 1, (size_t)(220 * 1024) / smem));
     if (fuse && q0 == 0) {
       // index algebra + the first (normally the only) group of row jobs in ONE launch
       FusedParams* fp = new FusedParams();
@@ -1883,11 +1907,14 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
                           : shape == 220 ? (const void*)gather_rows_async_kernel<2, 20>
                                          : (const void*)gather_rows_async_kernel<kAsyncStages, kAsyncWarps>;
     OGB_CUDA(cudaFuncSetAttribute(gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int resident = 0;   // CTAs of this kernel that fit one SM (registers and shared memory): the persistent grid is exactly that
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, gather_fn, n_warps * 32, smem) != cudaSuccess || resident < 1)
+      return bail(fail(OGB_ERR_CUDA, "gather_rows_async_kernel: occupancy query failed (%zu bytes of shared memory)", smem));
     gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
       ap.row_begin = begin;
       ap.row_end = end;
       const int64_t n_warp_tiles = (end - begin + 31) / 32;
-      const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * ctas_per_sm);
+      const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * resident);
       void* args[] = {(void*)&ap};
       if (cudaLaunchKernel(gather_fn, dim3(grid), dim3((unsigned)n_warps * 32), args, smem, st) != cudaSuccess)
         return fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -2499,10 +2526,15 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
     if (chunk_flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
     return 0;
   }
-  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->stream));
+  // The copy runs on a stream of its own behind the batch's `ready` event, not on the sampler's stream: a caller that has
+  // already launched the NEXT batch (Prefetcher: launch k+1, then copy k) gets that launch's upload and kernels under
+  // this copy instead of behind it.
+  if (!s->copy_stream) OGB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  OGB_CUDA(cudaStreamWaitEvent(s->copy_stream, b->ready, 0));
+  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
   int32_t flag = 0;
-  if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->stream));
-  OGB_CUDA(cudaStreamSynchronize(s->stream));
+  if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
+  OGB_CUDA(cudaStreamSynchronize(s->copy_stream));
   if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
   return 0;
 } OGB_CATCH_ALL

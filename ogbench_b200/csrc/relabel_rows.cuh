@@ -324,7 +324,12 @@ __device__ __forceinline__ void split_row(const RelabelParams& p, const int64_t 
 
 // All per-row work of sample(): index draws, goal relabelling, rewards/masks, the rows of <= 16 bytes, crop shifts.
 // On return sr[] holds the dataset row of every slot for batch row g.
-template <bool kInject, int kFlavour, bool kSmemTables = false>
+// kPoint: the copies of the point-maze record are compiled in (see the host's point_record check): ONE tiny group of the
+// transition's own 32-byte record laid out as observations f32[2] | actions f32[2] | terminals | valids | shadow next
+// observation f32[2], plus the two 8-byte goal rows.  The generic descriptor walk below costs ~420 of the index kernel's
+// ~820 instructions per 32 rows on that shape (profiles/r2_c1_lines_before.txt); with the layout fixed at compile time it
+// is 4 loads and 7 stores.  Every OGBench pointmaze dataset has this shape; anything else takes the generic path.
+template <bool kInject, int kFlavour, bool kSmemTables = false, bool kPoint = false>
 __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegView& seg, const int64_t g, int32_t* sr) {
   constexpr int kSlots = FlavourSlots<kFlavour>::value;
   uint64_t batch_id;
@@ -355,11 +360,11 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
   for (int u = 0; u < kMaxTinyGroups; ++u) {
     grp_a[u] = make_uint4(0, 0, 0, 0);
     grp_b[u] = make_uint4(0, 0, 0, 0);
-    if (u < p.n_tiny_groups && p.tiny_groups[u].slot == SLOT_IDX) {
+    if (kPoint ? u == 0 : (u < p.n_tiny_groups && p.tiny_groups[u].slot == SLOT_IDX)) {
       const TinyGroup& grp = p.tiny_groups[u];
       const uint4* sp = reinterpret_cast<const uint4*>(grp.src + (size_t)(uint32_t)i * grp.stride);
       grp_a[u] = __ldg(sp);
-      if (grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
+      if (kPoint || grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
     }
   }
   // :82 clamps idx + 1 to size - 1; with frame stacking (:231) and for ATC (:408) the reference does not clamp, and a
@@ -451,6 +456,17 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     }
   }
 
+  if (kPoint) {
+    const uint2 vgo = __ldg(reinterpret_cast<const uint2*>(p.tiny[0].src + (size_t)(uint32_t)sr[GC_VALUE_GOAL] * p.tiny[0].stride));
+    const uint2 ago = __ldg(reinterpret_cast<const uint2*>(p.tiny[1].src + (size_t)(uint32_t)sr[GC_ACTOR_GOAL] * p.tiny[1].stride));
+    reinterpret_cast<uint2*>(p.tiny_fields[0].dst)[g] = make_uint2(grp_a[0].x, grp_a[0].y);     // observations
+    reinterpret_cast<uint2*>(p.tiny_fields[1].dst)[g] = make_uint2(grp_a[0].z, grp_a[0].w);     // actions
+    reinterpret_cast<uint32_t*>(p.tiny_fields[2].dst)[g] = grp_b[0].x;                          // terminals
+    reinterpret_cast<uint32_t*>(p.tiny_fields[3].dst)[g] = grp_b[0].y;                          // valids
+    reinterpret_cast<uint2*>(p.tiny_fields[4].dst)[g] = make_uint2(grp_b[0].z, grp_b[0].w);     // next_observations (shadow)
+    reinterpret_cast<uint2*>(p.tiny[0].dst)[g] = vgo;                                           // value_goals
+    reinterpret_cast<uint2*>(p.tiny[1].dst)[g] = ago;                                           // actor_goals
+  } else {
   // grouped tiny fields: one record load per group (the groups of the transition's own row were fetched above), all
   // loads issued before any store.  (Unrolling the field and job loops completely, so that the descriptors sit at fixed
   // constant-bank offsets, was measured: the code growth costs more than the saved LDCs, 0.052 vs 0.047 ms on C1 and
@@ -523,6 +539,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     else for (uint32_t e = 0; e < job.row_bytes; ++e) dp[e] = __ldg(sp + e);
   }
 
+  }
+
   if (p.crop_out != nullptr) {
     int dy = -128, dx = -128;
     if (p.aug_mode) {                                                               // :278-279, :621-622
@@ -556,7 +574,7 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
 
 // kSmemTables: a persistent grid (a few CTAs per SM) whose CTAs first copy the segment table into shared memory
 // (dynamic: 16 B * n_seg_table + 4 B * n_seg_bucket) and then walk the rows with a grid stride.
-template <bool kInject, int kFlavour, bool kSmemTables>
+template <bool kInject, int kFlavour, bool kSmemTables, bool kPoint = false>
 __global__ void __launch_bounds__(kRelabelThreads, 4) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
   extern __shared__ __align__(16) uint8_t smem_tables[];
   SegView seg{p.seg_bucket, p.seg_table};
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(kRelabelThreads, 4) relabel_index_kernel(const
     int32_t sr[kMaxSlots];
 #pragma unroll
     for (int v = 0; v < kMaxSlots; ++v) sr[v] = 0;
-    relabel_row<kInject, kFlavour, kSmemTables>(p, seg, g, sr);
+    relabel_row<kInject, kFlavour, kSmemTables, kPoint>(p, seg, g, sr);
   }
 }
 

@@ -510,6 +510,14 @@ class _Sampler:
         flat = np.frombuffer(raw, dtype=np.uint8)
         return {name: flat[off:off + nb].view(dtype).reshape(shape) for name, dtype, shape, off, nb in keys}
 
+    def launch(self, batch_size, idxs=None, evaluation=False, n_batches=1, keep_axis=False) -> PendingBatch:
+        """sample() split in two: the launch now, the hand-over (and, for host output, the copy) in PendingBatch.result()."""
+        handle = self.sample_native(batch_size, n_batches, idxs, evaluation, None)
+        if keep_axis:
+            _native.check(_native.lib().ogb_batch_keep_leading_axis(handle.ptr, 1))
+        n_rows = len(idxs) // int(n_batches) if idxs is not None else int(batch_size)
+        return PendingBatch(self, handle, ('sample', n_rows, int(n_batches), bool(evaluation), bool(keep_axis)))
+
     def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         handle = self.sample_native(batch_size, n_batches, idxs, evaluation, draws)
         if keep_axis:   # sample_many: arrays are [n_batches, batch, ...] for every n_batches, 1 included
@@ -588,6 +596,24 @@ def _crop_array(arr, crop_froms, padding, device, output):
     _native.check(_native.lib().ogb_sampler_gather_cropped(sampler.ptr, idxs.ctypes.data_as(C.c_void_p), n,
                                                            crop.ctypes.data_as(C.c_void_p), int(padding), C.byref(out)))
     return next(iter(sampler.wrap(BatchHandle(out, device, None)).values()))
+
+
+class PendingBatch:
+    """A batch whose kernels have been launched; `result()` returns the dict `sample()` would have returned.
+
+    With output='numpy' the device-to-host copy happens in `result()`, on a stream of its own: launching the next batch
+    before asking for this one's result puts that launch (index upload, kernels) under this copy (what Prefetcher does)."""
+
+    __slots__ = ('_sampler', '_handle', '_layout_key', '_result')
+
+    def __init__(self, sampler, handle, layout_key):
+        self._sampler, self._handle, self._layout_key, self._result = sampler, handle, layout_key, None
+
+    def result(self):
+        if self._result is None:
+            self._result = self._sampler.wrap(self._handle, self._layout_key)
+            self._handle = None
+        return self._result
 
 
 class _Lookahead:
@@ -745,6 +771,18 @@ class GCDataset:
         `idxs` (optional, num_batches * batch_size rows) plays the role of sample()'s `idxs`."""
         self._settle()
         return self._sampler.sample(batch_size, idxs, evaluation, None, n_batches=num_batches, keep_axis=True)
+
+    def sample_async(self, batch_size, idxs=None, evaluation=False, num_batches=None) -> PendingBatch:
+        """Launch `sample(batch_size, idxs, evaluation)` (or, with `num_batches`, `sample_many`) and return at once;
+        `.result()` of the returned object gives the batch.  rng='philox' only: the draws are made by the launch."""
+        if self.rng != 'philox':
+            raise ValueError("sample_async needs rng='philox' (rng='numpy' draws on the host, in the reference's call order)")
+        self._settle()
+        if idxs is not None and num_batches is None:
+            batch_size = len(idxs)
+        if num_batches is None:
+            return self._sampler.launch(batch_size, idxs, evaluation)
+        return self._sampler.launch(batch_size, idxs, evaluation, n_batches=num_batches, keep_axis=True)
 
     # ---- reference helpers that other scripts call (impls/pretrain_atc.py:195, pretrain_vae.py:162) ----
     def get_observations(self, idxs):

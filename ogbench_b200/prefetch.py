@@ -44,7 +44,9 @@ class Prefetcher:
 
     _STOP = object()
 
-    def __init__(self, dataset, batch_size: int, depth: int = 2, **sample_kwargs):
+    def __init__(self, dataset, batch_size: int, depth: int = 2, idxs=None, **sample_kwargs):
+        """`idxs`: optional iterable of index arrays, one per batch (the `idxs` argument of successive sample() calls); the
+        iterator ends when it does.  `num_batches=K` in `sample_kwargs` draws sample_many(K, batch_size) per item."""
         if depth < 1:
             raise ValueError('depth must be at least 1')
         if getattr(dataset, 'rng', 'philox') == 'numpy':
@@ -52,6 +54,7 @@ class Prefetcher:
         self.dataset = dataset
         self.batch_size = int(batch_size)
         self.sample_kwargs = dict(sample_kwargs)
+        self._idxs = iter(idxs) if idxs is not None else None
         self._queue: 'queue.Queue[Any]' = queue.Queue(maxsize=depth)
         self._closing = threading.Event()
         self._thread: Optional[threading.Thread] = threading.Thread(target=self._work, daemon=True)
@@ -59,16 +62,47 @@ class Prefetcher:
         _LIVE.add(self)
         self._thread.start()
 
+    def _put(self, item):
+        while not self._closing.is_set():
+            try:
+                self._queue.put(item, timeout=0.05)
+                return
+            except queue.Full:
+                continue
+
+    def _launch(self):
+        """Start the next batch: a PendingBatch when the sampler can split launch and hand-over (sample_async), else the
+        finished batch.  None when the `idxs` iterator is exhausted."""
+        kwargs = self.sample_kwargs
+        if self._idxs is not None:
+            try:
+                kwargs = dict(kwargs, idxs=next(self._idxs))
+            except StopIteration:
+                return None
+        if hasattr(self.dataset, 'sample_async'):
+            return self.dataset.sample_async(self.batch_size, **kwargs)
+        if 'num_batches' in kwargs:
+            kwargs = dict(kwargs)
+            return self.dataset.sample_many(kwargs.pop('num_batches'), self.batch_size, **kwargs)
+        return self.dataset.sample(self.batch_size, **kwargs)
+
     def _work(self):
+        # Software-pipelined by one batch: batch k+1 is launched BEFORE batch k is finished, so with host output the
+        # upload and the kernels of k+1 run under the device-to-host copy of k (which has a stream of its own).
         try:
-            while not self._closing.is_set():
-                item = self.dataset.sample(self.batch_size, **self.sample_kwargs)
-                while not self._closing.is_set():
-                    try:
-                        self._queue.put(item, timeout=0.05)
-                        break
-                    except queue.Full:
-                        continue
+            pending = self._launch()
+            while pending is not None and not self._closing.is_set():
+                failure = None
+                try:
+                    nxt = self._launch()
+                except BaseException as exc:      # surfaces after the batch launched before it has been handed over
+                    nxt, failure = None, exc
+                self._put(pending.result() if hasattr(pending, 'result') else pending)
+                if failure is not None:
+                    raise failure
+                pending = nxt
+            if pending is None:
+                self._put(self._STOP)
         except BaseException as exc:  # handed to the consumer at its next call
             self._queue.put(exc)
 
@@ -79,6 +113,9 @@ class Prefetcher:
         if self._thread is None:
             raise StopIteration
         item = self._queue.get()
+        if item is self._STOP:
+            self._thread = None
+            raise StopIteration
         if isinstance(item, BaseException):
             self._thread = None
             raise item

@@ -120,3 +120,31 @@ def test_jax_compat_scalars_are_the_narrowed_reference_scalars(kind, over):
     host = device_sampler(fields, config, kind, seed=8, jax_compat=True, output='numpy', lookahead=3)
     batch = host.sample(50)
     assert batch['masks'].dtype == np.float32 and batch['rewards'].dtype == np.float32
+
+
+@pytest.mark.parametrize('output', ['device', 'numpy'])
+def test_prefetcher_pipelines_given_idxs_and_multi_batch_items(output):
+    """Prefetcher over sample_async: items are launched one ahead of the one being handed over; with an `idxs` iterable
+    and num_batches every item is sample_many(K, B, idxs=...) of the next index array, and the iterator ends with it."""
+    from ogbench_b200 import Prefetcher
+
+    fields = toy_fields(41, ragged(41, 90, 4, 50), (13,), 4, np.float32)
+    config = cfg()
+    valid = np.nonzero(fields['valids'] > 0)[0]
+    rng = np.random.default_rng(5)
+    K, B = 3, 40
+    index_arrays = [rng.choice(valid, K * B) for _ in range(7)]
+    direct = device_sampler(fields, config, 'gc', seed=12, output=output)
+    ahead = device_sampler(fields, config, 'gc', seed=12, output=output)
+    got = []
+    with Prefetcher(ahead, B, depth=2, num_batches=K, idxs=iter(index_arrays)) as batches:
+        for item in batches:
+            got.append(to_host(item))
+    assert len(got) == len(index_arrays)
+    for step, idxs in enumerate(index_arrays):
+        _same(got[step], to_host(direct.sample_many(K, B, idxs=idxs)), step)
+    # a pending batch is a plain two-phase call as well
+    a, b = ahead.sample_async(B), ahead.sample_async(B, evaluation=True)
+    _same(to_host(a.result()), to_host(direct.sample(B)), 'async 0')
+    _same(to_host(b.result()), to_host(direct.sample(B, evaluation=True)), 'async 1')
+    assert a.result() is a.result()
