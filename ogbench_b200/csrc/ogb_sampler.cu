@@ -1728,7 +1728,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     else { OGB_PICK_INDEX_KERNEL(false, false); }
 #undef OGB_PICK_INDEX_KERNEL
     if (point_record && !smem_tables)
-      fn = inject ? (const void*)relabel_index_kernel<true, FLAVOUR_GC, false, true> : (const void*)relabel_index_kernel<false, FLAVOUR_GC, false, true>;
+      // 48 registers, five CTAs per SM: 0.556 vs 0.541 of peak with four (six spill: 0.541), profiles/r2_ab_shapes.txt
+      fn = inject ? (const void*)relabel_index_kernel<true, FLAVOUR_GC, false, true> : (const void*)relabel_index_kernel<false, FLAVOUR_GC, false, true, 5>;
     int64_t grid_cap = (int64_t)ds->sm_count * (ab().index_grid > 0 ? ab().index_grid : 16);
     size_t smem = 0;
     if (smem_tables) {

@@ -574,8 +574,8 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
 
 // kSmemTables: a persistent grid (a few CTAs per SM) whose CTAs first copy the segment table into shared memory
 // (dynamic: 16 B * n_seg_table + 4 B * n_seg_bucket) and then walk the rows with a grid stride.
-template <bool kInject, int kFlavour, bool kSmemTables, bool kPoint = false>
-__global__ void __launch_bounds__(kRelabelThreads, 4) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
+template <bool kInject, int kFlavour, bool kSmemTables, bool kPoint = false, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kRelabelThreads, kMinBlocks) relabel_index_kernel(const __grid_constant__ RelabelParams p) {
   extern __shared__ __align__(16) uint8_t smem_tables[];
   SegView seg{p.seg_bucket, p.seg_table};
   if (kSmemTables) {
