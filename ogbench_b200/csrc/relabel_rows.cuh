@@ -156,6 +156,7 @@ struct RelabelParams {
   int64_t row_begin, row_end;  // rows this launch handles
   int32_t n_slots;
   int32_t narrow;              // jax_compat: the scalar outputs below are float32 / int32 arrays
+  int32_t pad1_[2];
   // ---- scalar outputs (float64 / int64 like the reference; float32 / int32 when `narrow`) ----
   double* masks;
   double* rewards;
