@@ -1052,6 +1052,9 @@ int ogb_dataset_set_active_rows(ogb_dataset* ds, int64_t n) try {
   if (!ds) return fail(OGB_ERR_INVALID, "null dataset");
   if (n < 0 || n > ds->size) return fail(OGB_ERR_INVALID, "active rows must be in [0, %lld]", (long long)ds->size);
   ds->active_rows = n;
+  // a buffer that is still filling up clamps idx + 1 at its CURRENT last row (datasets.py:82 with ReplayBuffer.size), which
+  // a shadow written against the allocated size cannot express: such datasets gather next_observations by row
+  if (n != ds->size) ds->shadow_next_field = -1;
   return 0;
 } OGB_CATCH_ALL
 int ogb_dataset_num_valid(const ogb_dataset* ds, int64_t* out) try {
@@ -1459,7 +1462,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   p.next_offset = (int32_t)spec.next_offset;
   p.trl = spec.trl ? 1 : 0;
   p.n_choices = n_choices;
-  p.n_rows_ds = (int32_t)ds->size;
+  // (a ReplayBuffer that is still filling up clamps idx + 1 at its current size, datasets.py:82 with self.size = fill)
+  p.n_rows_ds = (int32_t)(spec.kind == OGB_KIND_PLAIN && ds->active_rows > 0 ? ds->active_rows : ds->size);
   const double p_cur[3] = {cfg.value_p_curgoal, cfg.value_p_curgoal, cfg.actor_p_curgoal};
   const double p_traj[3] = {cfg.value_p_trajgoal, cfg.value_p_trajgoal, cfg.actor_p_trajgoal};
   const double disc[3] = {cfg.discount, cfg.has_low_discount ? cfg.low_discount : cfg.discount, cfg.discount};

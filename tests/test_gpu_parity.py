@@ -174,6 +174,8 @@ def test_no_writes_outside_the_keys(spec):
         assert np.array_equal(out['terminals'].reshape(n), fields['terminals'][idx])
         if fs is None:
             assert np.array_equal(out['observations'].reshape(n, *obs_shape), fields['observations'][idx])
+            nxt = np.minimum(idx + 1, len(fields['terminals']) - 1)      # datasets.py:82 (from the record's shadow copy when it has one)
+            assert np.array_equal(out['next_observations'].reshape(n, *obs_shape), fields['observations'][nxt])
 
 
 def test_mixed_dtypes_against_oracle():
