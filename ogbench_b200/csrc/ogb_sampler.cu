@@ -338,9 +338,25 @@ struct ogb_dataset {
   size_t resident_bytes = 0;
   int sm_count = 148;
 
+  // Pytree fields (the reference maps every gather over arbitrary pytrees, datasets.py:13,80,344,365-366): the host
+  // wrapper flattens a nested dict into one field per leaf named "<key>/<path>".  Every leaf under "observations/" is an
+  // observation: obs_field is the first of them (or the plain "observations" field), obs_extra the others.
+  std::vector<int> obs_extra;
+
   int find(const char* name) const {
     for (size_t i = 0; i < fields.size(); ++i)
       if (fields[i].name == name) return (int)i;
+    return -1;
+  }
+  static bool under(const std::string& field_name, const char* key) {   // the field is `key` itself or a leaf below it
+    const size_t n = strlen(key);
+    return field_name.compare(0, n, key) == 0 && (field_name.size() == n || field_name[n] == '/');
+  }
+  int find_under(const char* key) const {
+    const int exact = find(key);
+    if (exact >= 0) return exact;
+    for (size_t i = 0; i < n_public && i < fields.size(); ++i)
+      if (under(fields[i].name, key)) return (int)i;
     return -1;
   }
 };
@@ -635,14 +651,14 @@ struct PlanBuilder {
     keys.push_back(std::move(k));
   }
 
-  void alias(const char* name, const char* target) {
-    for (size_t i = 0; i < keys.size(); ++i)
-      if (keys[i].name == target) {
+  void alias(const char* name, const char* target) {   // every leaf of `target` (the key itself, or "target/<path>")
+    const size_t n_before = keys.size();
+    for (size_t i = 0; i < n_before; ++i)
+      if (ogb_dataset::under(keys[i].name, target)) {
         KeyPlan k = keys[i];
-        k.name = name;
+        k.name = std::string(name) + keys[i].name.substr(strlen(target));
         k.alias_of = keys[i].alias_of >= 0 ? keys[i].alias_of : (int)i;
         keys.push_back(std::move(k));
-        return;
       }
   }
 
@@ -665,8 +681,16 @@ struct PlanBuilder {
     k.route = (fs > 1 || k.crop) ? ROUTE_FRAMES : ROUTE_ROW;
     push(std::move(k));
   }
+  // key `name` for observation leaf `field`: "value_goals" for the plain "observations" field, "value_goals/<path>" for the
+  // leaf "observations/<path>" of a pytree
+  std::string leaf_name(const char* name, int field) const {
+    const std::string& f = ds->fields[(size_t)field].name;
+    return f.size() > 12 && f.compare(0, 13, "observations/") == 0 ? std::string(name) + f.substr(12) : std::string(name);
+  }
   void obs_key(const char* name, int slot, bool in_aug) {
-    field_key(name, ds->obs_field, slot, in_aug, cfg->frame_stack > 0 ? cfg->frame_stack : 1);
+    const int fs = cfg->frame_stack > 0 ? cfg->frame_stack : 1;
+    field_key(leaf_name(name, ds->obs_field).c_str(), ds->obs_field, slot, in_aug, fs);
+    for (int leaf : ds->obs_extra) field_key(leaf_name(name, leaf).c_str(), leaf, slot, in_aug, fs);
   }
   void goal_key(const char* name, int slot, bool in_aug) {  // datasets.py:348-357
     if (ds->oracle_field >= 0) field_key(name, ds->oracle_field, slot, in_aug);
@@ -685,8 +709,9 @@ struct PlanBuilder {
   void base_keys() {  // datasets.py:78-83 (+ :229-231)
     for (size_t i = 0; i < ds->n_public; ++i) {
       const std::string& nm = ds->fields[i].name;
-      if ((int)i == ds->obs_field) obs_key("observations", ogb::SLOT_IDX, true);
-      else field_key(nm.c_str(), (int)i, ogb::SLOT_IDX, nm == "next_observations");
+      if ((int)i == ds->obs_field) obs_key("observations", ogb::SLOT_IDX, true);        // every observation leaf
+      else if (ogb_dataset::under(nm, "observations")) continue;                        // (emitted with the first leaf)
+      else field_key(nm.c_str(), (int)i, ogb::SLOT_IDX, ogb_dataset::under(nm, "next_observations"));
     }
     if (ds->next_obs_field < 0) {
       // observations[min(idx + 1, size - 1)] (datasets.py:82): from the record's shadow copy when there is one
@@ -974,8 +999,10 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
     }
   }
   ds->n_public = ds->fields.size();
-  ds->obs_field = ds->find("observations");
-  if (ds->obs_field >= 0 && ds->find("next_observations") < 0 && !ab().no_shadow) {
+  ds->obs_field = ds->find_under("observations");
+  for (size_t i = 0; i < ds->n_public; ++i)
+    if ((int)i != ds->obs_field && ogb_dataset::under(ds->fields[i].name, "observations")) ds->obs_extra.push_back((int)i);
+  if (ds->obs_field >= 0 && ds->obs_extra.empty() && ds->find_under("next_observations") < 0 && !ab().no_shadow) {
     const Field obs = ds->fields[(size_t)ds->obs_field];
     size_t a = 16;
     while (obs.row_bytes % a != 0) a >>= 1;
@@ -995,7 +1022,7 @@ int ogb_dataset_create(const ogb_field* fields, int32_t n_fields, int32_t device
   }
   ds->terminals_field = ds->find("terminals");
   ds->valids_field = ds->find("valids");
-  ds->next_obs_field = ds->find("next_observations");
+  ds->next_obs_field = ds->find_under("next_observations");
   ds->oracle_field = ds->find("oracle_reps");
   if (ds->obs_field < 0) return bail(fail(OGB_ERR_ASSERT, "assert 'observations' in data (datasets.py:54)"));
 

@@ -27,9 +27,37 @@ from .device_array import BatchHandle, DeviceArray
 TRL_AGENTS = ('trl', 'latent_trl', 'discrete_latent_trl')
 
 
+SEP = '/'   # path separator of flattened pytree fields: {'observations': {'image': a, 'state': b}} -> 'observations/image', ...
+
+
+def _leaves(tree, prefix=''):
+    """(path, leaf) pairs of a nested dict, keys sorted like jax's dict flattening (datasets.py:13,80 map over pytrees)."""
+    if isinstance(tree, Mapping):
+        for k in sorted(tree):
+            yield from _leaves(tree[k], f'{prefix}{SEP}{k}' if prefix else str(k))
+    else:
+        yield prefix, tree
+
+
+def _flatten(fields) -> Dict[str, Any]:
+    return dict(_leaves(fields))
+
+
+def _nest(flat: Dict[str, Any]) -> Dict[str, Any]:
+    """Inverse of _flatten for a batch: 'value_goals/image' -> batch['value_goals']['image']."""
+    out: Dict[str, Any] = {}
+    for path, v in flat.items():
+        parts = path.split(SEP)
+        node = out
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = v
+    return out
+
+
 def get_size(data) -> int:
-    """Return the size of the dataset: the longest field (datasets.py:11-14)."""
-    return max(len(v) for v in data.values())
+    """Return the size of the dataset: the longest leaf of the field pytree (datasets.py:11-14)."""
+    return max(len(v) for _, v in _leaves(data))
 
 
 def _is_device_array(x) -> bool:
@@ -122,7 +150,7 @@ class Dataset(Mapping):
         data = fields
         assert 'observations' in data
         if freeze:
-            for arr in data.values():
+            for _, arr in _leaves(data):
                 if isinstance(arr, np.ndarray):
                     arr.setflags(write=False)
         return cls(data)
@@ -132,9 +160,9 @@ class Dataset(Mapping):
             self._dict = dict(args[0]._dict)
         else:
             self._dict = dict(*args, **kwargs)
-        for k, v in self._dict.items():
-            if isinstance(v, Mapping):
-                raise NotImplementedError(f'field {k!r}: nested (pytree) fields are not supported by the device sampler')
+        # nested dicts (pytree fields, e.g. observations = {'image': ..., 'state': ...}) are flattened into one resident field
+        # per leaf; every key derived from them comes back nested the same way
+        self._nested = any(isinstance(v, Mapping) for v in self._dict.values())
         self.size = get_size(self._dict)
         if 'valids' in self._dict and isinstance(self._dict['valids'], np.ndarray):
             (self.valid_idxs,) = np.nonzero(self['valids'] > 0)
@@ -165,7 +193,7 @@ class Dataset(Mapping):
 
     def native(self, device: int = 0) -> _NativeDataset:
         if device not in self._native:
-            self._native[device] = _NativeDataset(self._dict, device)
+            self._native[device] = _NativeDataset(_flatten(self._dict) if self._nested else self._dict, device)
         return self._native[device]
 
     def _plain_sampler(self, device=0) -> '_Sampler':
@@ -198,13 +226,13 @@ class ReplayBuffer(Dataset):
     @classmethod
     def create(cls, transition, size, **kwargs):
         """Create a replay buffer from the example transition (datasets.py:92-106)."""
-        fields = {k: _ZeroField((size, *np.array(v).shape), np.array(v).dtype) for k, v in transition.items()}
+        fields = {k: _ZeroField((size, *np.array(v).shape), np.array(v).dtype) for k, v in _leaves(transition)}   # pytrees: one buffer per leaf
         return cls(fields, **kwargs)
 
     @classmethod
     def create_from_initial_dataset(cls, init_dataset, size, **kwargs):
         """Create a replay buffer from the initial dataset (datasets.py:108-125)."""
-        init = {k: np.asarray(v) for k, v in dict(init_dataset).items()}
+        init = {k: np.asarray(v) for k, v in _leaves(dict(init_dataset))}
         n = get_size(init)
 
         def create_buffer(init_buffer):
@@ -220,6 +248,7 @@ class ReplayBuffer(Dataset):
 
     def __init__(self, fields, rng='philox', output='device', device=0):
         self._dict = dict(fields)
+        self._nested = any(SEP in k for k in self._dict)      # leaves of pytree transitions, flattened by create()
         self.rng, self.output, self._device = rng, output, device
         self.max_size = get_size(self._dict)
         self.size = 0
@@ -245,6 +274,8 @@ class ReplayBuffer(Dataset):
         sampler = self._plain_sampler(self._device)
         ptrs = (C.c_void_p * len(self._names))()
         keep = []
+        if self._nested:
+            transition = _flatten(transition)
         for i, name in enumerate(self._names):
             zf = self._dict[name]
             arr = np.ascontiguousarray(np.asarray(transition[name]), dtype=zf.dtype).reshape(zf.shape[1:])
@@ -337,6 +368,7 @@ class _Sampler:
         self.kind = kind
         self.device = device
         self.output = output
+        self.nested = bool(getattr(dataset, '_nested', False))   # pytree fields: batches are re-nested on the way out
         self._keepalive = []
         cfg = _native.Config()
         cfg.dedup_keys = int(dedup)
@@ -452,7 +484,7 @@ class _Sampler:
         idxs = np.ascontiguousarray(np.asarray(idxs), dtype=np.int64).reshape(-1)
         out = C.c_void_p()
         _native.check(_native.lib().ogb_sampler_gather(self.ptr, which, idxs.ctypes.data_as(C.c_void_p), len(idxs), C.byref(out)))
-        return next(iter(self.wrap(BatchHandle(out, self.device, None), ('gather', int(which), len(idxs))).values()))
+        return next(iter(self.wrap(BatchHandle(out, self.device, None), ('gather', int(which), len(idxs))).values()))   # (a dict of leaves for pytree observations)
 
     def sample_atc(self, batch_size, k, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         keep = []
@@ -501,14 +533,16 @@ class _Sampler:
             base = C.c_void_p()
             _native.check(lib.ogb_batch_device_block(handle.ptr, C.byref(base)))
             base = base.value or 0
-            return {name: DeviceArray(handle, i, name, dtype, shape, base + off, nb) for i, (name, dtype, shape, off, nb) in enumerate(keys)}
+            out = {name: DeviceArray(handle, i, name, dtype, shape, base + off, nb) for i, (name, dtype, shape, off, nb) in enumerate(keys)}
+            return _nest(out) if self.nested else out
         # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it
         block = _PINNED.take(total)
         _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
         raw = (C.c_ubyte * total).from_address(block.ptr)
         raw._owner = block  # numpy views -> ctypes buffer -> pinned block: returned to the pool when all views die
         flat = np.frombuffer(raw, dtype=np.uint8)
-        return {name: flat[off:off + nb].view(dtype).reshape(shape) for name, dtype, shape, off, nb in keys}
+        out = {name: flat[off:off + nb].view(dtype).reshape(shape) for name, dtype, shape, off, nb in keys}
+        return _nest(out) if self.nested else out
 
     def launch(self, batch_size, idxs=None, evaluation=False, n_batches=1, keep_axis=False) -> PendingBatch:
         """sample() split in two: the launch now, the hand-over (and, for host output, the copy) in PendingBatch.result()."""
@@ -622,10 +656,13 @@ class _Lookahead:
     The Philox draws of a launch of K batches are those of K single launches (counter = batch index), so the sequence of
     batches is exactly the one direct sample() calls return (tests/test_gpu_lookahead.py)."""
 
-    __slots__ = ('counter0', 'n', 'pos', 'batch', 'evaluation', 'handle', 'keys', 'host')
+    __slots__ = ('counter0', 'n', 'pos', 'batch', 'evaluation', 'handle', 'keys', 'host', 'nested')
 
     def __init__(self, counter0, n, batch, evaluation, many):
         self.counter0, self.n, self.pos, self.batch, self.evaluation = counter0, n, 0, batch, evaluation
+        self.nested = any(isinstance(v, Mapping) for v in many.values())       # pytree fields: slices are re-nested
+        if self.nested:
+            many = _flatten(many)
         first = next(iter(many.values()))
         if isinstance(first, DeviceArray):
             self.handle, self.host = first._batch, None
@@ -638,9 +675,11 @@ class _Lookahead:
         i = self.pos
         self.pos = i + 1
         if self.host is not None:
-            return {k: v[i] for k, v in self.host.items()}       # views into the pinned block of the whole launch
-        handle = self.handle
-        return {k: DeviceArray(handle, idx, k, dtype, shape, ptr + i * step, step, i) for k, idx, dtype, shape, ptr, step in self.keys}
+            out = {k: v[i] for k, v in self.host.items()}        # views into the pinned block of the whole launch
+        else:
+            handle = self.handle
+            out = {k: DeviceArray(handle, idx, k, dtype, shape, ptr + i * step, step, i) for k, idx, dtype, shape, ptr, step in self.keys}
+        return _nest(out) if self.nested else out
 
 
 class GCDataset:
@@ -683,6 +722,9 @@ class GCDataset:
         # datasets.py:191-196 (checked before touching the device, like the reference's __post_init__)
         assert np.isclose(config['value_p_curgoal'] + config['value_p_trajgoal'] + config['value_p_randomgoal'], 1.0)
         assert np.isclose(config['actor_p_curgoal'] + config['actor_p_trajgoal'] + config['actor_p_randomgoal'], 1.0)
+        if getattr(dataset, '_nested', False) and config['p_aug']:
+            # the reference's augment() reads batch[key].shape (datasets.py:337): a pytree observation has none
+            raise NotImplementedError('image augmentation (p_aug > 0) is not defined for pytree observations (datasets.py:329-339)')
         self._trl = self._KIND == _native.KIND_GC and config.get('agent_name') in TRL_AGENTS
         if self._trl:
             # datasets.py:254-257 asserts idxs != value_goal_idxs on every call; with any current/random goal mass that

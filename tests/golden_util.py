@@ -11,7 +11,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 def case_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
-    return [n for n in names if not n.startswith(('rb_', 'loader_'))]  # those fixtures have their own tests
+    return [n for n in names if not n.startswith(('rb_', 'loader_', 'pytree_'))]  # those fixtures have their own tests
 
 
 def load_case(name):

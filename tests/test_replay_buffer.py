@@ -91,7 +91,7 @@ def test_replay_buffer_without_next_observations_tracks_row_writes():
 
     def transition():
         return dict(observations=rng.standard_normal(2).astype(np.float32), actions=rng.uniform(-1, 1, 2).astype(np.float32),
-                    terminals=np.float32(0.0), valids=np.float32(1.0))
+                    terminals=np.float32(0.0), rewards=np.float32(1.0))
 
     def check(rb, mirror, filled):
         idxs = np.arange(filled)
@@ -114,7 +114,7 @@ def test_replay_buffer_without_next_observations_tracks_row_writes():
     from ogbench_b200 import Dataset, _native
 
     n = 12
-    init = {k: np.stack([transition()[k] for _ in range(n)]) for k in ('observations', 'actions', 'terminals', 'valids')}
+    init = {k: np.stack([transition()[k] for _ in range(n)]) for k in ('observations', 'actions', 'terminals', 'rewards')}
     ds = Dataset.create(**{k: v.copy() for k, v in init.items()})
     ds.output = 'numpy'
     sampler = ds._plain_sampler()
