@@ -93,21 +93,67 @@ def add_oracle_reps(env_name, env, dataset, num_cubes=None, num_buttons=None):
     dataset['oracle_reps'] = oracle_reps.astype(np.float32)
 
 
+def relabel_dataset(env_name, env, dataset):
+    """Add the single-task 'rewards' and 'masks' of the environment's fixed task (same contract as
+    ogbench/relabel_utils.py:4-90).  `env` is the single-task environment (anything exposing the attributes the reference
+    reads from `env.unwrapped`: `_reward_task_id`, `cur_goal_xy` / `_goal_tol` for the mazes and antsoccer, `_num_cubes`,
+    `_num_buttons`, `_data.mocap_pos`, `_target_button_states`, `_target_drawer_pos`, `_target_window_pos` for
+    manipulation); `env.reset()` is called first, as in the reference, so that the task is set.  The dataset must carry
+    'qpos' (and 'button_states' for scene / puzzle), i.e. be loaded with add_info=True.
+    """
+    task = env.unwrapped
+    assert task._reward_task_id is not None, 'The environment is not in the single-task mode.'
+    env.reset()
+    tol = 0.04                                              # object / drawer / window tolerance of the manipulation tasks
+    if 'maze' in env_name or 'soccer' in env_name:
+        first = 0 if 'maze' in env_name else 15             # the agent's xy, or the ball's for antsoccer
+        gap = np.linalg.norm(dataset['qpos'][:, first:first + 2] - task.cur_goal_xy, axis=-1)
+        reached = (gap <= task._goal_tol).astype(np.float32)
+        rewards, masks = reached - 1.0, 1.0 - reached       # -1 until the goal is reached; the episode stops mattering there
+    elif 'cube' in env_name or 'scene' in env_name or 'puzzle' in env_name:
+        obj0, cube_len = 14, 7
+        done = []                                           # one boolean column per sub-goal of the task
+        if 'cube' in env_name or 'scene' in env_name:
+            n_cubes = task._num_cubes
+            xyz = np.stack([dataset['qpos'][:, obj0 + c * cube_len:obj0 + c * cube_len + 3] for c in range(n_cubes)], axis=1)
+            done.append(np.linalg.norm(task._data.mocap_pos.copy() - xyz, axis=-1) <= tol)
+        if 'scene' in env_name and 'cube' not in env_name:
+            drawer = obj0 + task._num_cubes * cube_len + task._num_buttons
+            done.append(dataset['button_states'] == task._target_button_states.copy())
+            done.append((np.abs(dataset['qpos'][:, drawer] - task._target_drawer_pos) <= tol)[:, None])
+            done.append((np.abs(dataset['qpos'][:, drawer + 1] - task._target_window_pos) <= tol)[:, None])
+        if 'puzzle' in env_name and 'cube' not in env_name and 'scene' not in env_name:
+            done.append(dataset['button_states'] == task._target_button_states.copy())
+        done = np.concatenate(done, axis=-1)
+        rewards = done.sum(axis=-1) - done.shape[-1]        # minus the number of unfinished sub-goals
+        masks = 1.0 - np.all(done, axis=-1)
+    else:
+        raise ValueError(f'Unsupported environment: {env_name}')
+    dataset['rewards'] = rewards.astype(np.float32)
+    dataset['masks'] = masks.astype(np.float32)
+
+
 def make_datasets(dataset_name, dataset_dir='~/.ogbench/data', dataset_path=None, compact_dataset=False, add_info=False,
                   env=None, num_cubes=None, num_buttons=None):
     """The dataset half of `ogbench.make_env_and_datasets(..., dataset_only=True)` (ogbench/utils.py:134-235): resolves the
     train / validation files of `dataset_name`, picks the dtypes by environment family, loads both splits and, for
     '-oraclerep-' names, adds the oracle goal representations.  Returns (train_dataset, val_dataset) as dicts of host
-    arrays.  Nothing is downloaded (the files must exist), and 'singletask' names are refused: their reward relabelling
-    (ogbench/relabel_utils.py:4-90) needs the live environment's goal, which is outside this package.
+    arrays; 'singletask' names are relabelled with the rewards / masks of `env`'s fixed task (relabel_dataset).  Nothing is
+    downloaded (the files must exist).
     """
     import os
 
     splits = dataset_name.split('-')
-    if 'singletask' in splits:
-        raise NotImplementedError("'singletask' datasets need the environment's task goal (ogbench/relabel_utils.py:4-90)")
     dataset_add_info = add_info
-    if 'oraclerep' in splits:
+    if 'singletask' in splits:
+        if env is None:
+            raise ValueError("'singletask' datasets are relabelled with the task of the single-task environment: pass env= "
+                             '(ogbench/utils.py:164-171, relabel_utils.py:4-90)')
+        pos = splits.index('singletask')
+        env_name = '-'.join(splits[:pos - 1] + splits[pos:])      # remove the dataset type
+        dataset_name = '-'.join(splits[:pos] + splits[-1:])        # the files carry neither 'singletask' nor 'task<n>'
+        dataset_add_info = True
+    elif 'oraclerep' in splits:
         env_name = '-'.join(splits[:-3] + splits[-1:])         # remove the dataset type and the word 'oraclerep'
         dataset_name = '-'.join(splits[:-2] + splits[-1:])     # the files carry no 'oraclerep'
         dataset_add_info = True
@@ -127,6 +173,8 @@ def make_datasets(dataset_name, dataset_dir='~/.ogbench/data', dataset_path=None
     out = []
     for path in (train_path, val_path):
         ds = load_dataset(path, ob_dtype=ob_dtype, action_dtype=action_dtype, compact_dataset=compact_dataset, add_info=dataset_add_info)
+        if 'singletask' in splits:
+            relabel_dataset(env_name, env, ds)
         if 'oraclerep' in splits:
             add_oracle_reps(env_name, env, ds, num_cubes=num_cubes, num_buttons=num_buttons)
         if not add_info:

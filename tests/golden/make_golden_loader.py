@@ -132,9 +132,62 @@ def main_make_datasets():
     print('loader_make_datasets', len(payload), 'arrays')
 
 
+SINGLETASK_ENVS = ['antmaze-large-singletask-task1-v0', 'antsoccer-arena-singletask-v0', 'cube-double-singletask-task2-v0',
+                   'scene-singletask-task3-v0', 'puzzle-3x3-singletask-v0']
+
+
+def singletask_env(name):
+    """What relabel_dataset reads from a single-task environment (ogbench/relabel_utils.py:13-84), as a plain namespace."""
+    rng = np.random.default_rng(len(name))
+    task = types.SimpleNamespace(_reward_task_id=1, cur_goal_xy=rng.standard_normal(2), _goal_tol=0.9, _num_cubes=2, _num_buttons=9,
+                                 _data=types.SimpleNamespace(mocap_pos=rng.standard_normal((2, 3)) * 0.05),
+                                 _target_button_states=rng.integers(0, 2, 9), _target_drawer_pos=0.01, _target_window_pos=-0.02)
+    return types.SimpleNamespace(unwrapped=task, reset=lambda: None)
+
+
+def singletask_inputs(env, seed=9, n=45):
+    """qpos / button_states: a third of the rows satisfies every sub-goal of `env`'s task, a third only some, the rest none."""
+    rng = np.random.default_rng(seed)
+    task = env.unwrapped
+    qpos = rng.standard_normal((n, 40))
+    buttons = rng.integers(0, 2, (n, 9)).astype(np.int64)
+    third = n // 3
+    drawer = 14 + task._num_cubes * 7 + task._num_buttons
+    for r in range(2 * third):
+        full = r < third
+        qpos[r, :2] = qpos[r, 15:17] = task.cur_goal_xy + rng.uniform(-0.3, 0.3, 2)
+        for c in range(task._num_cubes if full else 1):
+            qpos[r, 14 + 7 * c:17 + 7 * c] = task._data.mocap_pos[c] + rng.uniform(-0.015, 0.015, 3)
+        if full:
+            buttons[r] = task._target_button_states
+            qpos[r, drawer], qpos[r, drawer + 1] = task._target_drawer_pos + 0.02, task._target_window_pos - 0.03
+    return dict(qpos=qpos, button_states=buttons)
+
+
+def main_singletask():
+    """ogbench/relabel_utils.py:4-90 run unmodified -> loader_singletask.npz; plus one make_env_and_datasets case."""
+    ref = load_reference_relabel()
+    payload = {}
+    for name in SINGLETASK_ENVS:
+        ds = singletask_inputs(singletask_env(name))
+        ref.relabel_dataset(name, singletask_env(name), ds)
+        payload[f'{name}/rewards'], payload[f'{name}/masks'] = ds['rewards'], ds['masks']
+        assert 0 < (ds['masks'] == 0).sum() < len(ds['masks']), name      # both outcomes occur
+    utils = load_reference_utils_with_relabel()
+    name = 'antmaze-large-navigate-singletask-task1-v0'                    # files: antmaze-large-navigate-v0(.npz, -val.npz)
+    train, val = utils.make_env_and_datasets(name, dataset_path=os.path.join(HERE, 'loader_raw', 'antmaze-large-navigate-v0.npz'),
+                                             compact_dataset=True, dataset_only=True, cur_env=singletask_env('antmaze-large-singletask-task1-v0'))
+    for split, ds in (('train', train), ('val', val)):
+        for k, v in ds.items():
+            payload[f'make/{split}/{k}'] = v
+    np.savez_compressed(os.path.join(HERE, 'loader_singletask.npz'), **payload)
+    print('loader_singletask', len(payload), 'arrays')
+
+
 def main():
     main_oracle_reps()
     main_make_datasets()
+    main_singletask()
     ref = load_reference_utils()
     for name, raw_kw, load_kw in CASES:
         raw = os.path.join(HERE, name + '_raw.npz')

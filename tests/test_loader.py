@@ -62,10 +62,38 @@ def test_make_datasets_matches_reference():
             for k in keys:
                 w = want[prefix + k]
                 assert ds[k].dtype == w.dtype and ds[k].shape == w.shape and np.array_equal(ds[k], w), (name, split, k)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                           # single-task relabelling needs the environment
         loader.make_datasets('cube-single-play-singletask-v0', dataset_path='x.npz')
     with pytest.raises(FileNotFoundError):
         loader.make_datasets('antmaze-large-navigate-v0', dataset_dir=raw_dir + '/missing')
+
+
+def test_singletask_relabelling_matches_reference():
+    """relabel_dataset (ogbench/relabel_utils.py:4-90) against rewards / masks computed by the unmodified reference function
+    for the five environment families, and make_datasets for a 'singletask' name (ogbench/utils.py:164-171, 217-220)."""
+    from tests.golden.make_golden_loader import SINGLETASK_ENVS, singletask_env, singletask_inputs
+
+    want = np.load(os.path.join(HERE, 'loader_singletask.npz'))
+    for name in SINGLETASK_ENVS:
+        ds = singletask_inputs(singletask_env(name))
+        loader.relabel_dataset(name, singletask_env(name), ds)
+        for k in ('rewards', 'masks'):
+            w = want[f'{name}/{k}']
+            assert ds[k].dtype == w.dtype == np.float32 and np.array_equal(ds[k], w), (name, k)
+    with pytest.raises(ValueError):
+        loader.relabel_dataset('powderworld-easy-singletask-v0', singletask_env('x'), singletask_inputs(singletask_env('x')))
+    env = singletask_env('x')
+    env.unwrapped._reward_task_id = None
+    with pytest.raises(AssertionError):
+        loader.relabel_dataset('antmaze-large-singletask-v0', env, singletask_inputs(env))
+    got = loader.make_datasets('antmaze-large-navigate-singletask-task1-v0', dataset_path=os.path.join(HERE, 'loader_raw', 'antmaze-large-navigate-v0.npz'),
+                               compact_dataset=True, env=singletask_env('antmaze-large-singletask-task1-v0'))
+    for split, ds in zip(('train', 'val'), got):
+        keys = {k[len(f'make/{split}/'):] for k in want.files if k.startswith(f'make/{split}/')}
+        assert set(ds) == keys and 'rewards' in keys and 'qpos' not in keys, (split, set(ds) ^ keys)
+        for k in keys:
+            w = want[f'make/{split}/{k}']
+            assert ds[k].dtype == w.dtype and np.array_equal(ds[k], w), (split, k)
 
 
 def test_list_shards(tmp_path):
