@@ -773,7 +773,7 @@ struct __align__(16) OutDesc {
 static_assert(sizeof(OutDesc) == 32, "OutDesc is read as two 16-byte words");
 
 constexpr int kMaxItems = 64;      // per launch; the host splits the job list over several launches beyond that
-constexpr int kMaxItemOuts = 96;
+constexpr int kMaxItemOuts = 192;
 
 struct AsyncGatherParams {
   const int32_t* vec_rows;

@@ -200,6 +200,40 @@ def test_mixed_dtypes_against_oracle():
             assert_batches_identical(got, want, label=f'mixed/{kind}/{it}:')
 
 
+@pytest.mark.parametrize('rng_mode', ['numpy', 'philox'])
+def test_long_rows_with_many_small_fields_fill_the_item_tables(rng_mode):
+    """1,200-byte observation rows (four rows per pipeline stage -> eight items per tile and job) next to a dozen small
+    per-transition fields that share the transition's record span: 150 entries in the per-launch output table and 32 items,
+    both Philox (the 2 x 16 fused shape) and injected draws (3 x 8), ragged last tile included."""
+    from oracle import philox_np
+    from oracle.replay_oracle import DrawsSource, OracleSampler
+    from tests.test_gpu_philox import goal_sets_for
+
+    rng = np.random.default_rng(13)
+    lengths = ragged(13, 60, 9, 50)
+    fields = toy_fields(13, lengths, (300,), 4, np.float32)
+    n = len(fields['terminals'])
+    for j in range(12):
+        fields[f'extra_{j:02d}'] = rng.standard_normal((n, 1 + j % 2)).astype(np.float32) if j % 3 else rng.integers(0, 9, n).astype(np.int32)
+    config = cfg()
+    B = 1000 + 13
+    if rng_mode == 'numpy':
+        sampler = device_sampler(fields, config, 'gc', rng='numpy', output='numpy')
+        np.random.seed(5)
+        _, want = oracle_with_draws(fields, config, 'gc', B)
+        np.random.seed(5)
+        assert_batches_identical(sampler.sample(B), want, label='long rows/numpy:')
+    else:
+        sampler = device_sampler(fields, config, 'gc', seed=17, stream_id=4)
+        oracle = OracleSampler(fields, config, 'gc')
+        got = to_host(sampler.sample(B))
+        draws, knife = philox_np.philox_draws(17, 4, 0, B, len(oracle.valid_table), goal_sets_for(config, 'gc'), True, 0.0)
+        want = oracle.sample(B, source=DrawsSource(draws))
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and np.array_equal(got[k][~knife], want[k][~knife]), k
+
+
 @pytest.mark.parametrize('kind', ['gc', 'hgc'])
 def test_large_batch_numpy_rng_matches_oracle(kind):
     """One sample() of 40,000 rows (>= 32,768: the big-launch code paths -- auxiliary stream, persistent index kernel with
