@@ -50,6 +50,8 @@ struct AbSwitches {
   bool no_shadow;        // OGB_NO_SHADOW       no shadow copy of the next row's observation inside the records
   int index_grid;        // OGB_INDEX_GRID=n    index kernel grid capped at n CTAs per SM instead of 16
   bool no_point;         // OGB_NO_POINT        point-maze records go through the generic tiny-field walk of the index kernel
+  bool static_tiles;     // OGB_STATIC_TILES    row gathers walk their tiles with a fixed stride instead of taking tickets
+  int claim_pairs;       // OGB_CLAIM_PAIRS=n   a tile's ticket is taken n (tile, job) pairs before it is needed (default: 1 fused, 3 un-fused)
 };
 
 const AbSwitches& ab() {
@@ -76,6 +78,8 @@ const AbSwitches& ab() {
     a.no_shadow = flag("OGB_NO_SHADOW");
     a.index_grid = number("OGB_INDEX_GRID", 0);
     a.no_point = flag("OGB_NO_POINT");
+    a.static_tiles = flag("OGB_STATIC_TILES");
+    a.claim_pairs = number("OGB_CLAIM_PAIRS", 0);
     return a;
   }();
   return sw;
@@ -406,6 +410,13 @@ struct ogb_sampler {
   std::map<int64_t, AtcTable> atc_tables;      // ATC anchor rows per temporal offset k (datasets.py:417-436)
   AtcTable trl_rows;                           // TRL: valid_idxs override = every non-terminal row (datasets.py:198-204)
   cudaStream_t aux_stream = nullptr;           // index kernels of chunked launches
+  // Ticket counters of the row gathers' dynamic tile scheduling (relabel_rows.cuh): kSchedSlots pairs, one 128-byte line
+  // each, handed out round-robin per launch.  A launch leaves its pair at zero, and launches of one stream run one after
+  // the other, so a pair is only ever shared by launches that are kSchedSlots launches apart.
+  static constexpr int kSchedSlots = 64;
+  uint32_t* d_sched = nullptr;
+  uint32_t sched_seq = 0;
+  uint32_t* next_sched() { return d_sched ? d_sched + 32 * (size_t)(sched_seq++ % kSchedSlots) : nullptr; }
   std::vector<cudaEvent_t> chunk_events;       // ring of join events (index kernel -> gathers)
   int next_event = 0;
   std::mutex cache_mu;
@@ -550,6 +561,7 @@ void sampler_unref(ogb_sampler* s) {
   if (s->d_term_bucket) cudaFree(s->d_term_bucket);
   if (s->d_seg_table) cudaFree(s->d_seg_table);
   if (s->d_seg_bucket) cudaFree(s->d_seg_bucket);
+  if (s->d_sched) cudaFree(s->d_sched);
   if (s->d_neg_lut) cudaFree(s->d_neg_lut);
   if (s->d_pow_lut) cudaFree(s->d_pow_lut);
   dataset_unref(s->ds);
@@ -1175,6 +1187,11 @@ int ogb_sampler_create(ogb_dataset* ds, const ogb_config* cfg, int32_t kind, uin
   s->n_slots = kind == OGB_KIND_GC ? (cfg->trl ? ogb::GC_TRL_NUM_SLOTS : ogb::GC_NUM_SLOTS) : (kind == OGB_KIND_HGC ? ogb::HGC_NUM_SLOTS : 2);
   s->plan[0] = build_plan(s, false);
   s->plan[1] = build_plan(s, true);
+  if (!ab().static_tiles) {   // ticket counters of the row gathers, zeroed once: every launch leaves its pair at zero
+    if (cudaMalloc((void**)&s->d_sched, (size_t)ogb_sampler::kSchedSlots * 128) != cudaSuccess ||
+        cudaMemset(s->d_sched, 0, (size_t)ogb_sampler::kSchedSlots * 128) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+      return bail(fail(OGB_ERR_CUDA, "ticket counters: %s", cudaGetErrorString(cudaGetLastError())));
+  }
   *out = s;
   return 0;
 } OGB_CATCH_ALL
@@ -1878,7 +1895,25 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       const bool wraps = nk == ap.n_items;
       ap.items[k].flags |= (ap.items[wraps ? 0 : nk].slot << 8) | (wraps ? 0x10000u : 0u);
     }
-    ap.ring_offset = (int)round_up((size_t)ap.n_items * sizeof(ItemDesc) + (size_t)ap.n_outs * sizeof(OutDesc), 128);
+    // Dynamic tile scheduling: the ticket of the next tile is taken ahead of the item where the head needs the tile -- the
+    // fused kernel needs it when it leaves the tile, the un-fused one already at the first item of the last pair, where it
+    // prefetches the next tile's index vector (a single-pair un-fused launch keeps static tiles).  How far ahead, measured
+    // (profiles/r2_ab_shapes.txt, batch r2k): the fused launches (16 warps per SM) are best with one pair -- a ticket taken
+    // earlier keeps a tile away from a faster warp (C2 0.890 / 0.888 / 0.876 of peak for 1 / 2 / all pairs ahead); the
+    // un-fused gather with 8 warps per SM does not cover a late ticket's round trip through the busy memory system
+    // (C3 0.952 / 0.956 / 0.960 / 0.963 for 1 / 2 / 3 / all), while C5b's shape prefers <= 3 (1.021 vs 1.011) -> three.
+    std::vector<int> pair_first;
+    for (int k = 0; k < ap.n_items; ++k) if (ap.items[k].flags & 1u) pair_first.push_back(k);
+    const bool fused_here = fuse && q0 == 0;
+    bool dyn_tiles = s->d_sched != nullptr && (fused_here || pair_first.size() >= 2);
+    {
+      // index (into pair_first) of the pair at whose first item the tile is needed; the fused kernel needs it one pair "later"
+      const int need = (int)pair_first.size() - (fused_here ? 0 : 1);
+      const int ahead = ab().claim_pairs > 0 ? ab().claim_pairs : (fused_here ? 1 : 3);
+      ap.claim_item = pair_first[(size_t)std::max(0, need - ahead)];
+    }
+    // shared memory: item table, output table, one 16-byte tile FIFO per warp, then the rings
+    ap.ring_offset = (int)round_up((size_t)ap.n_items * sizeof(ItemDesc) + (size_t)ap.n_outs * sizeof(OutDesc) + (size_t)n_warps * 16, 128);
     const size_t smem = (size_t)ap.ring_offset + (size_t)n_warps * ap.ring_bytes;
     if (smem > (size_t)225 * 1024) return bail(fail(OGB_ERR_UNSUPPORTED, "gather shape %d needs %zu bytes of shared memory", shape, smem));
     // persistent grid: exactly the CTAs that are resident at once (shared memory bounds them here; the fused kernels are
@@ -1905,6 +1940,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
         f.relabel.row_end = f.gather.row_end = end;
+        f.gather.sched = dyn_tiles && !ws ? s->next_sched() : nullptr;
         const int64_t n_warp_tiles = (end - begin + 31) / 32;
         const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * ctas_per_sm);
         const void* fn = nullptr;
@@ -1945,6 +1981,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
       ap.row_begin = begin;
       ap.row_end = end;
+      ap.sched = dyn_tiles ? s->next_sched() : nullptr;
       const int64_t n_warp_tiles = (end - begin + 31) / 32;
       const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * resident);
       void* args[] = {(void*)&ap};

@@ -783,8 +783,9 @@ struct AsyncGatherParams {
   int32_t n_outs;              // outputs of all items
   int32_t stage_bytes;
   int32_t ring_bytes;          // kAsyncStages * stage_bytes
-  int32_t ring_offset;         // the per-warp rings start this far into dynamic shared memory (after the tables)
-  int32_t pad_;
+  int32_t ring_offset;         // the per-warp rings start this far into dynamic shared memory (after the tables and the tile FIFOs)
+  int32_t claim_item;          // dynamic tile scheduling: the item at whose issue a warp claims its next tile
+  uint32_t* sched;             // [0] tile tickets, [1] CTAs finished; nullptr: static round-robin tiles (see below)
   ItemDesc items[kMaxItems];
   OutDesc outs[kMaxItemOuts];
 };
@@ -927,10 +928,45 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
   const uint4* outs_s = items_s + n_items * (int)(sizeof(ItemDesc) / 16);
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(smem_dyn) + (uint32_t)p.ring_offset + (uint32_t)warp * (uint32_t)p.ring_bytes;
 
-  auto advance = [&](TileCursor& c) {
+  // Tile scheduling.  Every warp starts on the tile of its global index; after that it either strides by the number of
+  // warps (static) or -- p.sched != nullptr -- takes the next unclaimed tile from a global ticket counter.  The SMs do not
+  // run at one speed (a DRAM-bound launch shares HBM unevenly), so with static tiles the slowest SM sets the launch time;
+  // with tickets every warp is busy until the tiles run out (C2/C5: the fixed 8-19 us per launch of profiles/
+  // r2_launch_size.txt).  The ticket is asked for at item `claim_item`, one (tile, job) pair before the head needs it, so
+  // the atomic's round trip hides behind a pair's issue loop.  The tail cursor drains the same tile sequence a few items
+  // later: the warp keeps its claimed tiles in a four-entry FIFO in shared memory (the head is at most kStages - 1 tile
+  // boundaries ahead of the tail, plus the tile it has resolved but not entered).
+  const bool dyn = kMode != MODE_QUEUE && p.sched != nullptr;
+  const int32_t dyn_base = (int32_t)(p.row_begin >> 5) + n_warps_global;            // ticket t names tile dyn_base + t
+  const uint32_t fifo_u32 = (uint32_t)__cvta_generic_to_shared(smem_dyn) + (uint32_t)p.ring_offset - 16u * (uint32_t)(kWarps - warp);
+  uint32_t ticket = 0;                   // lane 0: the ticket in flight
+  int32_t head_next = 0;                 // the tile after the head's, once resolved
+  bool head_resolved = false;
+  uint32_t head_ord = 0, tail_ord = 0;   // ordinals of the head's and the tail's tile in this warp's sequence
+  auto resolve = [&]() {                 // wait for the ticket and publish the tile to the tail
+    head_next = dyn_base + (int32_t)__shfl_sync(0xffffffffu, ticket, 0);
+    head_resolved = true;
+    if (lane == 0) sts32(fifo_u32 + (((head_ord + 1u) & 3u) << 2), head_next);
+  };
+  auto advance_head = [&](TileCursor& c) {
     if (++c.k == n_items) {
       c.k = 0;
-      c.tile += n_warps_global;
+      if (dyn) {
+        if (!head_resolved) resolve();
+        c.tile = head_next;
+        head_resolved = false;
+        ++head_ord;
+      } else {
+        c.tile += n_warps_global;
+      }
+      c.n = c.tile == n_tiles - 1 ? last_n : 32;
+    }
+  };
+  auto advance_tail = [&](TileCursor& c) {
+    if (++c.k == n_items) {
+      c.k = 0;
+      if (dyn) c.tile = (int32_t)lds32(fifo_u32 + (((++tail_ord) & 3u) << 2));   // written before an earlier __syncwarp of the loop
+      else c.tile += n_warps_global;
       c.n = c.tile == n_tiles - 1 ? last_n : 32;
     }
   };
@@ -952,6 +988,7 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
     if (c.tile < n_tiles) {
       const uint4* it = items_s + c.k * (int)(sizeof(ItemDesc) / 16);
       const uint4 d0 = it[0], d1 = it[1], d2 = it[2];
+      if (dyn && c.k == p.claim_item && lane == 0) ticket = atomicAdd(p.sched, 1u);
       if (d2.z & 1u) {                                           // entering the next (tile, job) pair
         if (kMode == MODE_FUSED) {
           if (c.k == 0 && lane < c.n) relabel_row<kInject, kFlavour>(rp, SegView{rp.seg_bucket, rp.seg_table}, ((int64_t)c.tile << 5) + lane, sr);
@@ -969,7 +1006,12 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
           issue_rows = pick_slot<kSlots>(sr, (int)d1.w);
         } else {
           issue_rows = pref_rows;
-          pref_rows = load_rows((d2.z & 0x10000u) ? c.tile + n_warps_global : c.tile, (d2.z >> 8) & 0xffu);
+          int32_t pref_tile = c.tile;
+          if (d2.z & 0x10000u) {                                 // the pair after this one opens the warp's next tile
+            if (dyn) { resolve(); pref_tile = head_next; }
+            else pref_tile = c.tile + n_warps_global;
+          }
+          pref_rows = load_rows(pref_tile, (d2.z >> 8) & 0xffu);
         }
       }
       const uint32_t cpr = d0.w, stride16 = d0.z, dr = d1.y, dch = d1.z;
@@ -1036,7 +1078,7 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
 #pragma unroll 1
   for (int t = 0; tail.tile < n_tiles; ++t) {
     issue(head, ring_u32 + head_off);    // one cp.async group per iteration (empty once the head has run off the end)
-    if (head.tile < n_tiles) advance(head);
+    if (head.tile < n_tiles) advance_head(head);
     head_off += stage_bytes;
     if (head_off == ring_bytes) head_off = 0;
     if (t >= kStages - 1) {
@@ -1044,9 +1086,24 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
       __syncwarp();                        // ... for every lane of this warp
       drain(tail, ring_u32 + tail_off);
       __syncwarp();                        // the stage may be overwritten by the next issue
-      advance(tail);
+      advance_tail(tail);
       tail_off += stage_bytes;
       if (tail_off == ring_bytes) tail_off = 0;
+    }
+  }
+}
+
+// Dynamic tile scheduling leaves its two counters at zero for the next launch that is handed the same pair: the last
+// CTA to finish clears them (every ticket has been consumed by then -- a warp uses the value of its last ticket before
+// it leaves the loop).
+__device__ __forceinline__ void sched_release(uint32_t* sched) {
+  if (sched == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
     }
   }
 }
@@ -1060,6 +1117,7 @@ __global__ void __launch_bounds__(kWarps * 32, gather_min_blocks(kWarps)) gather
   stage_tables(p, smem_dyn);
   __syncthreads();
   gather_rows_async_body<MODE_VECTORS, false, FLAVOUR_PLAIN, kStages, kWarps>(p, *reinterpret_cast<const RelabelParams*>(&p), smem_dyn, QueueView{0, 0, 0});
+  sched_release(p.sched);
 }
 
 struct FusedParams {
@@ -1074,6 +1132,7 @@ __global__ void __launch_bounds__(kWarps * 32, gather_min_blocks(kWarps)) relabe
   stage_tables(p.gather, smem_dyn);
   __syncthreads();
   gather_rows_async_body<MODE_FUSED, kInject, kFlavour, kStages, kWarps>(p.gather, p.relabel, smem_dyn, QueueView{0, 0, 0});
+  sched_release(p.gather.sched);
 }
 
 // sample() in one launch, warp-specialised: warps [0, kAsyncWarps) gather, warps [kAsyncWarps, +kIndexWarps) run the
