@@ -72,9 +72,16 @@ def hbm_peak():
 
 
 def default_batches_per_launch(w):
-    # ~1M transitions per launch for vector workloads, 16 batches for the pixel workload: ~1.1 GB of output per launch
-    # in both cases (>> 126 MB L2)
-    return 16 if w.obs_dtype == 'uint8' else max(1, (1 << 20) // w.batch)
+    # A launch costs 8-19 us beyond its bytes (ramp-up and tail: profiles/r2_ab_shapes.txt, batch r2i), so a launch is sized
+    # to last ~1 ms: ~4M transitions for vector workloads (16M for rows of a few bytes, halved while one launch would move more
+    # than 9 GB), 64 batches for the pixel workload.  The line also reports the round-1 size (a quarter / a sixteenth of this)
+    # under `launch_size_sweep`.
+    if w.obs_dtype == 'uint8':
+        return 64
+    transitions = (16 << 20) if w.bytes_per_transition < 256 else (4 << 20)
+    while transitions * w.bytes_per_transition > 9e9:
+        transitions //= 2
+    return max(1, transitions // w.batch)
 
 
 def config_dict(key, L):
@@ -316,12 +323,13 @@ def measure_config(key, args, ctx, headline):
         torch.cuda.synchronize(local)
 
     def launch():
-        batch = sampler.sample_many(L, w.batch)                  # the public call: dict of DeviceArray, [L, B, ...] per key
+        batch = sampler.sample_many(cur_L[0], w.batch)           # the public call: dict of DeviceArray, [L, B, ...] per key
         handle = next(iter(batch.values()))._batch
         n = C.c_int32()
         lib.ogb_batch_launches(handle.ptr, C.byref(n))
         return handle, n.value
 
+    cur_L = [L]
     launches = 0
     dominant_ms = []
     dominant_name = C.c_char_p()
@@ -379,6 +387,30 @@ def measure_config(key, args, ctx, headline):
     per_step = w.batch * L
     value = dist_util.reduce_scalar(n_steps * per_step, 'sum', device=dev) / (elapsed_ms * 1e-3)
     resident = dataset.native(local).resident_bytes()
+
+    # ---- the same launch at a quarter and a sixteenth of the size (c2: 1024 = the round-1 launch, 256): short regions ----
+    sweep = []
+    if not os.environ.get('OGB_BENCH_NO_SWEEP'):
+        n_launches, n_kernel_ms = launches, len(dominant_ms)
+        for Ls in (max(1, L // 4), max(1, L // 16)):
+            if Ls == L:
+                continue
+            cur_L[0] = Ls
+            del run(5, False)[:]
+            barrier()
+            probe = dist_util.reduce_scalar(timed(10, False), 'max', device=dev)
+            n = 10 * max(1, int(np.ceil(60.0 / max(probe, 1e-3))))
+            barrier()
+            before = len(dominant_ms)
+            ms = dist_util.reduce_scalar(timed(n, True), 'max', device=dev) / n
+            k_ms = float(np.mean(dominant_ms[before:])) if len(dominant_ms) > before else ms
+            bytes_launch = w.bytes_per_transition * w.batch * Ls
+            sweep.append({'batches_per_launch': Ls, 'ms_per_step': ms, 'kernel_ms': k_ms, 'value': world * w.batch * Ls / (ms * 1e-3),
+                          'frac': bytes_launch / (k_ms * 1e-3) / 1e9 / hbm_peak()[0],
+                          'step_frac': bytes_launch / (ms * 1e-3) / 1e9 / hbm_peak()[0]})
+        cur_L[0] = L
+        launches = n_launches
+        del dominant_ms[n_kernel_ms:]
 
     # ---- end to end through the public API with host buffers ----
     e2e = None
@@ -463,6 +495,7 @@ def measure_config(key, args, ctx, headline):
                              'stream); step_frac = the same bytes / whole step time (index kernel and launch gaps included)'},
         'clocks': clocks.summary(),
         'gpu_launches': launches,
+        'launch_size_sweep': sweep,
         'notes': f'each step writes {out_bytes / 1e6:.0f} MB into one of three rotating output blocks and gathers random rows of a '
                  f'{resident / 1e6:.0f} MB resident dataset (L2 is 126 MB)'
                  + (f'; OGB_BENCH_EPISODES={episodes}: NOT the BASELINE shape' if episodes != w.episodes else ''),
