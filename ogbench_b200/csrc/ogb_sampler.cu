@@ -51,6 +51,7 @@ struct AbSwitches {
   int index_grid;        // OGB_INDEX_GRID=n    index kernel grid capped at n CTAs per SM instead of 16
   bool no_point;         // OGB_NO_POINT        point-maze records go through the generic tiny-field walk of the index kernel
   bool static_tiles;     // OGB_STATIC_TILES    row gathers walk their tiles with a fixed stride instead of taking tickets
+  bool no_wide_record;   // OGB_NO_WIDE_RECORD  point-maze kernel: two 128-bit loads of the record instead of one 256-bit load
   int claim_pairs;       // OGB_CLAIM_PAIRS=n   a tile's ticket is taken n (tile, job) pairs before it is needed (default: 1 fused, 3 un-fused)
 };
 
@@ -80,6 +81,7 @@ const AbSwitches& ab() {
     a.no_point = flag("OGB_NO_POINT");
     a.static_tiles = flag("OGB_STATIC_TILES");
     a.claim_pairs = number("OGB_CLAIM_PAIRS", 0);
+    a.no_wide_record = flag("OGB_NO_WIDE_RECORD");
     return a;
   }();
   return sw;
@@ -379,6 +381,7 @@ struct ogb_sampler {
   bool defer_index_check = false;        // host-output mode: given indices are range-checked by the kernel, the error
                                          // surfaces at ogb_batch_copy_to_host / ogb_batch_sync instead of at sample()
   bool prefer_ws = false;                // debug bit 2: use the warp-specialised fused kernel
+  bool static_tiles = false;             // debug bit 3: row gathers walk their tiles with a fixed stride (no ticket counter)
   bool canary = false;                   // debug: fill every batch block with 0xA5 first, so that tests can verify that
                                          // no kernel wrote outside the keys (ogb_batch_check_gaps)
   bool profile = false;                  // record timing events around the dominant kernel of every call
@@ -1229,6 +1232,7 @@ int ogb_sampler_set_debug(ogb_sampler* s, int32_t keep) try {
   s->debug = (keep & 1) != 0;
   s->canary = (keep & 2) != 0;
   s->prefer_ws = (keep & 4) != 0;
+  s->static_tiles = (keep & 8) != 0;
   return 0;
 } OGB_CATCH_ALL
 int ogb_sampler_num_choices(const ogb_sampler* s, int64_t* out) try {
@@ -1778,7 +1782,24 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     if (point_record && !smem_tables)
       // 48 registers, five CTAs per SM: 0.556 vs 0.541 of peak with four (six spill: 0.541), profiles/r2_ab_shapes.txt
       fn = inject ? (const void*)relabel_index_kernel<true, FLAVOUR_GC, false, true> : (const void*)relabel_index_kernel<false, FLAVOUR_GC, false, true, 5>;
-    int64_t grid_cap = (int64_t)ds->sm_count * (ab().index_grid > 0 ? ab().index_grid : 16);
+    if (point_record && smem_tables && !inject) fn = (const void*)relabel_index_kernel<false, FLAVOUR_GC, true, true, 5>;
+    p.wide_record = ab().no_wide_record ? 0 : 1;   // +1.2 % on C1 at 16M rows per launch (0.740 vs 0.731, batch r2l)
+    // Grid cap: a whole number of waves of resident CTAs (a 16-per-SM grid of the five-per-SM point-maze kernel is 3.2
+    // waves, and the last, fifth-full wave cost C1 5 %: 0.731 vs 0.771-0.775 of peak for 5, 10 or 32 per SM, batch r2l).
+    static std::mutex occ_mu;
+    static std::map<const void*, int> occ_cache;
+    int resident_index = 0;
+    {
+      std::lock_guard<std::mutex> occ_lock(occ_mu);
+      auto it = occ_cache.find(fn);
+      if (it == occ_cache.end()) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kRelabelThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        it = occ_cache.emplace(fn, per_sm).first;
+      }
+      resident_index = it->second;
+    }
+    int64_t grid_cap = (int64_t)ds->sm_count * (ab().index_grid > 0 ? ab().index_grid : 2 * resident_index);
     size_t smem = 0;
     if (smem_tables) {
       smem = table_bytes;
@@ -1905,7 +1926,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     std::vector<int> pair_first;
     for (int k = 0; k < ap.n_items; ++k) if (ap.items[k].flags & 1u) pair_first.push_back(k);
     const bool fused_here = fuse && q0 == 0;
-    bool dyn_tiles = s->d_sched != nullptr && (fused_here || pair_first.size() >= 2);
+    const bool dyn_tiles = s->d_sched != nullptr && !s->static_tiles && (fused_here || pair_first.size() >= 2);
     {
       // index (into pair_first) of the pair at whose first item the tile is needed; the fused kernel needs it one pair "later"
       const int need = (int)pair_first.size() - (fused_here ? 0 : 1);

@@ -175,6 +175,7 @@ struct RelabelParams {
   int32_t n_tiny;              // the first n_tiny_fast of them have rows of 4, 8 or 16 bytes
   int32_t n_tiny_fast;
   int32_t write_vecs;          // 0: no later kernel needs the index vectors (everything was tiny) and debug is off
+  int32_t wide_record;         // kPoint: fetch the 32-byte record with one 256-bit load (measurement switch OGB_WIDE_RECORD)
   TinyJob tiny[kMaxTinyJobs];
   int32_t n_tiny_groups;
   int32_t n_tiny_fields;
@@ -364,8 +365,15 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     if (kPoint ? u == 0 : (u < p.n_tiny_groups && p.tiny_groups[u].slot == SLOT_IDX)) {
       const TinyGroup& grp = p.tiny_groups[u];
       const uint4* sp = reinterpret_cast<const uint4*>(grp.src + (size_t)(uint32_t)i * grp.stride);
-      grp_a[u] = __ldg(sp);
-      if (kPoint || grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
+      if (kPoint && p.wide_record) {
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(grp_a[u].x), "=r"(grp_a[u].y), "=r"(grp_a[u].z), "=r"(grp_a[u].w), "=r"(grp_b[u].x), "=r"(grp_b[u].y),
+                       "=r"(grp_b[u].z), "=r"(grp_b[u].w)
+                     : "l"(sp));
+      } else {
+        grp_a[u] = __ldg(sp);
+        if (kPoint || grp.n_vec > 1) grp_b[u] = __ldg(sp + 1);
+      }
     }
   }
   // :82 clamps idx + 1 to size - 1; with frame stacking (:231) and for ATC (:408) the reference does not clamp, and a

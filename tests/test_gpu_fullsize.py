@@ -112,3 +112,24 @@ def test_full_size_given_idxs_and_many(key):
         draws, knife = philox_np.philox_draws(seed, stream_id, call, w.batch, n_choices, goal_sets_for(w.config, w.kind), True, 0.0)
         want = oracle.sample(w.batch, source=DrawsSource(draws))
         _compare({k: v[call] for k, v in many.items()}, want, rows_ok=~knife, tag=f'{key} many {call}')
+
+
+@pytest.mark.parametrize('key,K', [('c2', 160), ('c3', 96), ('c5', 40)])
+def test_many_tile_launch_bit_exact_vs_oracle(key, K):
+    """A launch with more 32-row tiles than the gather kernel has warps (C2/C5: 2,368 warps, C3: 1,184), so that most tiles
+    are handed out by the ticket counter: every batch of the launch against the oracle on the rebuilt Philox draws."""
+    from ogbench_b200 import Dataset, GCDataset, HGCDataset
+
+    w, fields = _fields(key)
+    cls = GCDataset if w.kind == 'gc' else HGCDataset
+    oracle = OracleSampler(fields, w.config, w.kind)
+    ds = Dataset.create(**fields)
+    seed, stream_id = 424242, 5
+    dev = cls(ds, w.config, seed=seed, stream_id=stream_id)
+    assert K * w.batch // 32 > 2 * (1184 if key == 'c3' else 2368)
+    many = to_host(dev.sample_many(K, w.batch))
+    n_choices = len(oracle.valid_table)
+    for call in range(K):
+        draws, knife = philox_np.philox_draws(seed, stream_id, call, w.batch, n_choices, goal_sets_for(w.config, w.kind), True, 0.0)
+        want = oracle.sample(w.batch, source=DrawsSource(draws))
+        _compare({k: v[call] for k, v in many.items()}, want, rows_ok=~knife, tag=f'{key} many-tile {call}')

@@ -450,3 +450,34 @@ def test_current_device_is_left_alone():
     gc.collect()                                      # batches and samplers of cuda:0 are released from a cuda:1 thread
     assert torch.cuda.current_device() == 1
     torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize('kind,obs_dim,K,B', [('gc', 29, 300, 1024), ('gc', 55, 97, 4096), ('hgc', 69, 150, 1024), ('gc', 29, 211, 1000)])
+def test_ticket_scheduled_tiles_equal_static_tiles(kind, obs_dim, K, B):
+    """Big launches hand their 32-row tiles to the warps through a ticket counter (relabel_rows.cuh, `sched`); debug bit 3
+    restores the fixed stride.  The two must return the same bytes: several thousand tiles per launch (more tiles than
+    warps, so tickets name real tiles), fused GC and un-fused HGC launches, a ragged last tile (211 x 1000 rows), launches
+    repeated so that the counters a launch leaves behind are reused, and the canary fill proving every byte of every key was
+    written exactly where it belongs."""
+    import ctypes as C
+    from ogbench_b200 import _native
+
+    lengths = ragged(31, 400, 30, 300)
+    fields = toy_fields(31, lengths, (obs_dim,), 8, np.float32)
+    config = cfg(subgoal_steps=7) if kind == 'hgc' else cfg()
+    a = device_sampler(fields, config, kind, seed=11)
+    b = device_sampler(fields, config, kind, seed=11)
+    a._sampler.set_debug(2)          # tickets + canary
+    b._sampler.set_debug(2 | 8)      # static tiles + canary
+    for rep in range(3):
+        ha = a._sampler.sample_native(B, n_batches=K)
+        hb = b._sampler.sample_native(B, n_batches=K)
+        for h in (ha, hb):
+            bad = C.c_int64(-1)
+            _native.check(_native.lib().ogb_batch_check_gaps(h.ptr, C.byref(bad)))
+            assert bad.value == 0
+        x, y = to_host(a._sampler.wrap(ha)), to_host(b._sampler.wrap(hb))
+        assert set(x) == set(y)
+        for k in x:
+            assert not (x[k].view(np.uint8) == 0xA5).all(), k
+            assert np.array_equal(x[k], y[k]), (k, rep)
