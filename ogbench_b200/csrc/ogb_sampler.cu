@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1321,9 +1322,37 @@ struct RunSpec {
   int crop_padding = -1;                 // >= 0: crop every image key with the injected shifts and this padding (augment())
 };
 
+// OGB_HOST_PHASES=1 (measurement switch): host time of run_sample by phase, summed over all calls, printed at exit.
+struct HostPhases {
+  static constexpr int kN = 7;
+  double ns[kN] = {0};
+  long calls = 0;
+  bool on = getenv("OGB_HOST_PHASES") != nullptr;
+  ~HostPhases() {
+    if (!on || calls == 0) return;
+    static const char* names[kN] = {"checks", "batch+layout", "block", "params", "classify", "prepare", "launch+event"};
+    fprintf(stderr, "[ogb host phases] %ld calls:", calls);
+    for (int i = 0; i < kN; ++i) fprintf(stderr, " %s %.2f us", names[i], ns[i] / calls * 1e-3);
+    fprintf(stderr, "\n");
+  }
+};
+HostPhases g_phases;
+struct PhaseClock {
+  std::chrono::steady_clock::time_point t;
+  int next = 0;
+  PhaseClock() { if (g_phases.on) t = std::chrono::steady_clock::now(); }
+  void mark() {
+    if (!g_phases.on) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (next < HostPhases::kN) g_phases.ns[next++] += std::chrono::duration<double, std::nano>(now - t).count();
+    t = now;
+  }
+};
+
 int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t n_batches, const int64_t* idxs, int32_t evaluation,
                const ogb_draws* draws, ogb_batch** out) {
   using namespace ogb;
+  PhaseClock phase;
   if (!s || !out) return fail(OGB_ERR_INVALID, "ogb_sampler_sample: null argument");
   if (batch_size < 0 || n_batches < 1) return fail(OGB_ERR_INVALID, "batch_size must be >= 0 and n_batches >= 1");
   if (draws && n_batches != 1) return fail(OGB_ERR_INVALID, "validation draws need n_batches == 1");
@@ -1380,6 +1409,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   DeviceGuard device_guard(ds->device);
   OGB_CUDA(device_guard.status);
   std::lock_guard<std::mutex> lock(s->mu);
+  phase.mark();   // checks
 
   const std::vector<KeyPlan>& plan = *spec.plan;
   bool any_frames = false;
@@ -1457,6 +1487,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     if (rc) return bail(rc);
   }
   cudaStream_t first = use_aux ? s->aux_stream : s->stream;
+  phase.mark();   // batch + layout
   {
     std::vector<cudaEvent_t> free_after;
     int rc = block_take(s, b->block_bytes, &b->block, &b->block_bytes, &free_after);
@@ -1468,6 +1499,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     if (rc) return bail(rc);
   }
   uint8_t* base = b->block;
+  phase.mark();   // block
   if (s->canary) {
     cudaMemsetAsync(base, 0xA5, b->block_bytes, first);
     if (first != s->stream) {   // the gathers on the main stream must not start before the fill has finished
@@ -1615,6 +1647,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       default: break;
     }
   }
+  phase.mark();   // params
   // ---- classify the vector-valued keys: tiny rows ride along in the index kernel, the rest go to a gather launch ----
   // A span job loads one contiguous piece of the source rows named by one index vector and feeds one output per key.
   // Fields of the packed record table that are gathered through the same index vector and lie next to each other
@@ -1749,6 +1782,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   // the index vectors only go to memory when a later launch (or the debug interface) reads them
   p.write_vecs = ((!fuse && any_async) || span_jobs.size() > (size_t)kMaxRowJobs || !lsu_keys.empty() || any_frames || s->debug) ? 1 : 0;
 
+  phase.mark();   // classify
   // ---- prepare every launch once; each is then issued per row chunk ----
   typedef std::function<int(int64_t, int64_t, cudaStream_t)> LaunchFn;
   std::vector<LaunchFn> gather_launches;
@@ -2155,6 +2189,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       cudaEventRecord(ev, st);
       g_timeline.push_back(ev);
     };
+    phase.mark();   // prepare
     // dominant kernel = the one that moves the batch's bytes: the frame gather, else the row gather (fused or not),
     // else the index kernel itself (datasets whose rows are all <= 16 bytes)
     b->dominant = any_frames ? "gather_frames_tma_kernel" : fused_launch ? fused_name
@@ -2208,6 +2243,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     return bail(fail(OGB_ERR_CUDA, "ready event failed"));
   if (!draws) s->counter += (uint64_t)n_batches;
   *out = b;
+  phase.mark();   // launch + event
+  if (g_phases.on) ++g_phases.calls;
   return 0;
 }
 
