@@ -200,7 +200,11 @@ int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms); /* th
                                                                      profile mode, its device time (host-waits for it); else -1 */
 int ogb_batch_sync(ogb_batch* b);                                 /* host-wait for the batch to be ready */
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream);/* make a consumer stream wait (DLPack protocol) */
-int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return */
+int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return (= begin + end) */
+int ogb_batch_copy_to_host_begin(ogb_batch* b, void* dst, size_t nbytes); /* enqueue that copy on the sampler's copy stream (behind the
+                                                                     batch's kernels) and return: copies begun one after the other
+                                                                     run back to back; `dst` (pinned) must stay valid until _end */
+int ogb_batch_copy_to_host_end(ogb_batch* b);                     /* host-wait for the begun copy; raises the deferred index error */
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes); /* one key, D2H, synchronous */
 int ogb_batch_copy_slice_to_host(ogb_batch* b, int32_t i, int64_t batch_index, void* dst, size_t nbytes); /* one batch of one key */
 int ogb_batch_index_vector(ogb_batch* b, int32_t slot, int64_t* dst_host); /* debug: needs set_debug(1) */

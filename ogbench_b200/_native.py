@@ -112,6 +112,8 @@ SIGNATURES = [
     ('ogb_batch_sync', C.c_int, [_P]),
     ('ogb_batch_wait_on_stream', C.c_int, [_P, _P]),
     ('ogb_batch_copy_to_host', C.c_int, [_P, _P, C.c_size_t]),
+    ('ogb_batch_copy_to_host_begin', C.c_int, [_P, _P, C.c_size_t]),
+    ('ogb_batch_copy_to_host_end', C.c_int, [_P]),
     ('ogb_batch_copy_key_to_host', C.c_int, [_P, C.c_int32, _P, C.c_size_t]),
     ('ogb_batch_copy_slice_to_host', C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_size_t]),
     ('ogb_batch_check_gaps', C.c_int, [_P, _P]),

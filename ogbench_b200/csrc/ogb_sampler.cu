@@ -417,6 +417,9 @@ struct ogb_sampler {
   // Ticket counters of the row gathers' dynamic tile scheduling (relabel_rows.cuh): kSchedSlots pairs, one 128-byte line
   // each, handed out round-robin per launch.  A launch leaves its pair at zero, and launches of one stream run one after
   // the other, so a pair is only ever shared by launches that are kSchedSlots launches apart.
+  int32_t* h_flags = nullptr;                  // pinned ring for the deferred index flags of copies in flight
+  uint32_t flag_seq = 0;
+  static constexpr int kFlagSlots = 64;
   static constexpr int kSchedSlots = 64;
   uint32_t* d_sched = nullptr;
   uint32_t sched_seq = 0;
@@ -455,6 +458,8 @@ struct ogb_batch {
   cudaEvent_t prof_begin = nullptr, prof_end = nullptr;   // profile mode: brackets of the dominant kernel
   const char* dominant = "";                               // its name
   cudaEvent_t ready = nullptr;
+  cudaEvent_t copied = nullptr;                            // ogb_batch_copy_to_host_begin: the D2H copy of the block has finished
+  volatile int32_t* h_idx_flag = nullptr;                  // ... and where the deferred index flag lands (pinned, sampler-owned)
   std::vector<cudaStream_t> consumers;
   bool main_stream_consumer = false;  // somebody took the batch on the sampler's own stream
   bool escaped = false;               // a raw pointer left through __cuda_array_interface__: consumers unknown
@@ -566,6 +571,7 @@ void sampler_unref(ogb_sampler* s) {
   if (s->d_seg_table) cudaFree(s->d_seg_table);
   if (s->d_seg_bucket) cudaFree(s->d_seg_bucket);
   if (s->d_sched) cudaFree(s->d_sched);
+  if (s->h_flags) cudaFreeHost(s->h_flags);
   if (s->d_neg_lut) cudaFree(s->d_neg_lut);
   if (s->d_pow_lut) cudaFree(s->d_pow_lut);
   dataset_unref(s->ds);
@@ -586,6 +592,7 @@ void batch_unref(ogb_batch* b) {
     if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
   }
   for (cudaEvent_t ev : b->chunk_done) cudaEventDestroy(ev);
+  if (b->copied) free_after.push_back(b->copied);   // a copy begun and never ended still reads the block
   if (b->prof_begin) cudaEventDestroy(b->prof_begin);
   if (b->prof_end) cudaEventDestroy(b->prof_end);
   if (b->escaped) cudaDeviceSynchronize();
@@ -2626,16 +2633,31 @@ int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream) try {
   if (std::find(b->consumers.begin(), b->consumers.end(), c) == b->consumers.end()) b->consumers.push_back(c);
   return 0;
 } OGB_CATCH_ALL
-int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
+// D2H of the whole block in two calls.  `begin` only enqueues: the copy runs on a stream of its own behind the batch's
+// `ready` event, not on the sampler's stream, so a caller that has already launched the NEXT batch gets that launch's
+// upload and kernels under this copy instead of behind it -- and copies begun one after the other queue back to back on
+// the copy engine (Prefetcher: launch k+1 and begin its copy, then end copy k).  `end` host-waits and reports the
+// deferred index check.
+int ogb_batch_copy_to_host_begin(ogb_batch* b, void* dst, size_t nbytes) try {
   if (!b || !dst) return fail(OGB_ERR_INVALID, "null argument");
   if (nbytes < b->keys_bytes) return fail(OGB_ERR_INVALID, "host buffer too small: %zu < %zu", nbytes, b->keys_bytes);
+  if (b->copied) return fail(OGB_ERR_INVALID, "a copy of this batch has already been begun");
   ogb_sampler* s = b->sampler;
   DeviceGuard device_guard(s->ds->device);
   OGB_CUDA(device_guard.status);
+  std::lock_guard<std::mutex> lock(s->mu);
+  if (!s->copy_stream) OGB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (b->idx_error) {
+    if (!s->h_flags) {
+      OGB_CUDA(cudaHostAlloc((void**)&s->h_flags, sizeof(int32_t) * ogb_sampler::kFlagSlots, cudaHostAllocDefault));
+      memset(s->h_flags, 0, sizeof(int32_t) * ogb_sampler::kFlagSlots);
+    }
+    b->h_idx_flag = s->h_flags + (s->flag_seq++ % ogb_sampler::kFlagSlots);
+    *b->h_idx_flag = 0;
+  }
   if (b->chunk_done.size() > 1) {
-    // pipelined: chunk c's rows of every key travel as soon as chunk c's kernels are done, on a stream of their own,
-    // while the kernels of chunk c+1 are still running
-    if (!s->copy_stream) OGB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    // pipelined: chunk c's rows of every key travel as soon as chunk c's kernels are done, while the kernels of chunk
+    // c+1 are still running
     int64_t begin = 0;
     for (size_t c = 0; c < b->chunk_done.size(); ++c) {
       const int64_t end = b->chunk_end[c];
@@ -2647,23 +2669,33 @@ int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
       }
       begin = end;
     }
-    int32_t chunk_flag = 0;   // the deferred index check covers chunked launches too (every chunk's kernels are done by now)
-    if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&chunk_flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
-    OGB_CUDA(cudaStreamSynchronize(s->copy_stream));
-    if (chunk_flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
-    return 0;
+  } else {
+    OGB_CUDA(cudaStreamWaitEvent(s->copy_stream, b->ready, 0));
+    OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
   }
-  // The copy runs on a stream of its own behind the batch's `ready` event, not on the sampler's stream: a caller that has
-  // already launched the NEXT batch (Prefetcher: launch k+1, then copy k) gets that launch's upload and kernels under
-  // this copy instead of behind it.
-  if (!s->copy_stream) OGB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  OGB_CUDA(cudaStreamWaitEvent(s->copy_stream, b->ready, 0));
-  OGB_CUDA(cudaMemcpyAsync(dst, b->block, b->keys_bytes, cudaMemcpyDeviceToHost, s->copy_stream));
-  int32_t flag = 0;
-  if (b->idx_error) OGB_CUDA(cudaMemcpyAsync(&flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
-  OGB_CUDA(cudaStreamSynchronize(s->copy_stream));
-  if (flag) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
+  // (the deferred index check covers chunked launches too: every chunk's kernels are done by the time this copy runs)
+  if (b->idx_error) OGB_CUDA(cudaMemcpyAsync((void*)b->h_idx_flag, b->idx_error, 4, cudaMemcpyDeviceToHost, s->copy_stream));
+  OGB_CUDA(cudaEventCreateWithFlags(&b->copied, cudaEventDisableTiming));
+  OGB_CUDA(cudaEventRecord(b->copied, s->copy_stream));
   return 0;
+} OGB_CATCH_ALL
+int ogb_batch_copy_to_host_end(ogb_batch* b) try {
+  if (!b) return fail(OGB_ERR_INVALID, "null argument");
+  if (!b->copied) return fail(OGB_ERR_INVALID, "no copy of this batch has been begun");
+  ogb_sampler* s = b->sampler;
+  DeviceGuard device_guard(s->ds->device);
+  OGB_CUDA(device_guard.status);
+  OGB_CUDA(cudaEventSynchronize(b->copied));
+  cudaEventDestroy(b->copied);
+  b->copied = nullptr;
+  const bool bad = b->h_idx_flag != nullptr && *b->h_idx_flag != 0;
+  b->h_idx_flag = nullptr;
+  if (bad) return fail(OGB_ERR_INDEX, "an index is out of bounds for axis 0 with size %lld", (long long)s->ds->size);
+  return 0;
+} OGB_CATCH_ALL
+int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes) try {
+  const int rc = ogb_batch_copy_to_host_begin(b, dst, nbytes);
+  return rc ? rc : ogb_batch_copy_to_host_end(b);
 } OGB_CATCH_ALL
 int ogb_batch_copy_key_to_host(ogb_batch* b, int32_t i, void* dst, size_t nbytes) try {
   if (!b || !dst || i < 0 || i >= (int32_t)b->keys.size()) return fail(OGB_ERR_INVALID, "bad argument");

@@ -519,17 +519,20 @@ class _Sampler:
         _native.check(lib.ogb_batch_nbytes(handle.ptr, C.byref(nbytes)))
         return (max(nbytes.value, 1), keys)
 
-    def wrap(self, handle: BatchHandle, layout_key=None) -> Dict[str, Any]:
-        """Batch handle -> dict of arrays.  The layout of a batch's block (name, dtype, shape, offset of every key) is a
-        function of the call's shape only, so it is read once per (batch_size, n_batches, evaluation, ...) and reused:
-        a steady-state call crosses the C boundary once or twice, not once per key."""
-        lib = _native.lib()
+    def _layout(self, handle: BatchHandle, layout_key):
         layout = self._layouts.get(layout_key) if layout_key is not None else None
         if layout is None:
             layout = self._read_layout(handle)
             if layout_key is not None:
                 self._layouts[layout_key] = layout
-        total, keys = layout
+        return layout
+
+    def wrap(self, handle: BatchHandle, layout_key=None, begun_block=None) -> Dict[str, Any]:
+        """Batch handle -> dict of arrays.  The layout of a batch's block (name, dtype, shape, offset of every key) is a
+        function of the call's shape only, so it is read once per (batch_size, n_batches, evaluation, ...) and reused:
+        a steady-state call crosses the C boundary once or twice, not once per key."""
+        lib = _native.lib()
+        total, keys = self._layout(handle, layout_key)
         if self.output == 'device':
             base = C.c_void_p()
             _native.check(lib.ogb_batch_device_block(handle.ptr, C.byref(base)))
@@ -537,8 +540,13 @@ class _Sampler:
             out = {name: DeviceArray(handle, i, name, dtype, shape, base + off, nb) for i, (name, dtype, shape, off, nb) in enumerate(keys)}
             return _nest(out) if self.nested else out
         # output == 'numpy': one D2H copy of the whole block into pinned memory, keys are views into it
-        block = _PINNED.take(total)
-        _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
+        # (launch() may have begun the copy already: copies begun one after the other run back to back on the copy stream)
+        if begun_block is None:
+            block = _PINNED.take(total)
+            _native.check(lib.ogb_batch_copy_to_host(handle.ptr, C.c_void_p(block.ptr), block.bucket))
+        else:
+            block = begun_block
+            _native.check(lib.ogb_batch_copy_to_host_end(handle.ptr))
         raw = (C.c_ubyte * total).from_address(block.ptr)
         raw._owner = block  # numpy views -> ctypes buffer -> pinned block: returned to the pool when all views die
         flat = np.frombuffer(raw, dtype=np.uint8)
@@ -551,7 +559,14 @@ class _Sampler:
         if keep_axis:
             _native.check(_native.lib().ogb_batch_keep_leading_axis(handle.ptr, 1))
         n_rows = len(idxs) // int(n_batches) if idxs is not None else int(batch_size)
-        return PendingBatch(self, handle, ('sample', n_rows, int(n_batches), bool(evaluation), bool(keep_axis)))
+        layout_key = ('sample', n_rows, int(n_batches), bool(evaluation), bool(keep_axis))
+        block = None
+        if self.output != 'device':
+            # the device-to-host copy is queued behind the launch right away (on the copy stream); result() waits for it
+            total, _ = self._layout(handle, layout_key)
+            block = _PINNED.take(total)
+            _native.check(_native.lib().ogb_batch_copy_to_host_begin(handle.ptr, C.c_void_p(block.ptr), block.bucket))
+        return PendingBatch(self, handle, layout_key, block)
 
     def sample(self, batch_size, idxs=None, evaluation=False, draws=None, n_batches=1, keep_axis=False):
         handle = self.sample_native(batch_size, n_batches, idxs, evaluation, draws)
@@ -636,19 +651,31 @@ def _crop_array(arr, crop_froms, padding, device, output):
 class PendingBatch:
     """A batch whose kernels have been launched; `result()` returns the dict `sample()` would have returned.
 
-    With output='numpy' the device-to-host copy happens in `result()`, on a stream of its own: launching the next batch
-    before asking for this one's result puts that launch (index upload, kernels) under this copy (what Prefetcher does)."""
+    With output='numpy' the device-to-host copy is queued behind the kernels at launch time, on a stream of its own
+    (`ogb_batch_copy_to_host_begin`), and `result()` waits for it: launching the next batch before asking for this one's
+    result puts that launch (index upload, kernels) under this copy, and its copy directly behind this one on the copy
+    engine (what Prefetcher does)."""
 
-    __slots__ = ('_sampler', '_handle', '_layout_key', '_result')
+    __slots__ = ('_sampler', '_handle', '_layout_key', '_result', '_block')
 
-    def __init__(self, sampler, handle, layout_key):
+    def __init__(self, sampler, handle, layout_key, block=None):
         self._sampler, self._handle, self._layout_key, self._result = sampler, handle, layout_key, None
+        self._block = block      # output='numpy': the pinned block a begun device-to-host copy is writing into
 
     def result(self):
         if self._result is None:
-            self._result = self._sampler.wrap(self._handle, self._layout_key)
-            self._handle = None
+            handle, block = self._handle, self._block
+            self._handle = self._block = None
+            self._result = self._sampler.wrap(handle, self._layout_key, block)
         return self._result
+
+    def __del__(self):
+        # a copy that was begun and never asked for must finish before its pinned block goes back to the pool
+        if getattr(self, '_block', None) is not None and self._handle is not None:
+            try:
+                _native.lib().ogb_batch_copy_to_host_end(self._handle.ptr)
+            except Exception:
+                pass
 
 
 class _Lookahead:

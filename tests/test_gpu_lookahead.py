@@ -148,3 +148,36 @@ def test_prefetcher_pipelines_given_idxs_and_multi_batch_items(output):
     _same(to_host(a.result()), to_host(direct.sample(B)), 'async 0')
     _same(to_host(b.result()), to_host(direct.sample(B, evaluation=True)), 'async 1')
     assert a.result() is a.result()
+
+
+def test_begun_host_copies_queue_and_report():
+    """output='numpy' + sample_async: the device-to-host copy is begun at launch time (ogb_batch_copy_to_host_begin) and
+    ended by result().  Several copies begun before any is ended return the batches direct calls return, in any result()
+    order; a pending batch dropped without result() leaves the sampler (and the pinned pool) usable; an index outside the
+    table surfaces as IndexError from result() (deferred check), and the sampler keeps working after it."""
+    import gc
+
+    fields = toy_fields(77, ragged(77, 120, 4, 60), (21,), 5, np.float32)
+    config = cfg()
+    valid = np.nonzero(fields['valids'] > 0)[0]
+    direct = device_sampler(fields, config, 'gc', seed=3, output='numpy')
+    ahead = device_sampler(fields, config, 'gc', seed=3, output='numpy')
+    pend = [ahead.sample_async(96) for _ in range(5)]
+    want = [direct.sample(96) for _ in range(5)]
+    for i in (3, 0, 4, 1, 2):
+        _same(pend[i].result(), want[i], i)
+    # dropped without result(): the copy is waited for before its pinned block is recycled
+    dropped = ahead.sample_async(96, num_batches=40)
+    del dropped
+    gc.collect()
+    direct.sample_many(40, 96)
+    _same(ahead.sample(50), direct.sample(50), 'after drop')
+    # deferred index check
+    n = len(fields['terminals'])
+    bad = np.array([valid[0], n + 5, valid[1]], dtype=np.int64)
+    p = ahead.sample_async(3, idxs=bad)
+    with pytest.raises(IndexError):
+        p.result()
+    direct.sample(3, idxs=valid[:3].astype(np.int64))      # (the failed launch advanced the Philox counter by one call)
+    good = valid[:7].astype(np.int64)
+    _same(ahead.sample_async(7, idxs=good).result(), direct.sample(7, idxs=good), 'after error')
