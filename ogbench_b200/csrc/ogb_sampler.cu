@@ -47,7 +47,7 @@ struct AbSwitches {
   int stage_bytes;       // OGB_STAGE_BYTES=n   per-warp stage budget instead of 4096 / 6144
   int ws;                // OGB_WS=0|1          warp-specialised fused kernel off / on (-1: ogb_sampler_set_debug decides)
   bool timeline;         // OGB_TIMELINE        record an event per phase for ogb_debug_timeline
-  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (default: 216 for the fused GCDataset launch, 308 otherwise; also 208, 316, 220)
+  int gather_shape;      // OGB_GATHER_SHAPE=SWW  stages * 100 + warps per CTA of the row-gather kernels (default: 220 for the fused GCDataset launch, 310 / 308 otherwise; also 208, 216, 316)
   bool no_shadow;        // OGB_NO_SHADOW       no shadow copy of the next row's observation inside the records
   int index_grid;        // OGB_INDEX_GRID=n    index kernel grid capped at n CTAs per SM instead of 16
   bool no_point;         // OGB_NO_POINT        point-maze records go through the generic tiny-field walk of the index kernel
@@ -1895,15 +1895,22 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     size_t stage = 0;
     for (size_t t = q0; t < q1; ++t) stage = std::max(stage, rows_for(span_jobs[t].bytes) * span_jobs[t].bytes);
     ap.stage_bytes = (int)round_up(stage, 128);
-    // (stages, warps per CTA): 3 x 8 built in; the alternatives are compiled for the GCDataset fused launch and the
-    // un-fused gather only (OGB_GATHER_SHAPE, measurement switch)
-    // Measured on B200 (profiles/r2_ab_shapes.txt): the fused GCDataset launch runs 4 % (C2) / 2 % (C5) faster as ONE CTA of
-    // 16 warps with two stages per warp (128 KB of shared memory, the rest of the SM's 228 KB stays L1 for the index
-    // algebra's table lookups) than as two CTAs of 8 warps with three stages; the un-fused gather (C3, 6 KB stages) is
-    // 3-6 % faster with three stages.  So: fused GC Philox launches 2 x 16, everything else 3 x 8.
+    // (stages, warps per CTA): 3 x 8 built in (two CTAs per SM); the alternatives are compiled for the GCDataset fused
+    // launch and the un-fused gather only (OGB_GATHER_SHAPE=SWW overrides, measurement switch).
+    // Measured on B200 (profiles/r2_ab_shapes.txt).  Fused GCDataset launch: ONE CTA of 20 warps with two stages per warp
+    // (160 KB of shared memory with 4 KB stages) -- 2 x 16 had beaten 3 x 8 x 2 CTAs by 4 % (C2) / 2 % (C5) with static
+    // tiles; with ticket-scheduled tiles and ~1 ms launches 2 x 20 is another 4 % ahead on C2 (0.945-0.961 vs 0.908-0.927
+    // of peak; five warps per scheduler instead of four) and level on C5 (0.950 vs 0.943-0.951); 18, 22 or 24 warps lose
+    // 4-13 % (uneven warps per scheduler, and a register cap that makes the index algebra spill).  Un-fused gather: three
+    // stages; with 6 KB stages (rows > 256 B: C3) ten warps in one CTA, 0.979 vs 0.964 for eight (twelve: 0.968).
     int shape = ab().gather_shape;
     const bool fused_gc = fuse && q0 == 0 && p.kind == OGB_KIND_GC && draws == nullptr;
-    if (shape != 308 && shape != 208 && shape != 216 && shape != 316 && shape != 220) shape = fused_gc ? 216 : 308;
+    const bool known = shape == 308 || shape == 208 || shape == 216 || shape == 316 || shape == 220 || shape == 310;
+    if (!known) {
+      if (fused_gc) shape = (size_t)20 * 2 * ap.stage_bytes <= (size_t)200 * 1024 ? 220 : 216;
+      else shape = (!(fuse && q0 == 0) && ap.stage_bytes > 4096 && (size_t)10 * 3 * ap.stage_bytes <= (size_t)200 * 1024) ? 310 : 308;
+    }
+    if (shape == 310 && fuse && q0 == 0) shape = 308;   // (un-fused only)
     if (shape != 308 && fuse && q0 == 0 && !fused_gc) shape = 308;
     const int n_stages = shape / 100, n_warps = shape % 100;
     ap.ring_bytes = n_stages * ap.stage_bytes;
@@ -2035,6 +2042,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
                           : shape == 216 ? (const void*)gather_rows_async_kernel<2, 16>
                           : shape == 316 ? (const void*)gather_rows_async_kernel<3, 16>
                           : shape == 220 ? (const void*)gather_rows_async_kernel<2, 20>
+                          : shape == 310 ? (const void*)gather_rows_async_kernel<3, 10>
                                          : (const void*)gather_rows_async_kernel<kAsyncStages, kAsyncWarps>;
     OGB_CUDA(cudaFuncSetAttribute(gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resident = 0;   // CTAs of this kernel that fit one SM (registers and shared memory): the persistent grid is exactly that
