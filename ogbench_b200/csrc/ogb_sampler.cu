@@ -1901,7 +1901,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     // (160 KB of shared memory with 4 KB stages) -- 2 x 16 had beaten 3 x 8 x 2 CTAs by 4 % (C2) / 2 % (C5) with static
     // tiles; with ticket-scheduled tiles and ~1 ms launches 2 x 20 is another 4 % ahead on C2 (0.945-0.961 vs 0.908-0.927
     // of peak; five warps per scheduler instead of four) and level on C5 (0.950 vs 0.943-0.951); 18, 22 or 24 warps lose
-    // 4-13 % (uneven warps per scheduler, and a register cap that makes the index algebra spill).  Un-fused gather: three
+    // 4-13 % (uneven warps per scheduler, and a register cap that makes the index algebra spill; 24 warps with the index
+    // algebra out of line, to keep the loops under the 80-register cap, lost 25 %).  Un-fused gather: three
     // stages; with 6 KB stages (rows > 256 B: C3) ten warps in one CTA, 0.979 vs 0.964 for eight (twelve: 0.968).
     int shape = ab().gather_shape;
     const bool fused_gc = fuse && q0 == 0 && p.kind == OGB_KIND_GC && draws == nullptr;
