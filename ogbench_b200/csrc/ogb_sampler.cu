@@ -2010,9 +2010,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
         f.relabel.row_end = f.gather.row_end = end;
-        f.gather.sched = dyn_tiles && !ws ? s->next_sched() : nullptr;
         const int64_t n_warp_tiles = (end - begin + 31) / 32;
         const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * ctas_per_sm);
+        // (tickets only when there are more tiles than warps: a small launch gives every warp at most its first tile)
+        f.gather.sched = dyn_tiles && !ws && n_warp_tiles > (int64_t)grid * n_warps ? s->next_sched() : nullptr;
         const void* fn = nullptr;
 #define OGB_PICK_FUSED(KERNEL, INJ)                                                      \
         fn = flavour == FLAVOUR_GC ? (const void*)KERNEL<INJ, FLAVOUR_GC>                   \
@@ -2052,9 +2053,9 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
     gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
       ap.row_begin = begin;
       ap.row_end = end;
-      ap.sched = dyn_tiles ? s->next_sched() : nullptr;
       const int64_t n_warp_tiles = (end - begin + 31) / 32;
       const unsigned grid = (unsigned)std::min<int64_t>((n_warp_tiles + n_warps - 1) / n_warps, (int64_t)ds->sm_count * resident);
+      ap.sched = dyn_tiles && n_warp_tiles > (int64_t)grid * n_warps ? s->next_sched() : nullptr;
       void* args[] = {(void*)&ap};
       if (cudaLaunchKernel(gather_fn, dim3(grid), dim3((unsigned)n_warps * 32), args, smem, st) != cudaSuccess)
         return fail(OGB_ERR_CUDA, "gather_rows_async_kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
