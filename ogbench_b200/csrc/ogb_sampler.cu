@@ -1778,7 +1778,10 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
   // The point-maze record (relabel_row<..., kPoint>): one group of the transition's own 32-byte record holding
   // observations f32[2] | actions f32[2] | terminals | valids | shadow next observation, and the two 8-byte goal rows;
   // nothing else to gather.  The index kernel then runs with these copies compiled in.
+  // (the kernel also compiles out what such a launch cannot need: index vectors in memory -- no later kernel, debug off --,
+  // frame-stack rows, the SLOT_NEXT row, the TRL branch, and every valid-row form but the segment table)
   bool point_record = !ab().no_point && spec.kind == OGB_KIND_GC && !spec.trl && !any_async && lsu_keys.empty() && !any_frames &&
+                      !s->debug && p.valid_mode == 3 && p.vec_init == nullptr &&
                       p.n_tiny_groups == 1 && p.n_tiny_fields == 5 && p.n_tiny == 2 && p.n_tiny_fast == 2 &&
                       p.tiny_groups[0].slot == SLOT_IDX && p.tiny_groups[0].n_vec == 2 &&
                       p.tiny[0].slot == GC_VALUE_GOAL && p.tiny[0].row_bytes == 8 && p.tiny[1].slot == GC_ACTOR_GOAL && p.tiny[1].row_bytes == 8;

@@ -230,9 +230,9 @@ __device__ __noinline__ int32_t valid_row_general(const RelabelParams& p, int64_
   return j + lower_bound_bucketed(p.gap_c, p.gap_bucket, p.gap_shift, j + 1);  // upper_bound(c, j)
 }
 
-template <bool kSmemTables>
+template <bool kSmemTables, bool kSegOnly = false>
 __device__ __forceinline__ int32_t valid_row(const RelabelParams& p, const SegView& seg, int64_t pos) {
-  if (p.valid_mode == 3) { int32_t unused; return valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, unused); }
+  if (kSegOnly || p.valid_mode == 3) { int32_t unused; return valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, unused); }
   return valid_row_general(p, pos);
 }
 
@@ -243,14 +243,14 @@ __device__ __forceinline__ int32_t uniform_future_goal(int32_t i, int32_t fin, d
 }
 
 // Validation mode: the reference's own draws (float64 uniforms, int64 offsets) decide.
-template <bool kSmemTables>
+template <bool kSmemTables, bool kSegOnly = false>
 __device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, const SegView& seg, const int gs, const int32_t i,
                                                       const int32_t fin, const int64_t g) {
   const GoalSpec& s = p.goal[gs];
   if (s.cur_only) return i;                                  // p_curgoal == 1.0  (datasets.py:317-318)
   const GoalInject& in = p.in_goal[gs];
   if (in.u_cur[g] < s.p_cur) return i;                       // np.where(rand < p_cur, idxs, ...)  :325
-  if (!(in.u_traj[g] < s.thr_traj)) return valid_row<kSmemTables>(p, seg, in.rand_pos[g]);   // random goal  :303,:320-322
+  if (!(in.u_traj[g] < s.thr_traj)) return valid_row<kSmemTables, kSegOnly>(p, seg, in.rand_pos[g]);   // random goal  :303,:320-322
   if (s.geom) {                                              // :309-310
     const int64_t t = (int64_t)i + in.offset[g];
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
@@ -260,13 +260,13 @@ __device__ __forceinline__ int32_t pick_goal_injected(const RelabelParams& p, co
 
 // Philox mode: `mix` = (u_traj, u_cur) as 32-bit words, `bits` = the 64 random bits of this goal set, spent either
 // on the random-goal position or on the geometric / distance uniform -- never both, since the mix decides first.
-template <bool kSmemTables>
+template <bool kSmemTables, bool kSegOnly = false>
 __device__ __forceinline__ int32_t pick_goal_philox(const RelabelParams& p, const SegView& seg, const int gs, const int32_t i,
                                                     const int32_t fin, const uint2 mix, const uint2 bits) {
   const GoalSpec& s = p.goal[gs];
   if (s.cur_only) return i;
   if (s.cur_always || mix.y < s.thr_cur32) return i;
-  if (!(s.traj_always || mix.x < s.thr_traj32)) return valid_row<kSmemTables>(p, seg, bounded_u32n(bits.x, bits.y, (uint32_t)p.n_choices));
+  if (!(s.traj_always || mix.x < s.thr_traj32)) return valid_row<kSmemTables, kSegOnly>(p, seg, bounded_u32n(bits.x, bits.y, (uint32_t)p.n_choices));
   if (s.geom) {
     const int64_t t = (int64_t)i + geometric_from_words(bits.x, bits.y, s.log_1mp, s.geo_abs_margin);
     return (int32_t)(t < (int64_t)fin ? t : (int64_t)fin);
@@ -291,8 +291,12 @@ __device__ __noinline__ int32_t trajectory_first_row(const RelabelParams& p, int
   return t == 0 ? 0 : __ldg(p.term + t - 1) + 1;
 }
 
+// kLean (the point-maze kernel): the host has checked that no later kernel reads the index vectors and that there is no
+// frame stacking, so the two stores and their parameter loads are compiled out.
+template <bool kLean = false>
 __device__ __forceinline__ void put_slot(const RelabelParams& p, int32_t* sr, const int slot, const int64_t g, const int32_t x) {
   sr[slot] = x;  // `slot` is a compile-time constant at every call site, so sr[] stays in registers
+  if (kLean) return;
   if (p.write_vecs) p.vec_rows[(int64_t)slot * p.total_rows + g] = x;
   if (p.vec_init != nullptr) p.vec_init[(int64_t)slot * p.total_rows + g] = trajectory_first_row(p, x);
 }
@@ -350,10 +354,10 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
     }
   } else {
     const int64_t pos = kInject ? p.in_idx_pos[g] : (int64_t)bounded_u32n(w0.x, w0.y, (uint32_t)p.n_choices);
-    if (p.valid_mode == 3) i = valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe
+    if (kPoint || p.valid_mode == 3) i = valid_row_fast<kSmemTables>(p, seg, (uint32_t)pos, fin);  // datasets.py:65-70 and :306 in one probe
     else i = valid_row<kSmemTables>(p, seg, pos);
   }
-  put_slot(p, sr, SLOT_IDX, g, i);
+  put_slot<kPoint>(p, sr, SLOT_IDX, g, i);
   // Grouped tiny fields of the transition's own record (observations, actions, terminals, valids of a point-maze row,
   // plus the shadow copy of the next row's observation): fetched NOW, so the load flies under the goal algebra below
   // (its first use was the hottest stall of C1's launch, 14 % of the samples, when it was issued after the goals).
@@ -379,12 +383,14 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
   // :82 clamps idx + 1 to size - 1; with frame stacking (:231) and for ATC (:408) the reference does not clamp, and a
   // row past the table is an IndexError there: here the gather stays inside the table and the error is reported through
   // the deferred index flag when the caller enabled it
-  int32_t nxt = i + p.next_offset;
-  if (nxt >= p.n_rows_ds) {
-    nxt = p.n_rows_ds - 1;
-    if (p.stacked_next && p.idx_error != nullptr) *p.idx_error = 1;
+  if (!kPoint) {   // (the point-maze record carries the next row's observation itself: nothing gathers through SLOT_NEXT)
+    int32_t nxt = i + p.next_offset;
+    if (nxt >= p.n_rows_ds) {
+      nxt = p.n_rows_ds - 1;
+      if (p.stacked_next && p.idx_error != nullptr) *p.idx_error = 1;
+    }
+    put_slot(p, sr, SLOT_NEXT, g, nxt);
   }
-  put_slot(p, sr, SLOT_NEXT, g, nxt);
 
   if (kFlavour != FLAVOUR_PLAIN) {
     uint4 gb = make_uint4(0, 0, 0, 0), amix = make_uint4(0, 0, 0, 0);
@@ -397,17 +403,17 @@ __device__ __forceinline__ void relabel_row(const RelabelParams& p, const SegVie
       fin = __ldg(p.term + tl);
     }
     const double neg = p.gc_negative ? 1.0 : 0.0;
-    const int32_t vg = kInject ? pick_goal_injected<kSmemTables>(p, seg, 0, i, fin, g)                   // :233-239 / :508-514
-                               : pick_goal_philox<kSmemTables>(p, seg, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
-    const int32_t ag = kInject ? pick_goal_injected<kSmemTables>(p, seg, 2, i, fin, g)                   // :240-246 / :585-591
-                               : pick_goal_philox<kSmemTables>(p, seg, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
+    const int32_t vg = kInject ? pick_goal_injected<kSmemTables, kPoint>(p, seg, 0, i, fin, g)           // :233-239 / :508-514
+                               : pick_goal_philox<kSmemTables, kPoint>(p, seg, 0, i, fin, make_uint2(w0.z, w0.w), make_uint2(gb.x, gb.y));
+    const int32_t ag = kInject ? pick_goal_injected<kSmemTables, kPoint>(p, seg, 2, i, fin, g)           // :240-246 / :585-591
+                               : pick_goal_philox<kSmemTables, kPoint>(p, seg, 2, i, fin, make_uint2(amix.x, amix.y), make_uint2(gb.z, gb.w));
     const double succ = (i == vg) ? 1.0 : 0.0;                         // :250-252 / :579-582
     put_f64(p, p.masks, g, 1.0 - succ);
     put_f64(p, p.rewards, g, succ - neg);
     if (kFlavour == FLAVOUR_GC) {
-      put_slot(p, sr, GC_VALUE_GOAL, g, vg);
-      put_slot(p, sr, GC_ACTOR_GOAL, g, ag);
-      if (p.trl) {                                                     // :259-267
+      put_slot<kPoint>(p, sr, GC_VALUE_GOAL, g, vg);
+      put_slot<kPoint>(p, sr, GC_ACTOR_GOAL, g, ag);
+      if (!kPoint && p.trl) {                                                     // :259-267
         const int64_t span = vg > i ? (int64_t)vg - i : 1;             // the reference asserts idxs != value_goal_idxs
         int32_t mid;
         if (kInject) {
