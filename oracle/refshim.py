@@ -5,8 +5,13 @@ The reference hot path lives in ``<reference>/impls/utils/datasets.py``.  That f
 Everything the sampler does with them on the GC/HGC path is: ``jax.tree_util.tree_map`` / ``tree_leaves``
 over plain dicts, ``FrozenDict`` as an immutable mapping, and one jitted crop (datasets.py:17-33).  This
 module registers minimal stand-ins for those three things in ``sys.modules`` *before* executing the reference
-file, and afterwards swaps ``batched_random_crop`` for the numpy restatement in ``oracle.replay_oracle``
-(JAX is absent, so that single function cannot run as written).
+file.  The crop runs AS WRITTEN in the reference (``random_crop`` = ``jnp.pad(mode='edge')`` + ``lax.dynamic_slice``,
+vmapped over the batch): ``jnp.pad`` is ``np.pad`` (same ``mode='edge'`` semantics), ``lax.dynamic_slice`` is a numpy
+slice with XLA's documented start clamping (start = clip(start, 0, dim - size)), ``jax.vmap`` is a Python loop over the
+mapped axis and ``jax.jit`` is the identity -- so the golden vectors' crops come from the reference's own function
+bodies, and the oracle's closed form (``shifted_edge_crop``) is checked against them, not against itself.
+``load_reference_datasets_module(fast_crop=True)`` swaps in the closed form instead (a Python loop per image is slow
+for big batches); the golden generator and the crop tests use the literal path.
 
 Used by ``tests/golden/make_golden.py`` (fixture generation, in the build container only) and by the
 live cross-check tests, which skip when the reference tree is not mounted.  Nothing in the product package
@@ -91,6 +96,28 @@ def _identity_decorator(fn=None, **_kwargs):
     return fn
 
 
+def _vmap(fn, in_axes=0, out_axes=0):
+    """jax.vmap for positional array arguments: apply `fn` per index of the mapped axes, stack the results."""
+    assert out_axes == 0
+
+    def mapped(*args):
+        axes = tuple(in_axes) if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        assert len(axes) == len(args)
+        n = next(np.shape(a)[ax] for a, ax in zip(args, axes) if ax is not None)
+        outs = [fn(*[np.take(np.asarray(a), i, axis=ax) if ax is not None else a for a, ax in zip(args, axes)]) for i in range(n)]
+        return np.stack(outs) if outs else np.zeros((0,) + tuple(np.shape(args[0])[1:]), dtype=np.asarray(args[0]).dtype)
+
+    return mapped
+
+
+def _dynamic_slice(operand, start_indices, slice_sizes):
+    """jax.lax.dynamic_slice: start indices are clamped so that the slice stays inside the operand (XLA DynamicSlice)."""
+    operand = np.asarray(operand)
+    assert len(start_indices) == operand.ndim == len(slice_sizes)
+    starts = [int(np.clip(int(s), 0, d - z)) for s, d, z in zip(start_indices, operand.shape, slice_sizes)]
+    return operand[tuple(slice(s, s + z) for s, z in zip(starts, slice_sizes))]
+
+
 def _install_stubs():
     if 'jax' in sys.modules and not getattr(sys.modules['jax'], '_ogb_stub', False):
         raise RuntimeError('a real jax is importable; refshim is only meant for images without it')
@@ -100,8 +127,9 @@ def _install_stubs():
     jax.tree_util.tree_map = _tree_map
     jax.tree_util.tree_leaves = _tree_leaves
     jax.jit = _identity_decorator
-    jax.vmap = lambda fn, in_axes=None: fn
+    jax.vmap = _vmap
     jax.lax = types.ModuleType('jax.lax')
+    jax.lax.dynamic_slice = _dynamic_slice
     jnp = types.ModuleType('jax.numpy')
     jnp.pad = np.pad
     jax.numpy = jnp
@@ -127,27 +155,33 @@ def _install_stubs():
 _CACHED = None
 
 
-def load_reference_datasets_module():
-    """Execute the reference's datasets.py (unmodified, read from its own location) and return the module."""
+def load_reference_datasets_module(fast_crop: bool = False):
+    """Execute the reference's datasets.py (unmodified, read from its own location) and return the module.
+
+    fast_crop=False: `random_crop` / `batched_random_crop` run as the reference wrote them (datasets.py:17-33) on the
+    numpy stand-ins above.  fast_crop=True: `batched_random_crop` is the oracle's closed form (same results --
+    tests/test_oracle_golden.py checks the two against each other -- without the per-image Python loop)."""
     global _CACHED
-    if _CACHED is not None:
-        return _CACHED
-    if not reference_available():
-        raise FileNotFoundError(f'reference sampler not found at {_REF_FILE}')
-    _install_stubs()
-    spec = importlib.util.spec_from_file_location('ogb_reference_datasets', _REF_FILE)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules['ogb_reference_datasets'] = mod
-    spec.loader.exec_module(mod)
+    if _CACHED is None:
+        if not reference_available():
+            raise FileNotFoundError(f'reference sampler not found at {_REF_FILE}')
+        _install_stubs()
+        spec = importlib.util.spec_from_file_location('ogb_reference_datasets', _REF_FILE)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules['ogb_reference_datasets'] = mod
+        spec.loader.exec_module(mod)
+        mod._literal_batched_random_crop = mod.batched_random_crop
+        _CACHED = mod
+    mod = _CACHED
+    if fast_crop:
+        from oracle.replay_oracle import shifted_edge_crop
 
-    # datasets.py:17-33 needs jnp.pad + lax.dynamic_slice under jit/vmap; substitute the closed form.
-    from oracle.replay_oracle import shifted_edge_crop
+        def batched_random_crop(imgs, crop_froms, padding):
+            return shifted_edge_crop(np.asarray(imgs), np.asarray(crop_froms)[:, :2], padding)
 
-    def batched_random_crop(imgs, crop_froms, padding):
-        return shifted_edge_crop(np.asarray(imgs), np.asarray(crop_froms)[:, :2], padding)
-
-    mod.batched_random_crop = batched_random_crop
-    _CACHED = mod
+        mod.batched_random_crop = batched_random_crop
+    else:
+        mod.batched_random_crop = mod._literal_batched_random_crop
     return mod
 
 

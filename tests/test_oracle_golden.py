@@ -65,3 +65,36 @@ def test_oracle_matches_live_reference(kind, seed):
         np.random.seed(7 * seed + it)
         got = ours.sample(33)
         assert_batches_identical(got, want, label=f'{kind}/{seed}/{it}:')
+
+
+def _pad_and_slice(img, cy, cx, p):
+    """datasets.py:17-27 spelled out with numpy: edge padding, then a slice of the original shape at (cy, cx)."""
+    padded = np.pad(img, ((p, p), (p, p), (0, 0)), mode='edge')
+    h, w, _ = img.shape
+    cy, cx = int(np.clip(cy, 0, padded.shape[0] - h)), int(np.clip(cx, 0, padded.shape[1] - w))    # lax.dynamic_slice clamps
+    return padded[cy:cy + h, cx:cx + w]
+
+
+@pytest.mark.parametrize('shape,dtype', [((8, 8, 3), np.uint8), ((7, 5, 3), np.uint8), ((6, 9, 1), np.float32), ((64, 64, 9), np.uint8)])
+@pytest.mark.parametrize('padding', [1, 3, 4])
+def test_crop_closed_form_equals_pad_and_slice(shape, dtype, padding):
+    """The oracle's closed form of the augmentation (clip(y + cy - p), clip(x + cx - p)) against the literal
+    pad(mode='edge') + slice for EVERY shift the reference can draw (randint(0, 2p + 1), datasets.py:333), and -- when the
+    reference tree is mounted -- against the reference's own random_crop / batched_random_crop bodies executed on the
+    numpy stand-ins of jnp.pad, lax.dynamic_slice and vmap (oracle/refshim.py)."""
+    from oracle.replay_oracle import shifted_edge_crop
+
+    rng = np.random.default_rng(padding * 100 + shape[0])
+    shifts = np.array([(cy, cx) for cy in range(2 * padding + 1) for cx in range(2 * padding + 1)], dtype=np.int64)
+    b = len(shifts)
+    imgs = (rng.integers(0, 256, (b, *shape)).astype(dtype) if np.dtype(dtype) == np.uint8
+            else rng.standard_normal((b, *shape)).astype(dtype))
+    got = shifted_edge_crop(imgs, shifts, padding)
+    want = np.stack([_pad_and_slice(imgs[i], shifts[i, 0], shifts[i, 1], padding) for i in range(b)])
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    if refshim.reference_available():
+        ref = refshim.load_reference_datasets_module()
+        crop_froms = np.concatenate([shifts, np.zeros((b, 1), dtype=np.int64)], axis=1)        # (cy, cx, 0), datasets.py:334
+        theirs = ref.batched_random_crop(imgs, crop_froms, padding)
+        assert ref.batched_random_crop is ref._literal_batched_random_crop
+        assert np.asarray(theirs).dtype == got.dtype and np.array_equal(np.asarray(theirs), got)
