@@ -190,6 +190,25 @@ def run_case(r, oracle_only=False):
             for k in want:
                 assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, f'philox mode, call {call}, key {k}: dtype/shape'
                 assert np.array_equal(got[k][~knife], want[k][~knife]), f'philox mode, call {call}, key {k}'
+        # One case in four (vector observations only): a launch with more 32-row tiles than the gather kernels have warps, so
+        # that tiles are handed out by the ticket counter -- byte-identical to the same launch with statically strided
+        # tiles (debug bit 3), and two of its batches against the oracle.
+        if fields['observations'].ndim == 2 and r.random() < 0.25:
+            K = int(np.ceil(float(r.integers(90_000, 200_000)) / B))
+            static = device_sampler(fields, config, kind, seed=pseed, stream_id=pstream, output=case['output'], dedup=case['dedup'])
+            static.load_state_dict(dev.state_dict())
+            static._sampler.set_debug(8)
+            counter0 = dev.state_dict()['counter']
+            many, many_static = to_host(dev.sample_many(K, B)), to_host(static.sample_many(K, B))
+            assert set(many) == set(many_static)
+            for k in many:
+                assert np.array_equal(many[k], many_static[k]), f'ticket-scheduled launch of {K} x {B} rows differs from static tiles, key {k}'
+            for b in sorted({0, K - 1, int(r.integers(0, K))}):
+                draws, knife = philox_np.philox_draws(pseed, pstream, counter0 + b, B, len(rows), goal_sets_for(config, kind),
+                                                      config['p_aug'] is not None, config['p_aug'] or 0.0)
+                want = oracle.sample(B, source=DrawsSource(draws))
+                for k in want:
+                    assert np.array_equal(many[k][b][~knife], want[k][~knife]), f'big launch, batch {b} of {K}, key {k}'
     except AssertionError as exc:
         raise AssertionError(f'{case["summary"]}\n   {exc}') from exc
     return case
