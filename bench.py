@@ -39,6 +39,7 @@ import numpy as np  # noqa: E402
 METRIC = 'relabeled transitions/sec'
 UNIT = 'transitions/s'
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+NOMINAL_HBM_GBS = 8000.0   # B200 data sheet (quoted next to the measured copy peak)
 HEADLINE = 'c2'
 ALL_CONFIGS = ['c1', 'c2', 'c3', 'c4', 'c5']
 MIN_REGION_MS = 250.0
@@ -491,6 +492,7 @@ def measure_config(key, args, ctx, headline):
                      'traffic_source': traffic_note, 'kernel': kernel_name, 'kernel_ms': kernel_ms,
                      'bytes_per_transition': w.bytes_per_transition, 'bytes_per_launch': w.bytes_per_transition * per_step,
                      'peak_source': peak_src,
+                     'nominal_peak': NOMINAL_HBM_GBS, 'frac_of_nominal': achieved / NOMINAL_HBM_GBS,
                      'step_frac': w.bytes_per_transition * per_step / (elapsed_ms / n_steps * 1e-3) / 1e9 / peak,
                      'note': 'achieved = algorithmic bytes of one launch / device time of the dominant kernel (CUDA events on its '
                              'stream); step_frac = the same bytes / whole step time (index kernel and launch gaps included)'},
