@@ -481,3 +481,29 @@ def test_ticket_scheduled_tiles_equal_static_tiles(kind, obs_dim, K, B):
         for k in x:
             assert not (x[k].view(np.uint8) == 0xA5).all(), k
             assert np.array_equal(x[k], y[k]), (k, rep)
+
+
+@pytest.mark.parametrize('obs_dim,extra_dim', [(16, None), (29, 40), (2, None)])
+def test_plain_dataset_big_launch_equals_numpy_indexing(obs_dim, extra_dim):
+    """Dataset.sample / get_subset (datasets.py:72-83) on a launch with more tiles than warps: the plain flavour of the
+    fused kernel also takes its tiles from the ticket counter (a one-pair launch -- a single record span, 64-byte rows =
+    one item per tile -- resolves its ticket in the very item that asked for it).  Explicit idxs, every field against
+    numpy fancy indexing, twice (the counters a launch leaves behind are reused)."""
+    from ogbench_b200 import Dataset
+
+    rng = np.random.default_rng(obs_dim)
+    n = 50_000
+    fields = dict(observations=rng.standard_normal((n, obs_dim)).astype(np.float32),
+                  actions=rng.standard_normal((n, 3)).astype(np.float32),
+                  terminals=(rng.random(n) < 0.01).astype(np.float32), rewards=rng.standard_normal(n).astype(np.float32))
+    fields['terminals'][-1] = 1.0
+    if extra_dim:
+        fields['qpos'] = rng.standard_normal((n, extra_dim)).astype(np.float32)
+    ds = Dataset.create(**fields)
+    for rep in range(2):
+        idxs = rng.integers(0, n, size=301_117)
+        got = to_host(ds.sample(len(idxs), idxs=idxs))
+        assert set(got) == set(fields) | {'next_observations'}
+        for k, v in fields.items():
+            assert np.array_equal(got[k], v[idxs]), (k, rep)
+        assert np.array_equal(got['next_observations'], fields['observations'][np.minimum(idxs + 1, n - 1)]), rep
