@@ -284,13 +284,16 @@ def link_probe(torch, device, nbytes, reps=8):
     for _ in range(2):
         dst.copy_(src, non_blocking=True)
     torch.cuda.synchronize(device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(reps):
-        dst.copy_(src, non_blocking=True)
-    ev1.record()
-    torch.cuda.synchronize(device)
-    return reps * nbytes / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    best = 0.0
+    for _ in range(2):      # the faster of two passes, like the e2e leg it is compared with
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize(device)
+        best = max(best, reps * nbytes / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+    return best
 
 
 def measure_config(key, args, ctx, headline):
@@ -453,12 +456,16 @@ def measure_config(key, args, ctx, headline):
             barrier()
             for _ in range(depth + 2):
                 next(batches)
-            t0 = time.perf_counter()
-            for _ in range(steps_e):
-                out = next(batches)
-                del out
-            dt = time.perf_counter() - t0
-        dt = dist_util.reduce_scalar(dt, 'max', device=dev)
+            # two passes of steps_e steps each, the faster one is reported (both are in `passes`): the hosts of this pool are
+            # shared VMs whose PCIe rate dips for seconds at a time (the raw probe below sees the same dips)
+            pass_dt = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                for _ in range(steps_e):
+                    out = next(batches)
+                    del out
+                pass_dt.append(dist_util.reduce_scalar(time.perf_counter() - t0, 'max', device=dev))
+        dt = min(pass_dt)
         barrier()
         link = link_probe(torch, torch.device('cuda', local), int(d2h))      # every rank copies at the same time, like the e2e leg
         link_min = -dist_util.reduce_scalar(-link, 'max', device=dev)
@@ -467,6 +474,7 @@ def measure_config(key, args, ctx, headline):
         e2e = {'value': e2e_value, 'unit': UNIT, 'numa_bound': ctx['numa'] is not None, 'h2d_bytes_per_step': rows * 8,
                'd2h_bytes_per_step': int(d2h), 'steps': steps_e, 'batches_per_step': Le,
                'direct_call_value': world * steps_e * rows / dt_direct,
+               'passes': [world * steps_e * rows / t for t in pass_dt],
                'link_gbs': link_sum, 'link_gbs_slowest_rank': link_min,
                'frac_of_link': e2e_value * (d2h / rows) / 1e9 / link_sum,
                'link_note': 'raw pinned cudaMemcpyAsync D2H of one e2e block per rank, all ranks copying at once, summed over ranks',
