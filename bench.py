@@ -18,7 +18,11 @@ under `configs` (c1..c5, each with value / roofline / e2e / cpu_baseline), C5 as
 memory every step, the whole batch copied back into pinned host memory, both inside the timed region), next to the
 raw pinned D2H copy rate of the same box measured in the same run (`link_gbs`);
 `roofline` = algorithmic bytes / average launch duration of the dominant kernel vs the measured
-HBM copy bandwidth; `cpu_baseline` = the numpy oracle port timed on this box's host cores in the same run.
+HBM copy bandwidth (and vs the 8 TB/s data-sheet figure, `frac_of_nominal`); `cpu_baseline` = the numpy oracle port
+timed on this box's host cores in the same run.  A launch costs 8-19 us beyond its bytes, so the default launch is sized
+to last about a millisecond (`default_batches_per_launch`) and every config also carries `launch_size_sweep`: the same
+measurement at a quarter and a sixteenth of that size.  `e2e.value` and `e2e.link_gbs` are each the faster of two passes
+(`e2e.passes`): the hosts of this pool are shared and their PCIe rate dips for seconds at a time.
 """
 
 from __future__ import annotations
