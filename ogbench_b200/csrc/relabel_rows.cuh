@@ -175,7 +175,7 @@ struct RelabelParams {
   int32_t n_tiny;              // the first n_tiny_fast of them have rows of 4, 8 or 16 bytes
   int32_t n_tiny_fast;
   int32_t write_vecs;          // 0: no later kernel needs the index vectors (everything was tiny) and debug is off
-  int32_t wide_record;         // kPoint: fetch the 32-byte record with one 256-bit load (measurement switch OGB_WIDE_RECORD)
+  int32_t wide_record;         // kPoint: fetch the 32-byte record with one 256-bit load (default; OGB_NO_WIDE_RECORD: two 128-bit loads)
   TinyJob tiny[kMaxTinyJobs];
   int32_t n_tiny_groups;
   int32_t n_tiny_fields;
@@ -945,9 +945,10 @@ __device__ __forceinline__ void gather_rows_async_body(const AsyncGatherParams& 
   // Tile scheduling.  Every warp starts on the tile of its global index; after that it either strides by the number of
   // warps (static) or -- p.sched != nullptr -- takes the next unclaimed tile from a global ticket counter.  The SMs do not
   // run at one speed (a DRAM-bound launch shares HBM unevenly), so with static tiles the slowest SM sets the launch time;
-  // with tickets every warp is busy until the tiles run out (C2/C5: the fixed 8-19 us per launch of profiles/
-  // r2_launch_size.txt).  The ticket is asked for at item `claim_item`, one (tile, job) pair before the head needs it, so
-  // the atomic's round trip hides behind a pair's issue loop.  The tail cursor drains the same tile sequence a few items
+  // with tickets every warp is busy until the tiles run out (profiles/r2_ab_shapes.txt, batches r2i-r2k: C5 0.85 -> 0.91
+  // of the HBM peak at equal launch size).  The ticket is asked for at item `claim_item`, which the host places one to
+  // three (tile, job) pairs before the item where the head needs the tile, so that the atomic's round trip hides behind
+  // those pairs' issue loops.  The tail cursor drains the same tile sequence a few items
   // later: the warp keeps its claimed tiles in a four-entry FIFO in shared memory (the head is at most kStages - 1 tile
   // boundaries ahead of the tail, plus the tile it has resolved but not entered).
   const bool dyn = kMode != MODE_QUEUE && p.sched != nullptr;
