@@ -341,11 +341,13 @@ def measure_config(key, args, ctx, headline):
     launches = 0
     dominant_ms = []
     dominant_name = C.c_char_p()
+    dominant_seen = ['']    # the name is owned by the batch: copied while the handle is alive
 
     def harvest(handle, keep):
         # device time of the launch's dominant kernel, from the events the library recorded on its own streams
         ms = C.c_float()
         _native.check(lib.ogb_batch_dominant_kernel(handle.ptr, C.byref(dominant_name), C.byref(ms)))
+        dominant_seen[0] = (dominant_name.value or b'').decode()
         if keep and ms.value >= 0:
             dominant_ms.append(ms.value)
 
@@ -390,7 +392,7 @@ def measure_config(key, args, ctx, headline):
     clocks.stop_flag.set()
     clocks.join()
     kernel_ms = float(np.mean(dominant_ms)) if dominant_ms else elapsed_ms / n_steps
-    kernel_name = (dominant_name.value or b'').decode()
+    kernel_name = dominant_seen[0]
     elapsed_ms = dist_util.reduce_scalar(elapsed_ms, 'max', device=dev)   # slowest rank
     per_step = w.batch * L
     value = dist_util.reduce_scalar(n_steps * per_step, 'sum', device=dev) / (elapsed_ms * 1e-3)

@@ -196,8 +196,10 @@ int ogb_batch_keep_leading_axis(ogb_batch* b, int32_t on);        /* shapes keep
 int ogb_batch_nbytes(const ogb_batch* b, size_t* out);            /* size of the single device block */
 int ogb_batch_device_block(const ogb_batch* b, void** out);       /* its base: key i lives at base + ogb_key_info.offset */
 int ogb_batch_launches(const ogb_batch* b, int32_t* out);         /* kernels launched to produce it */
-int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms); /* the kernel that moved the batch's bytes and, in
-                                                                     profile mode, its device time (host-waits for it); else -1 */
+int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms); /* the kernel that moved the batch's bytes, named with its
+                                                                     template arguments as ncu prints them (the string lives
+                                                                     as long as the batch), and, in profile mode, its device
+                                                                     time (host-waits for it); else -1 */
 int ogb_batch_sync(ogb_batch* b);                                 /* host-wait for the batch to be ready */
 int ogb_batch_wait_on_stream(ogb_batch* b, void* consumer_stream);/* make a consumer stream wait (DLPack protocol) */
 int ogb_batch_copy_to_host(ogb_batch* b, void* dst, size_t nbytes);  /* whole block, D2H, synchronous at return (= begin + end) */

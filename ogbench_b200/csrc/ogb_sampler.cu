@@ -456,7 +456,9 @@ struct ogb_batch {
   std::vector<cudaEvent_t> chunk_done;                     // ... are complete once chunk_done[c] has fired
   int32_t* idx_error = nullptr;                            // device flag of the deferred index check (inside the block)
   cudaEvent_t prof_begin = nullptr, prof_end = nullptr;   // profile mode: brackets of the dominant kernel
-  const char* dominant = "";                               // its name
+  const char* dominant = "";                               // its name ...
+  std::string dominant_full;                               // ... with the template arguments ncu prints, e.g. "relabel_gather_kernel<0, 0, 2, 20>"
+  std::string name_fused, name_async, name_frames, name_index;   // (as chosen by the launches of this batch)
   cudaEvent_t ready = nullptr;
   cudaEvent_t copied = nullptr;                            // ogb_batch_copy_to_host_begin: the D2H copy of the block has finished
   volatile int32_t* h_idx_flag = nullptr;                  // ... and where the deferred index flag lands (pinned, sampler-owned)
@@ -1329,6 +1331,13 @@ struct RunSpec {
   int crop_padding = -1;                 // >= 0: crop every image key with the injected shifts and this padding (augment())
 };
 
+std::string kernel_name(const char* base, std::initializer_list<int> args) {
+  std::string out = std::string(base) + "<";
+  bool first = true;
+  for (int a : args) { out += (first ? "" : ", ") + std::to_string(a); first = false; }
+  return out + ">";
+}
+
 // OGB_HOST_PHASES=1 (measurement switch): host time of run_sample by phase, summed over all calls, printed at exit.
 struct HostPhases {
   static constexpr int kN = 7;
@@ -1827,6 +1836,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       // 48 registers, five CTAs per SM: 0.556 vs 0.541 of peak with four (six spill: 0.541), profiles/r2_ab_shapes.txt
       fn = inject ? (const void*)relabel_index_kernel<true, FLAVOUR_GC, false, true> : (const void*)relabel_index_kernel<false, FLAVOUR_GC, false, true, 5>;
     if (point_record && smem_tables && !inject) fn = (const void*)relabel_index_kernel<false, FLAVOUR_GC, true, true, 5>;
+    b->name_index = kernel_name("relabel_index_kernel", {inject ? 1 : 0, flavour, smem_tables ? 1 : 0, point_record && !(smem_tables && inject) ? 1 : 0,
+                                                        point_record && !inject ? 5 : 4});
     p.wide_record = ab().no_wide_record ? 0 : 1;   // +1.2 % on C1 at 16M rows per launch (0.740 vs 0.731, batch r2l)
     // Grid cap: a whole number of waves of resident CTAs (a 16-per-SM grid of the five-per-SM point-maze kernel is 3.2
     // waves, and the last, fifth-full wave cost C1 5 %: 0.731 vs 0.771-0.775 of peak for 5, 10 or 32 per SM, batch r2l).
@@ -2009,6 +2020,8 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
       const size_t ws_smem = smem + (size_t)kAsyncWarps * ((size_t)kQueueDepth * n_slots_fl * 128 + 16 * kQueueDepth);
       const bool ws = (ws_env >= 0 ? ws_env != 0 : s->prefer_ws) && ws_smem <= 113 * 1024 && shape == 308;
       fused_name = ws ? "relabel_gather_ws_kernel" : "relabel_gather_kernel";
+      b->name_fused = ws ? kernel_name("relabel_gather_ws_kernel", {inject ? 1 : 0, flavour})
+                         : kernel_name("relabel_gather_kernel", {inject ? 1 : 0, flavour, n_stages, n_warps});
       fused_launch = [=](int64_t begin, int64_t end, cudaStream_t st) -> int {
         FusedParams& f = *keep;
         f.relabel.row_begin = f.gather.row_begin = begin;
@@ -2050,6 +2063,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
                           : shape == 310 ? (const void*)gather_rows_async_kernel<3, 10>
                                          : (const void*)gather_rows_async_kernel<kAsyncStages, kAsyncWarps>;
     OGB_CUDA(cudaFuncSetAttribute(gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (b->name_async.empty()) b->name_async = kernel_name("gather_rows_async_kernel", {n_stages, n_warps});
     int resident = 0;   // CTAs of this kernel that fit one SM (registers and shared memory): the persistent grid is exactly that
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, gather_fn, n_warps * 32, smem) != cudaSuccess || resident < 1)
       return bail(fail(OGB_ERR_CUDA, "gather_rows_async_kernel: occupancy query failed (%zu bytes of shared memory)", smem));
@@ -2167,6 +2181,7 @@ int run_sample(ogb_sampler* s, const RunSpec& spec, int64_t batch_size, int32_t 
         if (rc) return bail(rc);
         const size_t smem = 2 * (size_t)ka.fs * rb * fp.W * 3;
         const int fs = ka.fs;
+        if (b->name_frames.empty()) b->name_frames = kernel_name("gather_frames_tma_kernel", {fs >= 1 && fs <= 3 ? fs : 4});
         gather_launches.push_back([=](int64_t begin, int64_t end, cudaStream_t st) mutable -> int {
           fp.row_begin = begin;
           fp.row_end = end;
@@ -2617,7 +2632,14 @@ int ogb_batch_launches(const ogb_batch* b, int32_t* out) try {
 } OGB_CATCH_ALL
 int ogb_batch_dominant_kernel(ogb_batch* b, const char** name, float* ms) try {
   if (!b || !name || !ms) return fail(OGB_ERR_INVALID, "null argument");
-  *name = b->dominant;
+  {
+    const std::string d = b->dominant;
+    const std::string& full = d == "gather_frames_tma_kernel" ? b->name_frames
+                            : (d == "relabel_gather_kernel" || d == "relabel_gather_ws_kernel") ? b->name_fused
+                            : d == "gather_rows_async_kernel" ? b->name_async : d == "relabel_index_kernel" ? b->name_index : d;
+    b->dominant_full = full.empty() ? d : full;
+  }
+  *name = b->dominant_full.c_str();
   *ms = -1.0f;
   if (b->prof_begin && b->prof_end) {
     OGB_CUDA(cudaEventSynchronize(b->prof_end));

@@ -36,7 +36,7 @@ def test_bench_gpu_arm_prints_the_contract_line():
     assert set(line['clocks']) >= {'sm_mhz', 'sm_max_mhz', 'reasons'}
     # the timed region is stretched to >= 250 ms by repeating the K-step loop, and says so
     assert line['repeats'] >= 1 and line['timed_region_ms'] >= 200 and line['steps_timed'] == line['steps'] * line['repeats']
-    assert line['clocks']['samples'] >= 20
+    assert line['clocks']['samples'] >= 5       # (~125 on most boxes: one NVML poll per 2 ms; some boxes answer NVML in ~20 ms)
     assert 0 < e2e['frac_of_link'] < 1.25 and e2e['link_gbs'] > 1   # (back-to-back copies can edge past the probe's serial copies)
     # every BASELINE.json config rides in the same line
     assert set(line['configs']) == {'c1', 'c2', 'c3', 'c4', 'c5'}
