@@ -98,9 +98,9 @@ def config_dict(key, L):
         'workload': w.name, 'key': w.key, 'rows_resident_per_gpu': w.rows, 'batch': w.batch, 'batches_per_launch': L,
         'transitions_per_step_per_gpu': w.batch * L,
         'placement': 'trajectory-aligned shard per GPU' if key.startswith('c5') else 'replica per GPU',
-        'l2': 'no explicit flush: outputs rotate through three blocks of one launch each (together larger than the 126 MB L2 for '
-              'every config, each block larger than L2 except c1), inputs are random rows of the resident dataset (per-config sizes '
-              'in notes; c1 and c2 are at or below L2 size, as the real datasets of these shapes are)',
+        'l2': 'no explicit flush: outputs rotate through three blocks of one launch each (every block is 1-4 GB, many times the '
+              '126 MB L2), inputs are random rows of the resident dataset (per-config sizes in notes; the c1 dataset (32 MB) fits L2 '
+              'and c2 (256 MB) partly, as the real datasets of these shapes do)',
     }
 
 
